@@ -1,0 +1,54 @@
+"""Golden-case definitions shared by oracle/gen_golden.py and the tests (test infrastructure)."""
+import torch
+
+MINI = dict(depths=[1, 1, 2, 1], channels=[32, 64, 96, 128])
+MINI2 = dict(depths=[2, 2, 3, 2], channels=[32, 64, 128, 256])
+
+# name -> (constructor kwargs, image spec, mode)
+CASES = {
+    # BASELINE config 1: ConvNeXt-T, no MoE, 1x3x256x256, eval forward
+    'tiny_dense_256': dict(kw=dict(arch='tiny'), img=(1, 256, 256), mode='eval', weights='trained', stride=4),
+    'tiny_dense_256_init': dict(kw=dict(arch='tiny'), img=(1, 256, 256), mode='eval', weights='init', stride=4),
+    'mini_dense': dict(kw=dict(arch=MINI), img=(2, 64, 64), mode='eval', weights='trained', stride=1),
+    'mini_moe_e4k2_eval': dict(kw=dict(arch=MINI, MoE_Block_inds=[[], [0], [0, 1], [0]], num_experts=4, top_k=2),
+                               img=(2, 64, 96), mode='eval', weights='trained', stride=1),
+    'mini_moe_e8k3_eval': dict(kw=dict(arch=MINI, MoE_Block_inds=[[0], [0], [1], [0]], num_experts=8, top_k=3),
+                               img=(3, 64, 64), mode='eval', weights='trained', stride=1),
+    'mini_moe_e6k1_eval': dict(kw=dict(arch=MINI, MoE_Block_inds=[[], [], [0, 1], []], num_experts=6, top_k=1),
+                               img=(2, 96, 64), mode='eval', weights='trained', stride=1),
+    'mini_moe_e2k2_eval': dict(kw=dict(arch=MINI, MoE_Block_inds=[[], [], [0], [0]], num_experts=2, top_k=2),
+                               img=(2, 64, 64), mode='eval', weights='trained', stride=1),
+    'mini_moe_e4k2_train_clean': dict(kw=dict(arch=MINI, MoE_Block_inds=[[], [0], [0, 1], [0]], num_experts=4, top_k=2,
+                                              noisy_gating=False),
+                                      img=(2, 64, 64), mode='train', weights='trained', stride=1),
+    'mini_moe_e4k2_train_noisy': dict(kw=dict(arch=MINI, MoE_Block_inds=[[], [0], [0, 1], [0]], num_experts=4, top_k=2),
+                                      img=(2, 64, 64), mode='train_noisy', weights='trained', stride=1),
+    'mini2_moe_e8k2_train_clean': dict(kw=dict(arch=MINI2, MoE_Block_inds=[[], [], [0, 2], [0]], num_experts=8, top_k=2,
+                                               noisy_gating=False),
+                                       img=(2, 128, 128), mode='train', weights='trained', stride=2),
+}
+
+
+def upstream_grads(outs, seed=99):
+    """Seeded upstream gradients for the 4 outputs: randn / sqrt(numel)."""
+    gs = []
+    for i, o in enumerate(outs):
+        g = torch.Generator().manual_seed(seed + i)
+        gs.append(torch.randn(o.shape, generator=g) / (o.numel() ** 0.5))
+    return gs
+
+
+def make_noise(cfg, n_tokens_per_layer, seed=7):
+    out = []
+    for i, t in enumerate(n_tokens_per_layer):
+        g = torch.Generator().manual_seed(seed + i)
+        out.append(torch.randn(t, cfg.num_experts, generator=g))
+    return out
+
+
+def summarize_grad(g: torch.Tensor):
+    g = g.detach().float().reshape(-1)
+    if g.numel() <= 4096:
+        return dict(full=g.clone())
+    idx = torch.linspace(0, g.numel() - 1, 256).long()
+    return dict(sample=g[idx].clone(), idx=idx, l2=g.double().norm().item(), s=g.double().sum().item())

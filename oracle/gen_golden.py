@@ -1,0 +1,106 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (via oracle/ref_shim.py).
+
+Run in the build container only (needs /root/reference):  python -m oracle.gen_golden
+Every case also asserts that the restated oracle reproduces the reference bit-for-bit on CPU
+(forward outputs, gate loss, routing decisions, parameter gradients) -- this is what pins the
+oracle.  Fixtures hold no weights: those are regenerated from seeds by sm3det_b200.synth.
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_shim                                   # noqa: E402
+from oracle.cases import CASES, make_noise, summarize_grad, upstream_grads   # noqa: E402
+from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes  # noqa: E402
+from sm3det_b200.synth import make_images, make_state_dict, state_dict_checksum    # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def moe_token_counts(cfg, n, h, w):
+    counts = []
+    for i in range(4):
+        t = n * (h // (4 * 2 ** i)) * (w // (4 * 2 ** i))
+        counts += [t] * len(cfg.moe_blocks(i))
+    return counts
+
+
+def run_case(name, spec):
+    kw = dict(spec['kw'])
+    cfg = OracleConfig(**kw)
+    net = ref_shim.build_reference_backbone('ConvNeXt_moe_MultiInput', seed=0, **kw)
+    shapes = param_shapes(cfg)
+    rsd = net.state_dict()
+    assert set(shapes) == set(rsd), set(shapes) ^ set(rsd)
+    for k, s in shapes.items():
+        assert tuple(rsd[k].shape) == tuple(s), k
+    sd = make_state_dict(shapes, seed=0, trained_like=(spec['weights'] == 'trained'))
+    net.load_state_dict(sd, strict=True)
+    n, h, w = spec['img']
+    x = make_images(n, h, w, seed=1234)
+    mode = spec['mode']
+    gold = dict(name=name, kw=kw, img=spec['img'], mode=mode, weights=spec['weights'],
+                sd_checksum=state_dict_checksum(sd), x_checksum=float(x.double().abs().sum()))
+    record = []
+    st = spec['stride']
+    if mode == 'eval':
+        net.eval()
+        with torch.no_grad():
+            ref = net(x)
+            orc = backbone_forward(sd, cfg, x, train=False, record=record)
+    else:
+        net.train()
+        noise = None
+        if mode == 'train_noisy':
+            noise = make_noise(cfg, moe_token_counts(cfg, n, h, w))
+            it = iter(noise)
+            orig = torch.randn_like
+            torch.randn_like = lambda t, *a, **k: next(it).to(t.dtype)   # inject the noise stream
+        try:
+            ref = net(x)
+        finally:
+            if mode == 'train_noisy':
+                torch.randn_like = orig
+        sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'ffn.mean' not in k and 'ffn.std' not in k else v)
+               for k, v in sd.items()}
+        orc = backbone_forward(sdg, cfg, x, train=True, noise=noise, record=record)
+    has_loss = isinstance(ref, tuple) and len(ref) == 2 and isinstance(ref[0], tuple)
+    r_outs, r_loss = (ref if has_loss else (ref, None))
+    o_outs, o_loss = (orc if has_loss else (orc, None))
+    for a, b in zip(r_outs, o_outs):
+        assert torch.equal(a, b), f'{name}: oracle output differs from reference by {(a - b).abs().max()}'
+    if has_loss:
+        assert torch.equal(r_loss, o_loss), (r_loss, o_loss)
+        gold['gate_loss'] = r_loss.detach().clone()
+    gold['outs'] = [o.detach()[:, :, ::st, ::st].clone() for o in r_outs]
+    gold['out_l2'] = [o.detach().double().norm().item() for o in r_outs]
+    gold['stride'] = st
+    gold['moe'] = [dict(prefix=r['prefix'], top_idx=r['top_idx'].to(torch.int16), top_gates=r['top_gates'],
+                        importance=r['importance'], load=r['load'], loss=r['loss']) for r in record]
+    if mode != 'eval':
+        ups = upstream_grads(r_outs)
+        (sum((o * g).sum() for o, g in zip(r_outs, ups)) + (r_loss if has_loss else 0.0)).backward()
+        (sum((o * g).sum() for o, g in zip(o_outs, ups)) + (o_loss if has_loss else 0.0)).backward()
+        grads = {}
+        for pname, p in net.named_parameters():
+            og = sdg[pname].grad
+            if p.grad is None:
+                assert og is None or float(og.abs().max()) == 0.0, pname
+                continue
+            assert og is not None, pname
+            assert torch.equal(p.grad, og), f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
+            grads[pname] = summarize_grad(p.grad)
+        gold['grads'] = grads
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + '.pt')
+    torch.save(gold, path)
+    print(f'{name}: ok, {os.path.getsize(path) / 1024:.0f} KiB, moe layers {len(record)}')
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(8)
+    names = sys.argv[1:] or list(CASES)
+    for nm in names:
+        run_case(nm, CASES[nm])

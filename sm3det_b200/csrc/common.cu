@@ -1,0 +1,42 @@
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+namespace sm3 {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+const char* last_error() { return g_last_error; }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return SM3_ERR_CUDA;
+  }
+  return SM3_OK;
+}
+
+int num_sms() {
+  static int cached[64];
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::call_once(once[dev], [dev]() {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  });
+  return cached[dev];
+}
+
+}  // namespace sm3

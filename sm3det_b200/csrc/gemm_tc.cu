@@ -1,0 +1,75 @@
+// Host launcher for the split-bf16 tcgen05 GEMM (see gemm_tc.cuh).
+#define SM3_GEMM_KERNEL_IMPL
+#include "gemm_tc.cuh"
+#include <mutex>
+
+namespace sm3 {
+const char* last_error();
+namespace gemm {
+
+int pick_bn(int N) {
+  static const int cand[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  for (int bn : cand)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch(Params p, cudaStream_t stream) {
+  SM3_REQUIRE(p.A && p.B && p.D, SM3_ERR_INVALID_ARG, "gemm: null operand");
+  SM3_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0, SM3_ERR_INVALID_ARG, "gemm: bad shape %d %d %d", p.M, p.N, p.K);
+  SM3_REQUIRE((p.a_smn == 1) != (p.a_sk == 1) || (p.a_smn == 1 && p.M == 1), SM3_ERR_INVALID_ARG,
+              "gemm: A needs exactly one unit stride");
+  SM3_REQUIRE((p.b_smn == 1) != (p.b_sk == 1), SM3_ERR_INVALID_ARG, "gemm: B needs exactly one unit stride");
+  const bool a_mn = (p.a_smn == 1 && p.a_sk != 1), b_mn = (p.b_smn == 1 && p.b_sk != 1);
+  if (p.BN == 0) p.BN = pick_bn(p.N);
+  SM3_REQUIRE(p.BN >= 32 && p.BN <= MAX_BN && p.BN % 32 == 0 && p.N % p.BN == 0, SM3_ERR_UNSUPPORTED_SHAPE,
+              "gemm: N=%d has no tile width (multiple of 32 <= 256 dividing N)", p.N);
+  SM3_REQUIRE(aligned16(p.A) && aligned16(p.B) && aligned16(p.D), SM3_ERR_INVALID_ARG, "gemm: pointers must be 16B aligned");
+  if (!a_mn) SM3_REQUIRE(p.a_smn % 4 == 0 && p.K % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: K-major A needs K%%4==0, lda%%4==0");
+  else       SM3_REQUIRE(p.a_sk % 4 == 0 && p.M % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major A needs M%%4==0, lda%%4==0");
+  if (!b_mn) SM3_REQUIRE(p.b_smn % 4 == 0 && p.K % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: K-major B needs K%%4==0, ldb%%4==0");
+  else       SM3_REQUIRE(p.b_sk % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major B needs ldb%%4==0");
+  SM3_REQUIRE(!(p.a_row_index && a_mn), SM3_ERR_INVALID_ARG, "gemm: row gather needs K-major A");
+  SM3_REQUIRE(p.ldd % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: ldd%%4");
+  if (p.epi & (EPI_GELU)) SM3_REQUIRE(!p.aux_out || (aligned16(p.aux_out) && p.ld_aux % 4 == 0), SM3_ERR_INVALID_ARG, "gemm: aux_out");
+  if (p.epi & EPI_DGELU) SM3_REQUIRE(p.aux_in && aligned16(p.aux_in) && p.ld_aux % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: aux_in");
+  if (p.epi & EPI_BIAS) SM3_REQUIRE(p.bias && aligned16(p.bias) && p.bias_group_stride % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: bias");
+  if (p.epi & EPI_COLSCALE) SM3_REQUIRE(p.col_scale && aligned16(p.col_scale), SM3_ERR_INVALID_ARG, "gemm: col_scale");
+  if (p.epi & EPI_ROWSCALE) SM3_REQUIRE(p.row_scale, SM3_ERR_INVALID_ARG, "gemm: row_scale");
+  if (p.epi & EPI_RESID) SM3_REQUIRE(p.resid && aligned16(p.resid) && p.ld_resid % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: resid");
+
+  p.n_tiles = p.N / p.BN;
+  p.m_tiles = (p.M + BM - 1) / BM;
+  if (p.sched == SCHED_DENSE) {
+    p.k_splits = 1; p.num_groups = 1;
+    p.num_tiles = p.m_tiles * p.n_tiles;
+  } else if (p.sched == SCHED_GROUPED) {
+    SM3_REQUIRE(p.tile_group && p.num_m_tiles_dev, SM3_ERR_INVALID_ARG, "gemm: grouped schedule needs tile map");
+    p.k_splits = 1;
+    p.num_tiles = p.m_tiles * p.n_tiles;  // upper bound; the device scalar decides
+  } else if (p.sched == SCHED_SPLITK) {
+    SM3_REQUIRE(p.k_splits >= 1 && p.num_groups >= 1, SM3_ERR_INVALID_ARG, "gemm: split-K needs k_splits/num_groups");
+    SM3_REQUIRE((p.epi & EPI_ATOMIC) || p.k_splits == 1, SM3_ERR_INVALID_ARG, "gemm: split-K>1 needs EPI_ATOMIC");
+    p.num_tiles = p.num_groups * p.m_tiles * p.n_tiles * p.k_splits;
+  } else {
+    SM3_REQUIRE(false, SM3_ERR_INVALID_ARG, "gemm: bad schedule %d", p.sched);
+  }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  });
+  // per-device attribute: set again cheaply if another device is current (idempotent)
+  if (attr_err != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return SM3_ERR_CUDA; }
+  cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  int grid = num_sms();
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  if (grid < 1) grid = 1;
+  gemm_bf16x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  return check_launch("gemm_bf16x3_kernel");
+}
+
+}  // namespace gemm
+}  // namespace sm3

@@ -1,0 +1,547 @@
+// Split-bf16 ("bf16x3") tensor-core GEMM for sm_100a: D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ).
+//
+// fp32 operands live in HBM.  Producer warps load them (coalesced float4, optional row gather),
+// split every value into bf16 hi + bf16 lo (a = hi + lo, |a-(hi+lo)| <= 2^-17 |a|), and store both
+// planes straight into the UMMA canonical shared-memory layouts (K-major SWIZZLE_64B or MN-major
+// SWIZZLE_128B).  One elected thread issues tcgen05.mma.kind::f16 three times per k-step
+// (hi*hi + hi*lo + lo*hi) into an fp32 accumulator in TMEM, so the product error is ~1e-5 relative
+// (vs 5e-4 for single-pass TF32) at 3 bf16 MMAs per logical MAC.  Epilogue warps read the
+// accumulator with tcgen05.ld and apply the fused epilogue (bias / GELU / GELU' / layer-scale /
+// gate / residual / atomic split-K).
+//
+// Replaces, on the reference hot path (convnext_moe.py): nn.Linear pointwise_conv1/2 + GELU
+// (:389-404), the per-expert Python loop (:244) incl. the gather x[_batch_index] (:265), and the
+// 2x2/s2 downsample convs (:549-558); and autograd's dgrad/wgrad GEMMs for all of them.
+#pragma once
+#include "common.cuh"
+
+namespace sm3 {
+namespace gemm {
+
+constexpr int BM = 128;          // UMMA M (rows of D per tile)
+constexpr int BK = 32;           // bf16 elements per k-block (2 UMMA k-steps of 16)
+constexpr int MAX_BN = 256;
+constexpr int STAGES = 4;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int MMA_WARP = 4;
+constexpr int NUM_PROD_WARPS = 8;
+constexpr int FIRST_PROD_WARP = 5;
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;  // 416
+constexpr int MAX_UNITS = 6;     // producer units per warp per k-block ((128+256)/8/8)
+
+constexpr uint32_t OFF_A_HI = 0;
+constexpr uint32_t OFF_A_LO = 8192;
+constexpr uint32_t OFF_B_HI = 16384;
+constexpr uint32_t OFF_B_LO = 32768;
+constexpr uint32_t STAGE_BYTES = 49152;
+constexpr uint32_t BAR_BYTES = 128;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+constexpr uint32_t TMEM_COLS = 512;  // two 256-column fp32 accumulators
+
+enum Sched : int { SCHED_DENSE = 0, SCHED_GROUPED = 1, SCHED_SPLITK = 2 };
+
+enum Epi : int {
+  EPI_BIAS = 1,       // acc += bias[n]
+  EPI_GELU = 2,       // (aux_out[m,n] = acc if aux_out) ; acc = gelu(acc)
+  EPI_DGELU = 4,      // acc *= gelu'(aux_in[m,n])
+  EPI_COLSCALE = 8,   // acc *= col_scale[n]
+  EPI_ROWSCALE = 16,  // acc *= row_scale[m]
+  EPI_RESID = 32,     // acc += resid[m,n]
+  EPI_ATOMIC = 64,    // atomicAdd(D, acc) instead of store
+};
+
+struct Params {
+  // operands: element (mn,k) at ptr + mn*s_mn + k*s_k ; exactly one stride must be 1
+  const float* A; long long a_smn, a_sk;
+  const float* B; long long b_smn, b_sk; long long b_group_stride;
+  const int* a_row_index;   // optional gather of A rows (K-major A only); -1 -> zero row
+  int M, N, K, BN;
+  // schedule
+  int sched;
+  int num_tiles;            // DENSE / SPLITK: total tiles; GROUPED: upper bound (unused)
+  int m_tiles, n_tiles, k_splits, num_groups;
+  const int* tile_group;        // GROUPED: group id per m tile
+  const int* num_m_tiles_dev;   // GROUPED: device scalar
+  const int* seg_begin;         // SPLITK: per-group reduction range (device) or null => [0,K)
+  const int* seg_end;
+  // epilogue
+  float* D; long long ldd; long long d_group_stride;
+  const float* bias; long long bias_group_stride;
+  int epi;
+  float* aux_out; const float* aux_in; long long ld_aux;
+  const float* col_scale; const float* row_scale;
+  const float* resid; long long ld_resid;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Canonical-layout offset functions (host+device so the CPU tests can check the mapping).
+// K-major, SWIZZLE_64B: rows of 32 bf16 (64 B); atom = 8 rows (512 B); chunk = 8 bf16 (16 B).
+__host__ __device__ inline uint32_t kmajor_sw64_offset(uint32_t row, uint32_t chunk) {
+  return (row >> 3) * 512u + (row & 7u) * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
+}
+// MN-major, SWIZZLE_128B: atom = 8 k-rows x 64 mn-elements (1024 B); atoms ordered (mn_group*4 + k_group).
+__host__ __device__ inline uint32_t mnmajor_sw128_offset(uint32_t k, uint32_t mn_chunk /* mn/8 */) {
+  const uint32_t g = mn_chunk >> 3, cc = mn_chunk & 7u;
+  return (g * 4u + (k >> 3)) * 1024u + (k & 7u) * 128u + ((cc ^ (k & 7u)) << 4);
+}
+constexpr uint32_t MN_LBO_BYTES = 4096;  // stride between 64-element mn groups
+constexpr uint32_t MN_SBO_BYTES = 1024;  // stride between 8-row k groups
+constexpr uint32_t K_SBO_BYTES = 512;    // stride between 8-row groups (K-major SW64)
+
+__host__ __device__ inline uint64_t make_smem_desc(uint32_t smem_addr, bool mn_major) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  if (mn_major) {
+    d |= (uint64_t)((MN_LBO_BYTES >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((MN_SBO_BYTES >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  } else {
+    d |= (uint64_t)1 << 16;  // LBO unused for swizzled K-major
+    d |= (uint64_t)((K_SBO_BYTES >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  }
+  d |= (uint64_t)1 << 46;    // descriptor version (Blackwell)
+  return d;
+}
+__host__ __device__ inline uint32_t make_instr_desc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4)                       // D format f32
+       | (1u << 7) | (1u << 10)          // A, B format bf16
+       | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+       | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+#if defined(__CUDACC__) && defined(SM3_GEMM_KERNEL_IMPL)
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug traps (launch failure) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) {  // ~10 s
+      printf("sm3 gemm: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Tile {
+  int m0, n0, group, k_begin, k_end;
+  __device__ __forceinline__ int nkb() const { return (k_end - k_begin + BK - 1) / BK; }
+};
+
+__device__ __forceinline__ int total_tiles(const Params& p) {
+  if (p.sched == SCHED_GROUPED) return __ldg(p.num_m_tiles_dev) * p.n_tiles;
+  return p.num_tiles;
+}
+
+__device__ __forceinline__ Tile decode_tile(const Params& p, int t) {
+  Tile tl;
+  if (p.sched == SCHED_SPLITK) {
+    const int s = t % p.k_splits;
+    int rest = t / p.k_splits;
+    const int nt = rest % p.n_tiles; rest /= p.n_tiles;
+    const int mt = rest % p.m_tiles;
+    tl.group = rest / p.m_tiles;
+    tl.m0 = mt * BM; tl.n0 = nt * p.BN;
+    int b = 0, e = p.K;
+    if (p.seg_begin) { b = __ldg(p.seg_begin + tl.group); e = __ldg(p.seg_end + tl.group); }
+    int len = e - b; if (len < 0) len = 0;
+    int chunk = (len + p.k_splits - 1) / p.k_splits;
+    chunk = (chunk + BK - 1) / BK * BK;
+    tl.k_begin = b + s * chunk;
+    tl.k_end = min(e, tl.k_begin + chunk);
+    if (tl.k_end < tl.k_begin) tl.k_end = tl.k_begin;
+  } else {
+    const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+    tl.m0 = mt * BM; tl.n0 = nt * p.BN;
+    tl.group = (p.sched == SCHED_GROUPED) ? __ldg(p.tile_group + mt) : 0;
+    tl.k_begin = 0; tl.k_end = p.K;
+  }
+  return tl;
+}
+
+// split 4 fp32 -> 2 packed bf16x2 hi (truncated) + 2 packed bf16x2 lo (rounded residual)
+__device__ __forceinline__ void split4(const float4& x, uint32_t& h01, uint32_t& h23, uint32_t& l01,
+                                       uint32_t& l23) {
+  const uint32_t u0 = __float_as_uint(x.x), u1 = __float_as_uint(x.y);
+  const uint32_t u2 = __float_as_uint(x.z), u3 = __float_as_uint(x.w);
+  h01 = __byte_perm(u0, u1, 0x7632);
+  h23 = __byte_perm(u2, u3, 0x7632);
+  const uint32_t r0 = __float_as_uint(x.x - __uint_as_float(u0 & 0xFFFF0000u)) + 0x8000u;
+  const uint32_t r1 = __float_as_uint(x.y - __uint_as_float(u1 & 0xFFFF0000u)) + 0x8000u;
+  const uint32_t r2 = __float_as_uint(x.z - __uint_as_float(u2 & 0xFFFF0000u)) + 0x8000u;
+  const uint32_t r3 = __float_as_uint(x.w - __uint_as_float(u3 & 0xFFFF0000u)) + 0x8000u;
+  l01 = __byte_perm(r0, r1, 0x7632);
+  l23 = __byte_perm(r2, r3, 0x7632);
+}
+
+// Producer unit bookkeeping: unit u of a k-block -> which operand and where.
+struct UnitMap {
+  int units_a, units_b, segs_b;   // per k-block
+};
+__device__ __forceinline__ UnitMap make_unit_map(const Params& p, bool a_mn, bool b_mn) {
+  UnitMap um;
+  um.units_a = 16;  // 128 rows / 8 (K-major) or 16 k-pairs x 1 segment (MN-major)
+  um.segs_b = (p.BN + 127) / 128;
+  um.units_b = b_mn ? 16 * um.segs_b : p.BN / 8;
+  return um;
+}
+
+__global__ void __maxnreg__(144) gemm_bf16x3_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 64u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 80u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 96u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool a_mn = (p.a_smn == 1 && p.a_sk != 1);
+  const bool b_mn = (p.b_smn == 1 && p.b_sk != 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), NUM_PROD_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int ntiles = total_tiles(p);
+
+  if (warp < NUM_EPI_WARPS) {
+    // ============================== EPILOGUE ==============================================
+    int acc = 0; uint32_t acc_phase = 0;
+    const int nchunks = p.BN / 32;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const Tile tl = decode_tile(p, t);
+      if (tl.nkb() == 0) continue;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = tl.m0 + warp * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* drow = p.D + (long long)tl.group * p.d_group_stride + (long long)row * p.ldd + tl.n0;
+      const float* bias = p.bias ? p.bias + (long long)tl.group * p.bias_group_stride + tl.n0 : nullptr;
+      const float rscale = ((p.epi & EPI_ROWSCALE) && row_ok) ? __ldg(p.row_scale + row) : 1.0f;
+      for (int c = 0; c < nchunks; ++c) {
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c * 32), v);
+        if (c == nchunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (!row_ok) continue;
+        const int col0 = c * 32;
+        if (p.epi & EPI_BIAS) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = ldg_f4(bias + col0 + i);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          }
+        }
+        if (p.epi & EPI_GELU) {
+          if (p.aux_out) {
+            float* arow = p.aux_out + (long long)row * p.ld_aux + tl.n0 + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(arow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (p.epi & EPI_DGELU) {
+          const float* arow = p.aux_in + (long long)row * p.ld_aux + tl.n0 + col0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 h = ldg_f4(arow + i);
+            v[i] *= gelu_erf_grad(h.x); v[i + 1] *= gelu_erf_grad(h.y);
+            v[i + 2] *= gelu_erf_grad(h.z); v[i + 3] *= gelu_erf_grad(h.w);
+          }
+        }
+        if (p.epi & EPI_COLSCALE) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s = ldg_f4(p.col_scale + tl.n0 + col0 + i);
+            v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
+          }
+        }
+        if (p.epi & EPI_ROWSCALE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= rscale;
+        }
+        if (p.epi & EPI_RESID) {
+          const float* rrow = p.resid + (long long)row * p.ld_resid + tl.n0 + col0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 r = ldg_f4(rrow + i);
+            v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+          }
+        }
+        if (p.epi & EPI_ATOMIC) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(drow + col0 + i, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(drow + col0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp == MMA_WARP) {
+    // ============================== MMA ISSUER ============================================
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(p.BN, a_mn, b_mn);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t a_kstep = a_mn ? 2u * MN_SBO_BYTES : 32u;   // advance 16 k per UMMA
+      const uint32_t b_kstep = b_mn ? 2u * MN_SBO_BYTES : 32u;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const Tile tl = decode_tile(p, t);
+        const int nkb = tl.nkb();
+        if (nkb == 0) continue;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sb = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            const uint64_t ahi = make_smem_desc(sb + OFF_A_HI + j * a_kstep, a_mn);
+            const uint64_t alo = make_smem_desc(sb + OFF_A_LO + j * a_kstep, a_mn);
+            const uint64_t bhi = make_smem_desc(sb + OFF_B_HI + j * b_kstep, b_mn);
+            const uint64_t blo = make_smem_desc(sb + OFF_B_LO + j * b_kstep, b_mn);
+            tc_mma(tmem_d, alo, bhi, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            tc_mma(tmem_d, ahi, blo, idesc, 1u);
+            tc_mma(tmem_d, ahi, bhi, idesc, 1u);
+          }
+          tc_commit(empty_bar(stage));
+          if (kb == nkb - 1) tc_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ============================== PRODUCERS =============================================
+    const int wq = warp - FIRST_PROD_WARP;
+    const UnitMap um = make_unit_map(p, a_mn, b_mn);
+    const int sub = lane >> 3, f4 = lane & 7;
+    const bool odd = lane & 1;
+
+    // Iterator over (tile, kb) with nkb > 0
+    struct It { int t, kb, nkb; Tile tl; bool valid; };
+    auto first_from = [&](int t) {
+      It it; it.kb = 0; it.valid = false; it.t = t; it.nkb = 0;
+      for (; it.t < ntiles; it.t += gridDim.x) {
+        it.tl = decode_tile(p, it.t);
+        it.nkb = it.tl.nkb();
+        if (it.nkb > 0) { it.valid = true; break; }
+      }
+      return it;
+    };
+    auto next_of = [&](const It& c) {
+      if (c.kb + 1 < c.nkb) { It n = c; n.kb = c.kb + 1; return n; }
+      return first_from(c.t + gridDim.x);
+    };
+
+    // issue the global loads of one k-block for this thread's units
+    auto load_kb = [&](float4 (&r)[MAX_UNITS][2], const It& it) {
+      const int k0 = it.tl.k_begin + it.kb * BK;
+#pragma unroll
+      for (int i = 0; i < MAX_UNITS; ++i) {
+        r[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int u = wq + NUM_PROD_WARPS * i;
+        const bool is_a = u < um.units_a;
+        const int ul = is_a ? u : u - um.units_a;
+        if (!is_a && ul >= um.units_b) continue;
+        const bool mn = is_a ? a_mn : b_mn;
+        const float* base = is_a ? p.A : p.B + (long long)it.tl.group * p.b_group_stride;
+        const long long s_mn = is_a ? p.a_smn : p.b_smn;
+        const long long s_k = is_a ? p.a_sk : p.b_sk;
+        const int mn0 = is_a ? it.tl.m0 : it.tl.n0;
+        const int mn_lim = is_a ? p.M : p.N;
+        if (!mn) {
+          const int k = k0 + 4 * f4;
+          if (k + 4 > it.tl.k_end) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = mn0 + 8 * ul + 2 * sub + h;
+            if (row >= mn_lim) continue;
+            long long ridx = row;
+            if (is_a && p.a_row_index) { ridx = __ldg(p.a_row_index + row); if (ridx < 0) continue; }
+            r[i][h] = ldg_f4(base + ridx * s_mn + k);
+          }
+        } else {
+          const int segs = is_a ? 1 : um.segs_b;
+          const int pi = ul / segs, seg = ul - pi * segs;
+          const int mnl = seg * 128 + 4 * lane;
+          const int tile_w = is_a ? BM : p.BN;
+          if (mnl + 4 > tile_w || mn0 + mnl + 4 > mn_lim) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = k0 + (pi >> 2) * 8 + (pi & 3) + 4 * h;
+            if (k >= it.tl.k_end) continue;
+            r[i][h] = ldg_f4(base + (long long)k * s_k + (mn0 + mnl));
+          }
+        }
+      }
+    };
+
+    // split + exchange + store one k-block into its smem stage
+    auto store_kb = [&](const float4 (&r)[MAX_UNITS][2], uint32_t sb) {
+#pragma unroll
+      for (int i = 0; i < MAX_UNITS; ++i) {
+        const int u = wq + NUM_PROD_WARPS * i;
+        const bool is_a = u < um.units_a;
+        const int ul = is_a ? u : u - um.units_a;
+        if (!is_a && ul >= um.units_b) continue;
+        const bool mn = is_a ? a_mn : b_mn;
+        uint32_t hA0, hA1, lA0, lA1, hB0, hB1, lB0, lB1;
+        split4(r[i][0], hA0, hA1, lA0, lA1);
+        split4(r[i][1], hB0, hB1, lB0, lB1);
+        // even lane keeps part 0 (needs the odd lane's part-0 half); odd lane keeps part 1
+        const uint32_t s0 = odd ? hA0 : hB0, s1 = odd ? hA1 : hB1;
+        const uint32_t s2 = odd ? lA0 : lB0, s3 = odd ? lA1 : lB1;
+        const uint32_t q0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+        const uint32_t q1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+        const uint32_t q2 = __shfl_xor_sync(0xffffffffu, s2, 1);
+        const uint32_t q3 = __shfl_xor_sync(0xffffffffu, s3, 1);
+        uint4 hi, lo;
+        if (!odd) { hi = make_uint4(hA0, hA1, q0, q1); lo = make_uint4(lA0, lA1, q2, q3); }
+        else      { hi = make_uint4(q0, q1, hB0, hB1); lo = make_uint4(q2, q3, lB0, lB1); }
+        uint32_t off;
+        if (!mn) {
+          const uint32_t row = 8u * ul + 2u * sub + (odd ? 1u : 0u);
+          off = kmajor_sw64_offset(row, (uint32_t)f4 >> 1);
+        } else {
+          const int segs = is_a ? 1 : um.segs_b;
+          const int pi = ul / segs, seg = ul - pi * segs;
+          const uint32_t k = (uint32_t)((pi >> 2) * 8 + (pi & 3) + (odd ? 4 : 0));
+          off = mnmajor_sw128_offset(k, (uint32_t)(seg * 16 + (lane >> 1)));
+        }
+        const uint32_t dst_hi = sb + (is_a ? OFF_A_HI : OFF_B_HI) + off;
+        const uint32_t dst_lo = sb + (is_a ? OFF_A_LO : OFF_B_LO) + off;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(dst_hi), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(dst_lo), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+      }
+    };
+
+    int stage = 0; uint32_t phase = 0;
+    auto publish = [&](const float4 (&r)[MAX_UNITS][2]) {
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      store_kb(r, smem_base + stage * STAGE_BYTES);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    };
+
+    float4 r0[MAX_UNITS][2], r1[MAX_UNITS][2];
+    It it = first_from(blockIdx.x);
+    if (it.valid) {
+      load_kb(r0, it);
+      while (true) {
+        It n1 = next_of(it);
+        if (n1.valid) load_kb(r1, n1);
+        publish(r0);
+        if (!n1.valid) break;
+        It n2 = next_of(n1);
+        if (n2.valid) load_kb(r0, n2);
+        publish(r1);
+        if (!n2.valid) break;
+        it = n2;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+#endif  // __CUDACC__ && SM3_GEMM_KERNEL_IMPL
+
+// Host-side launcher (gemm_tc.cu): validates shapes, fills derived fields, launches on `stream`.
+int launch(Params p, cudaStream_t stream);
+// Picks the largest supported tile width that divides N (multiple of 32, <= 256); 0 if none.
+int pick_bn(int N);
+
+}  // namespace gemm
+}  // namespace sm3

@@ -1,0 +1,103 @@
+"""The CPU oracle against (a) the committed golden fixtures generated from the unmodified reference
+and (b) the live reference module when /root/reference is present (build container only)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle.cases import CASES, make_noise, summarize_grad, upstream_grads
+from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes
+from oracle.gen_golden import moe_token_counts
+from sm3det_b200.synth import make_images, make_state_dict, state_dict_checksum
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _run_oracle(gold, record):
+    kw = gold['kw']
+    cfg = OracleConfig(**kw)
+    sd = make_state_dict(param_shapes(cfg), 0, gold['weights'] == 'trained')
+    assert abs(state_dict_checksum(sd) - gold['sd_checksum']) <= 1e-9 * abs(gold['sd_checksum']), 'weight RNG drift'
+    n, h, w = gold['img']
+    x = make_images(n, h, w, seed=1234)
+    assert abs(float(x.double().abs().sum()) - gold['x_checksum']) <= 1e-9 * gold['x_checksum'], 'image RNG drift'
+    mode = gold['mode']
+    if mode == 'eval':
+        with torch.no_grad():
+            return cfg, sd, backbone_forward(sd, cfg, x, train=False, record=record)
+    noise = make_noise(cfg, moe_token_counts(cfg, n, h, w)) if mode == 'train_noisy' else None
+    sdg = {k: (v.clone().requires_grad_(True) if 'ffn.mean' not in k and 'ffn.std' not in k else v) for k, v in sd.items()}
+    return cfg, sdg, backbone_forward(sdg, cfg, x, train=True, noise=noise, record=record)
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, '*.pt'))), ids=lambda p: os.path.basename(p)[:-3])
+def test_oracle_matches_reference_golden(path):
+    gold = torch.load(path, weights_only=False)
+    record = []
+    cfg, sd, res = _run_oracle(gold, record)
+    has_loss = 'gate_loss' in gold
+    outs, loss = res if has_loss else (res, None)
+    st = gold['stride']
+    # same torch build => bit-exact; tolerate 2e-6 relative for a different CPU kernel selection
+    for o, g, l2 in zip(outs, gold['outs'], gold['out_l2']):
+        torch.testing.assert_close(o.detach()[:, :, ::st, ::st], g, rtol=2e-6, atol=2e-6)
+        assert abs(o.detach().double().norm().item() - l2) <= 2e-6 * l2
+    if has_loss:
+        torch.testing.assert_close(loss.detach(), gold['gate_loss'], rtol=1e-6, atol=1e-9)
+    assert len(record) == len(gold['moe'])
+    for r, g in zip(record, gold['moe']):
+        assert r['prefix'] == g['prefix']
+        assert torch.equal(r['top_idx'].to(torch.int16), g['top_idx']), 'router top-k indices must be bit-exact'
+        torch.testing.assert_close(r['top_gates'], g['top_gates'], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(r['load'], g['load'], rtol=1e-6, atol=1e-6)
+    if 'grads' in gold:
+        ups = upstream_grads(outs)
+        (sum((o * u).sum() for o, u in zip(outs, ups)) + (loss if has_loss else 0.0)).backward()
+        for name, g in gold['grads'].items():
+            s = summarize_grad(sd[name].grad)
+            if 'full' in g:
+                torch.testing.assert_close(s['full'], g['full'], rtol=1e-5, atol=1e-7)
+            else:
+                torch.testing.assert_close(s['sample'], g['sample'], rtol=1e-5, atol=1e-7)
+                assert abs(s['l2'] - g['l2']) <= 1e-5 * (g['l2'] + 1e-12)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason='/root/reference not mounted')
+@pytest.mark.parametrize('name', ['mini_moe_e4k2_eval', 'mini_moe_e8k3_eval'])
+def test_oracle_matches_live_reference(name):
+    spec = CASES[name]
+    kw = dict(spec['kw'])
+    cfg = OracleConfig(**kw)
+    net = ref_shim.build_reference_backbone('ConvNeXt_moe_MultiInput', seed=0, **kw)
+    sd = make_state_dict(param_shapes(cfg), 3, True)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = make_images(2, 64, 64, seed=5)
+    with torch.no_grad():
+        ref = net(x)
+        orc = backbone_forward(sd, cfg, x)
+    for a, b in zip(ref[0], orc[0]):
+        assert torch.equal(a, b)
+    assert torch.equal(ref[1], orc[1])
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason='/root/reference not mounted')
+def test_plain_convnext_moe_class_matches():
+    """ConvNeXt_moe (stem inside downsample_layers.0) -- convnext_moe.py:407-600."""
+    kw = dict(arch=dict(depths=[1, 1, 2, 1], channels=[32, 64, 96, 128]), MoE_Block_inds=[[], [], [1], []],
+              num_experts=4, top_k=2)
+    cfg = OracleConfig(multi_input=False, **kw)
+    net = ref_shim.build_reference_backbone('ConvNeXt_moe', seed=0, **kw)
+    shapes = param_shapes(cfg)
+    assert set(shapes) == set(net.state_dict())
+    sd = make_state_dict(shapes, 1, True)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = make_images(1, 64, 64, seed=2)
+    with torch.no_grad():
+        ref = net(x)
+        orc = backbone_forward(sd, cfg, x)
+    for a, b in zip(ref[0], orc[0]):
+        assert torch.equal(a, b)
