@@ -1,0 +1,179 @@
+/* sm3det_b200 -- C ABI of the B200 (sm_100a) kernel library behind SM3Det's ConvNeXt-MoE backbone.
+ *
+ * The reference hot path is pure Python/PyTorch (mmrotate/models/backbones/convnext_moe.py); it has
+ * no FFI of its own.  The closest analogue of this boundary is the `mmcv._ext` extension built at
+ * mmcv/setup.py:238-296, which the backbone never calls.  Each entry point below therefore cites the
+ * reference *Python* call site(s) it replaces (file:line relative to the SM3Det tree) -- that is the
+ * place where a maintainer binds it (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never allocates,
+ *    frees or retains memory past the call; workspaces are passed in explicitly;
+ *  - tensors are fp32, contiguous, NHWC ("tokens x channels") unless stated; indices are int32;
+ *  - `stream` is a cudaStream_t passed as void*; calls are stream-ordered, never synchronise and
+ *    never touch the default stream implicitly;
+ *  - return 0 on success, a negative SM3_ERR_* otherwise; sm3_last_error() returns a thread-local
+ *    message; no C++ exception or STL type crosses the boundary.
+ */
+#ifndef SM3DET_B200_H_
+#define SM3DET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SM3_ABI_VERSION 1
+
+#define SM3_OK 0
+#define SM3_ERR_INVALID_ARG (-1)
+#define SM3_ERR_UNSUPPORTED_SHAPE (-2)
+#define SM3_ERR_CUDA (-3)
+#define SM3_ERR_WORKSPACE (-4)
+
+int sm3_abi_version(void);
+const char* sm3_last_error(void);
+/* 1 if the current device is compute capability 10.x (the only supported target), else 0 */
+int sm3_device_supported(void);
+
+/* ---- tensor-core GEMM ------------------------------------------------------------------------
+ * D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ), fp32 in HBM, split-bf16 (hi+lo) operands on tcgen05,
+ * fp32 accumulation in TMEM (product error ~1e-5 relative).
+ * Replaces: FFN.forward nn.Linear/GELU/nn.Linear (convnext_moe.py:397-405), the expert loop
+ * (:244) with its gather x[_batch_index] (:265), the 2x2/s2 downsample Conv2d (:549-558), and the
+ * dgrad / wgrad GEMMs autograd derives for them.
+ * Element (mn,k) of an operand is at ptr + mn*stride_mn + k*stride_k; exactly one stride is 1.
+ */
+enum { SM3_SCHED_DENSE = 0, SM3_SCHED_GROUPED = 1, SM3_SCHED_SPLITK = 2 };
+enum {
+  SM3_EPI_BIAS = 1,      /* acc += bias[n] */
+  SM3_EPI_GELU = 2,      /* aux_out[m,n] = acc (if aux_out); acc = gelu_erf(acc) */
+  SM3_EPI_DGELU = 4,     /* acc *= gelu_erf'(aux_in[m,n]) */
+  SM3_EPI_COLSCALE = 8,  /* acc *= col_scale[n]   (layer scale gamma) */
+  SM3_EPI_ROWSCALE = 16, /* acc *= row_scale[m]   (drop-path / gate) */
+  SM3_EPI_RESID = 32,    /* acc += resid[m,n]     (shortcut) */
+  SM3_EPI_ATOMIC = 64,   /* atomicAdd into D (split-K) */
+  SM3_EPI_AUXSTORE = 128 /* aux_out[m,n] = acc after bias (no activation) */
+};
+typedef struct sm3_gemm_args {
+  const float* A; int64_t a_stride_mn, a_stride_k;
+  const float* B; int64_t b_stride_mn, b_stride_k, b_group_stride;
+  const int32_t* a_row_index;      /* optional row gather of A (K-major A); -1 = zero row */
+  const int32_t* b_k_index;        /* optional gather of B along the reduction index (MN-major B) */
+  int32_t M, N, K;
+  int32_t tile_n;                  /* 0 = auto */
+  int32_t sched;
+  int32_t k_splits, num_groups;    /* SPLITK */
+  const int32_t* tile_group;       /* GROUPED: expert id of each 128-row tile (device) */
+  const int32_t* num_m_tiles;      /* GROUPED: device scalar, number of live 128-row tiles */
+  const int32_t* seg_begin;        /* SPLITK: per-group reduction range (device), or NULL = [0,K) */
+  const int32_t* seg_end;
+  float* D; int64_t ldd, d_group_stride;
+  const float* bias; int64_t bias_group_stride;
+  int32_t epilogue;
+  float* aux_out; const float* aux_in; int64_t ld_aux;
+  const float* col_scale; const float* row_scale;
+  const float* resid; int64_t ld_resid;
+} sm3_gemm_args;
+int sm3_gemm(const sm3_gemm_args* args, void* stream);
+
+/* ---- LayerNorm over channels (F.layer_norm, eps inside rsqrt, biased variance) ---------------
+ * Replaces LayerNorm2d.forward (convnext_moe.py:34-47) at :351 (block norm), :549-551 (downsample
+ * norm, written directly in 2x2-patch order for the following GEMM) and :811-817 (output norm incl.
+ * the NHWC->NCHW permute+contiguous).  stats (optional) receives (mean, rstd) per token.
+ */
+enum { SM3_LN_NHWC = 0, SM3_LN_PATCH2 = 1, SM3_LN_NCHW = 2 };
+int sm3_layernorm_fwd(const float* x, const float* weight, const float* bias, float* y, float* stats,
+                      int64_t tokens, int32_t C, float eps, int32_t out_mode, int32_t H, int32_t W, void* stream);
+int sm3_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* weight, float* dx,
+                      float* dweight, float* dbias, int64_t tokens, int32_t C, int32_t in_mode, int32_t H,
+                      int32_t W, int32_t dx_accumulate, void* stream);
+
+/* ---- stem: LN(conv ps x ps / stride ps) NCHW -> NHWC ------------------------------------------
+ * Replaces dataset_stems['single'] + downsample_layers[0] (convnext_moe.py:783-791, :800-806) and
+ * the plain-class stem (:532-536).  weight_t is the conv weight transposed to [Cin*ps*ps][C0].
+ */
+int sm3_stem_fwd(const float* x_nchw, const float* weight_t, const float* bias, const float* ln_weight,
+                 const float* ln_bias, float* y, float* conv_out, float* stats, int32_t N, int32_t Cin,
+                 int32_t H, int32_t W, int32_t ps, int32_t C0, float eps, void* stream);
+int sm3_stem_wgrad(const float* x_nchw, const float* dconv, float* dweight_t, float* dbias, int32_t N,
+                   int32_t Cin, int32_t H, int32_t W, int32_t ps, int32_t C0, void* stream);
+
+/* ---- 7x7 depthwise conv, NHWC ------------------------------------------------------------------
+ * Replaces ConvNeXtBlock.depthwise_conv (convnext_moe.py:311-312, :347).  weight_t = taps as
+ * [49][C].  dgrad = the same call on dy with the taps flipped; wgrad accumulates into dweight_t.
+ */
+int sm3_dwconv7_fwd(const float* x, const float* weight_t, const float* bias, const float* resid, float* y,
+                    int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int sm3_dwconv7_wgrad(const float* x, const float* dy, float* dweight_t, float* dbias, int32_t N, int32_t H,
+                      int32_t W, int32_t C, void* stream);
+
+/* ---- MoE routing --------------------------------------------------------------------------------
+ * sm3_moe_router : CosineTopKGate.forward :99-106 + noisy_top_k_gating :194-223 (+ _prob_in_top_k
+ *                  :152-174 when `noise` is given and k < E); true fp32 FMA so top-k is exact.
+ * sm3_moe_plan   : importance/load reduction, cv_squared :140-147 and the loss :234-238, plus the
+ *                  expert-major slot layout that SparseDispatcher.__init__ :252-262 builds with two
+ *                  host syncs -- here entirely on device; segments start at multiples of 128 rows.
+ * sm3_moe_assign : pair (token, j) -> slot, and pair_token[slot] = token (caller pre-fills -1).
+ * sm3_moe_combine: SparseDispatcher.combine :269-284 + layer scale :367-368 + shortcut/drop-path
+ *                  :370: out = resid + row_scale * gamma * sum_j gate_j * o[slot_j]  (ascending
+ *                  expert order, no atomics).
+ */
+typedef struct sm3_router_args {
+  const float* v; const float* proj_weight; const float* proj_bias; const float* sim_matrix;
+  const float* temperature; const float* w_noise; const float* noise;
+  int32_t T, C, P, E, k;
+  int32_t* top_idx; float* top_gate; float* logits; float* top_vals; float* p_out;
+  float* partials;                 /* [sm3_moe_router_blocks(T)][3*E] workspace */
+} sm3_router_args;
+int sm3_moe_router_blocks(int32_t T);
+int sm3_moe_router(const sm3_router_args* args, void* stream);
+
+typedef struct sm3_plan_args {
+  const float* partials; int32_t T, E, k, max_m_tiles;
+  float* importance; float* load; float* loss;
+  int32_t* counts; int32_t* seg_begin; int32_t* seg_end; int32_t* cursor;
+  int32_t* tile_group; int32_t* num_m_tiles;
+} sm3_plan_args;
+int sm3_moe_plan(const sm3_plan_args* args, void* stream);
+int sm3_moe_assign(const int32_t* top_idx, int32_t T, int32_t k, int32_t E, const int32_t* seg_begin,
+                   int32_t* cursor, int32_t* slot_of, int32_t* pair_token, void* stream);
+int sm3_moe_combine(const float* expert_out, const int32_t* slot_of, const int32_t* top_idx, const float* gate,
+                    const float* gamma, const float* resid, const float* row_scale, float* out, float* y_opt,
+                    int32_t T, int32_t C, int32_t k, void* stream);
+
+/* ---- backward-only helpers ------------------------------------------------------------------------
+ * (autograd derives these in the reference; each cites the forward statement it differentiates)
+ * sm3_moe_combine_bwd : backward of combine/layer-scale/shortcut (convnext_moe.py:269-284,:367-370)
+ * sm3_moe_router_bwd  : backward of softmax-of-k, cosine logits and the importance loss
+ *                       (:99-106, :208-217, :234-238) for clean gating -> dp [T,P], d sim_hat, d tau
+ * sm3_colsum          : out[g][c] += sum_r a[r,c]*(b?b[r,c]:1)*(rs?rs[r]:1) over rows of segment g
+ *                       (bias / gamma gradients)
+ * sm3_gather_sum      : out[t] = add[t] + sum_j src[slot_of[t,j]]  (backward of x[_batch_index], :265)
+ * sm3_scale_rows      : out = x * row_scale[r] * col_scale[c]
+ */
+int sm3_moe_combine_bwd(const float* dout, const float* expert_out, const int32_t* slot_of, const int32_t* top_idx,
+                        const float* gate, const float* gamma, const float* row_scale, float* d_expert_out,
+                        float* dgate, float* dgamma, int32_t T, int32_t C, int32_t k, void* stream);
+typedef struct sm3_router_bwd_args {
+  const float* p; const float* sim_matrix; const float* temperature;
+  const int32_t* top_idx; const float* top_gate; const float* dgate; const float* logits;
+  const float* importance; const float* loss_scale;
+  int32_t T, P, E, k;
+  float* dp; float* dsim_hat; float* dtemperature;
+} sm3_router_bwd_args;
+int sm3_moe_router_bwd(const sm3_router_bwd_args* args, void* stream);
+int sm3_moe_router_bwd_finalize(const float* dsim_hat, const float* sim_matrix, float* dsim, int32_t P, int32_t E,
+                                void* stream);
+int sm3_colsum(const float* a, const float* b, const float* row_scale, const int32_t* seg_begin,
+               const int32_t* seg_end, int32_t groups, float* out, int64_t rows, int32_t C, void* stream);
+int sm3_gather_sum(const float* src, const int32_t* slot_of, const float* add, float* out, int32_t T, int32_t C,
+                   int32_t k, void* stream);
+int sm3_scale_rows(const float* x, const float* row_scale, const float* col_scale, float* out, int64_t rows,
+                   int32_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SM3DET_B200_H_ */

@@ -1,0 +1,387 @@
+"""Drop-in ConvNeXt-MoE backbones running on the sm3det_b200 CUDA library.
+
+Same class names, constructor kwargs, ``state_dict`` layout, forward signature and return
+convention as the reference (mmrotate/models/backbones/convnext_moe.py):
+  ConvNeXt_moe            :407-728     ConvNeXt_moe_MultiInput   :730-899
+  ConvNeXtBlock           :295-379     FFN :381-405   MoE_layer :108-248   CosineTopKGate :88-106
+  LayerNorm2d             :30-47
+The sub-modules below are *parameter containers* with the reference's attribute names; all compute
+goes through sm3det_b200.functional (NHWC fp32 end-to-end, NCHW only at the input and the 4 outputs).
+"""
+import math
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .registry import ROTATED_BACKBONES, BaseModule
+
+ARCH_SETTINGS = {
+    'atto': dict(depths=[2, 2, 6, 2], channels=[40, 80, 160, 320]),
+    'femto': dict(depths=[2, 2, 6, 2], channels=[48, 96, 192, 384]),
+    'pico': dict(depths=[2, 2, 6, 2], channels=[64, 128, 256, 512]),
+    'nano': dict(depths=[2, 2, 8, 2], channels=[80, 160, 320, 640]),
+    'tiny': dict(depths=[3, 3, 9, 3], channels=[96, 192, 384, 768]),
+    'small': dict(depths=[3, 3, 27, 3], channels=[96, 192, 384, 768]),
+    'base': dict(depths=[3, 3, 27, 3], channels=[128, 256, 512, 1024]),
+    'swin_large': dict(depths=[2, 2, 18, 2], channels=[192, 384, 768, 1536]),
+    'large': dict(depths=[3, 3, 27, 3], channels=[192, 384, 768, 1536]),
+    'xlarge': dict(depths=[3, 3, 27, 3], channels=[256, 512, 1024, 2048]),
+    'huge': dict(depths=[3, 3, 27, 3], channels=[352, 704, 1408, 2816]),
+}
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """Parameter holder (weight, bias, eps); normalisation runs in sm3_layernorm_fwd."""
+
+    def __init__(self, num_channels: int, **kwargs) -> None:
+        super().__init__(num_channels, **kwargs)
+        self.num_channels = self.normalized_shape[0]
+
+
+def build_LayerNorm2d_layer(cfg: dict, num_features: int) -> nn.Module:
+    if not isinstance(cfg, dict):
+        raise TypeError('cfg must be a dict')
+    if 'type' not in cfg:
+        raise KeyError('the cfg dict must contain the key "type"')
+    cfg_ = cfg.copy()
+    cfg_.pop('type')
+    requires_grad = cfg_.pop('requires_grad', True)
+    cfg_.setdefault('eps', 1e-5)
+    layer = LayerNorm2d(num_features, **cfg_)
+    for param in layer.parameters():
+        param.requires_grad = requires_grad
+    return layer
+
+
+class FFN(nn.Module):
+    def __init__(self, in_channels, mid_channels):
+        super().__init__()
+        self.pointwise_conv1 = nn.Linear(in_channels, mid_channels)
+        self.pointwise_conv2 = nn.Linear(mid_channels, in_channels)
+
+
+class CosineTopKGate(nn.Module):
+    def __init__(self, model_dim, num_global_experts, init_t=0.5):
+        super().__init__()
+        proj_dim = min(model_dim // 2, 256)
+        self.temperature = nn.Parameter(torch.log(torch.full([1], 1.0 / init_t)), requires_grad=True)
+        self.cosine_projector = nn.Linear(model_dim, proj_dim)
+        self.sim_matrix = nn.Parameter(torch.randn(size=(proj_dim, num_global_experts)), requires_grad=True)
+        nn.init.normal_(self.sim_matrix, 0, 0.01)
+
+
+class MoE_layer(nn.Module):
+    def __init__(self, in_channels, mid_channels, num_experts, top_k, noisy_gating, gating):
+        super().__init__()
+        if gating != 'cosine':
+            raise NotImplementedError(
+                "sm3det_b200: only gate='cosine' is implemented (gate='linear' starts from an all-zero w_gate, "
+                'i.e. fully tied logits whose routing is implementation-defined in the reference)')
+        assert top_k <= num_experts
+        self.noisy_gating = noisy_gating
+        self.num_experts = num_experts
+        self.input_size = in_channels
+        self.k = top_k
+        self.gating = gating
+        self.experts = nn.ModuleList([FFN(in_channels, mid_channels) for _ in range(num_experts)])
+        self.w_gate = CosineTopKGate(in_channels, num_experts)
+        self.w_noise = nn.Parameter(torch.zeros(in_channels, num_experts), requires_grad=True)
+        self.register_buffer('mean', torch.tensor([0.0]))
+        self.register_buffer('std', torch.tensor([1.0]))
+
+    def expert_params(self):
+        e = self.experts
+        w1 = [m.pointwise_conv1.weight for m in e]
+        b1 = [m.pointwise_conv1.bias for m in e]
+        w2 = [m.pointwise_conv2.weight for m in e]
+        b2 = [m.pointwise_conv2.bias for m in e]
+        for group in (w1, b1, w2, b2):
+            Fn.stack_expert_params(group)
+        return w1 + b1 + w2 + b2
+
+
+class ConvNeXtBlock(nn.Module):
+    def __init__(self, in_channels, norm_cfg, mlp_ratio=4., MoE_cfg=None, drop_path_rate=0.,
+                 layer_scale_init_value=1e-6):
+        super().__init__()
+        self.depthwise_conv = nn.Conv2d(in_channels, in_channels, groups=in_channels, kernel_size=7, padding=3)
+        self.norm = build_LayerNorm2d_layer(norm_cfg, in_channels)
+        mid = int(mlp_ratio * in_channels)
+        self.MoE_cfg = MoE_cfg
+        if MoE_cfg is not None:
+            self.ffn = MoE_layer(in_channels, mid, MoE_cfg['num_experts'], MoE_cfg['top_k'], MoE_cfg['noisy_gating'],
+                                 MoE_cfg['gating'])
+        else:
+            self.ffn = FFN(in_channels, mid)
+        if not layer_scale_init_value > 0:
+            raise NotImplementedError('sm3det_b200: layer_scale_init_value must be > 0 (gamma is fused in the epilogue)')
+        self.gamma = nn.Parameter(layer_scale_init_value * torch.ones((in_channels)), requires_grad=True)
+        self.drop_path_rate = float(drop_path_rate)
+
+    def _row_scale(self, x):
+        """timm DropPath as a per-token scale (per-sample Bernoulli(keep) / keep), None when inactive."""
+        if self.drop_path_rate == 0. or not self.training:
+            return None
+        keep = 1.0 - self.drop_path_rate
+        N, H, W, _ = x.shape
+        mask = getattr(self, '_injected_drop_mask', None)
+        if mask is None:
+            mask = x.new_empty((N,)).bernoulli_(keep)
+            if keep > 0.0:
+                mask = mask / keep
+        return mask.to(x.device, torch.float32).repeat_interleave(H * W).contiguous()
+
+    def forward(self, x, record=None):
+        """x: NHWC fp32.  Returns (x, loss) like the reference block (:343-379); loss is None if dense."""
+        rs = self._row_scale(x)
+        eps = self.norm.eps
+        dw = self.depthwise_conv
+        if self.MoE_cfg is None:
+            f = self.ffn
+            out = Fn.DenseBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias,
+                                        f.pointwise_conv1.weight, f.pointwise_conv1.bias, f.pointwise_conv2.weight,
+                                        f.pointwise_conv2.bias, self.gamma, rs, eps)
+            return out, None
+        m = self.ffn
+        noise = None
+        if m.noisy_gating and self.training:
+            noise = getattr(m, '_injected_noise', None)
+            if noise is None:
+                T = x.shape[0] * x.shape[1] * x.shape[2]
+                noise = torch.randn((T, m.num_experts), device=x.device, dtype=torch.float32)
+            noise = noise.to(x.device, torch.float32).contiguous()
+        g = m.w_gate
+        out, loss = Fn.MoEBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias, self.gamma,
+                                        g.cosine_projector.weight, g.cosine_projector.bias, g.sim_matrix, g.temperature,
+                                        m.w_noise, rs, noise, eps, m.num_experts, m.k, record, *m.expert_params())
+        return out, loss
+
+
+@ROTATED_BACKBONES.register_module()
+class ConvNeXt_moe(BaseModule):
+    arch_settings = ARCH_SETTINGS
+
+    def __init__(self, arch='tiny', in_channels=3, stem_patch_size=4, norm_cfg=dict(type='LN2d', eps=1e-6),
+                 act_cfg=dict(type='GELU'), linear_pw_conv=True, use_grn=False, drop_path_rate=0.,
+                 layer_scale_init_value=1e-6, out_indices=[0, 1, 2, 3], MoE_Block_inds=[[], [], [], []],
+                 noisy_gating=True, num_experts=2, gate='cosine', top_k=2, frozen_stages=0,
+                 gap_before_final_norm=False, with_cp=False,
+                 init_cfg=[dict(type='TruncNormal', layer=['Conv2d', 'Linear'], std=.02, bias=0.),
+                           dict(type='Constant', layer=['LayerNorm'], val=1., bias=0.)]):
+        super().__init__(init_cfg=init_cfg)
+        if isinstance(arch, str):
+            assert arch in self.arch_settings, \
+                f'Unavailable arch, please choose from ({set(self.arch_settings)}) or pass a dict.'
+            arch = self.arch_settings[arch]
+        elif isinstance(arch, dict):
+            assert 'depths' in arch and 'channels' in arch, \
+                f'The arch dict must have "depths" and "channels", but got {list(arch.keys())}.'
+        if act_cfg.get('type', 'GELU') != 'GELU':
+            raise NotImplementedError('sm3det_b200: only act_cfg=dict(type="GELU") is implemented')
+        if not linear_pw_conv:
+            raise NotImplementedError('sm3det_b200: linear_pw_conv=False (1x1 Conv2d FFN) is not implemented')
+        if use_grn:
+            raise NotImplementedError('sm3det_b200: use_grn=True is not implemented (no SM3Det config enables it)')
+        if gap_before_final_norm:
+            raise NotImplementedError('sm3det_b200: gap_before_final_norm=True is not implemented')
+        self.depths = list(arch['depths'])
+        self.channels = list(arch['channels'])
+        assert (isinstance(self.depths, Sequence) and isinstance(self.channels, Sequence)
+                and len(self.depths) == len(self.channels))
+        for c in self.channels:
+            if c % 32 != 0 or c > 1024:
+                raise NotImplementedError(f'sm3det_b200: channel count {c} unsupported (multiple of 32, <= 1024)')
+        self.num_stages = len(self.depths)
+        if isinstance(out_indices, int):
+            out_indices = [out_indices]
+        out_indices = list(out_indices)
+        for i, index in enumerate(out_indices):
+            if index < 0:
+                out_indices[i] = 4 + index
+                assert out_indices[i] >= 0, f'Invalid out_indices {index}'
+        self.out_indices = out_indices
+        self.MoE_Block_inds = MoE_Block_inds
+        self.num_experts = num_experts
+        self.frozen_stages = frozen_stages
+        self.gap_before_final_norm = gap_before_final_norm
+        self.with_cp = with_cp     # activation checkpointing is not needed at 180 GB; accepted and ignored
+        self.stem_patch_size = stem_patch_size
+        self.norm_eps = norm_cfg.get('eps', 1e-5)
+
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(self.depths))]
+        block_idx = 0
+        self.downsample_layers = nn.ModuleList()
+        stem = nn.Sequential(
+            nn.Conv2d(in_channels, self.channels[0], kernel_size=stem_patch_size, stride=stem_patch_size),
+            build_LayerNorm2d_layer(norm_cfg, self.channels[0]))
+        self.downsample_layers.append(stem)
+        self.stages = nn.ModuleList()
+        for i in range(self.num_stages):
+            depth = self.depths[i]
+            channels = self.channels[i]
+            if i >= 1:
+                self.downsample_layers.append(nn.Sequential(
+                    build_LayerNorm2d_layer(norm_cfg, self.channels[i - 1]),
+                    nn.Conv2d(self.channels[i - 1], channels, kernel_size=2, stride=2)))
+            moe_ind = [list(range(depth))[q] for q in self.MoE_Block_inds[i] if q < depth]
+            stage = nn.Sequential(*[
+                ConvNeXtBlock(in_channels=channels, drop_path_rate=dpr[block_idx + j], norm_cfg=norm_cfg,
+                              MoE_cfg={'noisy_gating': noisy_gating, 'num_experts': num_experts, 'top_k': top_k,
+                                       'gating': gate} if j in moe_ind else None,
+                              layer_scale_init_value=layer_scale_init_value) for j in range(depth)])
+            block_idx += depth
+            self.stages.append(stage)
+            if i in self.out_indices:
+                self.add_module(f'norm{i}', build_LayerNorm2d_layer(norm_cfg, channels))
+        self._init_like_reference()
+        self._freeze_stages()
+
+    def _init_like_reference(self):
+        """The reference never runs init_cfg (init_weights() only supports 'Pretrained'); weights stay at
+        torch defaults.  We keep torch's default constructors too, so nothing to do."""
+
+    # ---- forward -------------------------------------------------------------------------------
+    def _stem(self, x):
+        conv, ln = self.downsample_layers[0][0], self.downsample_layers[0][1]
+        return Fn.StemFn.apply(x, conv.weight, conv.bias, ln.weight, ln.bias, ln.eps, self.stem_patch_size)
+
+    def _trunk(self, x, record=None):
+        outs, gate_losses = [], []
+        for i, stage in enumerate(self.stages):
+            if i >= 1:
+                ln, conv = self.downsample_layers[i][0], self.downsample_layers[i][1]
+                x = Fn.DownsampleFn.apply(x, ln.weight, ln.bias, conv.weight, conv.bias, ln.eps)
+            for blk in stage:
+                x, gate_loss = blk(x, record)
+                if gate_loss is not None:
+                    gate_losses.append(gate_loss)
+            if i in self.out_indices:
+                nl = getattr(self, f'norm{i}')
+                outs.append(Fn.OutNormFn.apply(x, nl.weight, nl.bias, nl.eps))
+        if len(gate_losses) > 0:
+            return tuple(outs), sum(gate_losses) / len(gate_losses)
+        return tuple(outs)
+
+    def forward(self, x, record=None):
+        self._check_input(x)
+        return self._trunk(self._stem(x), record)
+
+    @staticmethod
+    def _check_input(x):
+        if not x.is_cuda:
+            raise RuntimeError('sm3det_b200 backbones run on CUDA (sm_100a) only; there is no CPU path')
+        if x.dim() != 4 or x.shape[2] % 32 != 0 or x.shape[3] % 32 != 0:
+            raise ValueError(f'expected [N,3,H,W] with H, W multiples of 32 (Pad size_divisor=32), got {tuple(x.shape)}')
+
+    def _freeze_stages(self):
+        for i in range(self.frozen_stages):
+            downsample_layer = self.downsample_layers[i]
+            stage = self.stages[i]
+            downsample_layer.eval()
+            stage.eval()
+            for param in list(downsample_layer.parameters()) + list(stage.parameters()):
+                param.requires_grad = False
+
+    def train(self, mode=True):
+        super().train(mode)
+        self._freeze_stages()
+        return self          # the reference returns None (:612-614); returning self is a harmless superset
+
+    def get_layer_depth(self, param_name: str, prefix: str = ''):
+        """Layer-wise depth of a parameter for layer-decay optimizers (:616-658)."""
+        max_layer_id = 12 if self.depths[-2] > 9 else 6
+        if not param_name.startswith(prefix):
+            return max_layer_id + 1, max_layer_id + 2
+        param_name = param_name[len(prefix):]
+        if param_name.startswith('downsample_layers'):
+            stage_id = int(param_name.split('.')[1])
+            if stage_id == 0:
+                layer_id = 0
+            elif stage_id == 1 or stage_id == 2:
+                layer_id = stage_id + 1
+            else:
+                layer_id = max_layer_id
+        elif param_name.startswith('stages'):
+            stage_id = int(param_name.split('.')[1])
+            block_id = int(param_name.split('.')[2])
+            if stage_id == 0 or stage_id == 1:
+                layer_id = stage_id + 1
+            elif stage_id == 2:
+                layer_id = 3 + block_id // 3
+            else:
+                layer_id = max_layer_id
+        else:
+            layer_id = max_layer_id + 1
+        return layer_id, max_layer_id + 2
+
+    # ---- checkpoint up-cycling (:660-727, :824-899) --------------------------------------------
+    def upcycle_state_dict(self, src, multi_input=False):
+        """Map a dense ConvNeXt detector checkpoint onto this module's keys: strip 'backbone.', copy each
+        dense pointwise_conv{1,2} into every expert of the MoE blocks, move the stem for MultiInput."""
+        out = {}
+        for k, v in src.items():
+            if not k.startswith('backbone.'):
+                continue
+            k = k[9:]
+            if multi_input and 'downsample_layers.0.0' in k:
+                out[k.replace('downsample_layers.0.0', 'dataset_stems.single')] = v
+            elif multi_input and 'downsample_layers.0.1' in k:
+                out[k.replace('downsample_layers.0.1', 'downsample_layers.0.0')] = v
+            elif 'pointwise_conv' in k:
+                parts = k.split('.')
+                stage_ind, block_ind = int(parts[1]), int(parts[2])
+                if block_ind in self.MoE_Block_inds[stage_ind]:
+                    for e in range(self.num_experts):
+                        out[k.replace('pointwise_conv', f'ffn.experts.{e}.pointwise_conv')] = v
+                else:
+                    out[k.replace('pointwise_conv', 'ffn.pointwise_conv')] = v
+            else:
+                out[k] = v
+        if out and next(iter(out)).startswith('module.'):
+            out = {k[7:]: v for k, v in out.items()}
+        return out
+
+    def init_weights(self):
+        cfg = self.init_cfg
+        if isinstance(cfg, dict) and cfg.get('type') == 'Pretrained' and cfg.get('checkpoint'):
+            ckpt = torch.load(cfg['checkpoint'], map_location='cpu')
+            sd = ckpt.get('state_dict', ckpt.get('model', ckpt))
+            sd = self.upcycle_state_dict(sd, multi_input=isinstance(self, ConvNeXt_moe_MultiInput))
+            print(self.load_state_dict(sd, strict=False))
+        # any other init_cfg: the reference constructor's own initialisation already ran
+
+
+@ROTATED_BACKBONES.register_module()
+class ConvNeXt_moe_MultiInput(ConvNeXt_moe):
+    def __init__(self, arch='tiny', in_channels=3, stem_patch_size=4, datasets=None,
+                 norm_cfg=dict(type='LN2d', eps=1e-6), act_cfg=dict(type='GELU'), linear_pw_conv=True,
+                 use_grn=False, drop_path_rate=0., layer_scale_init_value=1e-6, out_indices=[0, 1, 2, 3],
+                 MoE_Block_inds=[[], [], [], []], noisy_gating=True, num_experts=2, top_k=2, gate='cosine',
+                 frozen_stages=0, gap_before_final_norm=False, with_cp=False,
+                 init_cfg=[dict(type='TruncNormal', layer=['Conv2d', 'Linear'], std=.02, bias=0.),
+                           dict(type='Constant', layer=['LayerNorm'], val=1., bias=0.)]):
+        super().__init__(MoE_Block_inds=MoE_Block_inds, noisy_gating=noisy_gating, num_experts=num_experts,
+                         gate=gate, top_k=top_k, arch=arch, in_channels=in_channels,
+                         stem_patch_size=stem_patch_size, norm_cfg=norm_cfg, act_cfg=act_cfg,
+                         linear_pw_conv=linear_pw_conv, use_grn=use_grn, drop_path_rate=drop_path_rate,
+                         layer_scale_init_value=layer_scale_init_value, out_indices=out_indices,
+                         frozen_stages=frozen_stages, gap_before_final_norm=gap_before_final_norm,
+                         with_cp=with_cp, init_cfg=init_cfg)
+        self.downsample_layers[0] = nn.Sequential(build_LayerNorm2d_layer(norm_cfg, self.channels[0]))
+        self.datasets = ['single']
+        self.dataset_stems = nn.ModuleDict()
+        self.dataset_stems['single'] = nn.Conv2d(in_channels, self.channels[0], kernel_size=stem_patch_size,
+                                                 stride=stem_patch_size)
+
+    def _stem(self, x):
+        conv, ln = self.dataset_stems['single'], self.downsample_layers[0][0]
+        return Fn.StemFn.apply(x, conv.weight, conv.bias, ln.weight, ln.bias, ln.eps, self.stem_patch_size)
+
+    def forward(self, x, datasets=['single'], record=None):
+        if len(datasets) == 1:
+            x = [x]
+        x = torch.cat(list(x), dim=0)          # one shared stem for every modality (:798-801)
+        self._check_input(x)
+        return self._trunk(self._stem(x), record)

@@ -1,0 +1,128 @@
+// extern "C" boundary: thin forwarding layer from include/sm3det_b200.h to the C++ launchers.
+#include "../../include/sm3det_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.h"
+
+using namespace sm3;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int sm3_abi_version(void) { return SM3_ABI_VERSION; }
+const char* sm3_last_error(void) { return sm3::last_error(); }
+
+int sm3_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int sm3_gemm(const sm3_gemm_args* a, void* stream) {
+  if (!a) { set_last_error("sm3_gemm: null args"); return SM3_ERR_INVALID_ARG; }
+  gemm::Params p{};
+  p.A = a->A; p.a_smn = a->a_stride_mn; p.a_sk = a->a_stride_k;
+  p.B = a->B; p.b_smn = a->b_stride_mn; p.b_sk = a->b_stride_k; p.b_group_stride = a->b_group_stride;
+  p.a_row_index = a->a_row_index; p.b_k_index = a->b_k_index;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.BN = a->tile_n;
+  p.sched = a->sched; p.k_splits = a->k_splits; p.num_groups = a->num_groups;
+  p.tile_group = a->tile_group; p.num_m_tiles_dev = a->num_m_tiles;
+  p.seg_begin = a->seg_begin; p.seg_end = a->seg_end;
+  p.D = a->D; p.ldd = a->ldd; p.d_group_stride = a->d_group_stride;
+  p.bias = a->bias; p.bias_group_stride = a->bias_group_stride;
+  p.epi = a->epilogue;
+  p.aux_out = a->aux_out; p.aux_in = a->aux_in; p.ld_aux = a->ld_aux;
+  p.col_scale = a->col_scale; p.row_scale = a->row_scale;
+  p.resid = a->resid; p.ld_resid = a->ld_resid;
+  return gemm::launch(p, S(stream));
+}
+
+int sm3_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int64_t T, int32_t C,
+                      float eps, int32_t out_mode, int32_t H, int32_t W, void* stream) {
+  return layernorm_fwd(x, w, b, y, stats, T, C, eps, out_mode, H, W, S(stream));
+}
+int sm3_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* w, float* dx, float* dw,
+                      float* db, int64_t T, int32_t C, int32_t in_mode, int32_t H, int32_t W, int32_t dx_accum,
+                      void* stream) {
+  return layernorm_bwd(dy, x, stats, w, dx, dw, db, T, C, in_mode, H, W, dx_accum, S(stream));
+}
+int sm3_stem_fwd(const float* x, const float* wt, const float* bias, const float* lnw, const float* lnb, float* y,
+                 float* conv_out, float* stats, int32_t N, int32_t Cin, int32_t H, int32_t W, int32_t ps, int32_t C0,
+                 float eps, void* stream) {
+  return stem_fwd(x, wt, bias, lnw, lnb, y, conv_out, stats, N, Cin, H, W, ps, C0, eps, S(stream));
+}
+int sm3_stem_wgrad(const float* x, const float* du, float* dwt, float* dbias, int32_t N, int32_t Cin, int32_t H,
+                   int32_t W, int32_t ps, int32_t C0, void* stream) {
+  return stem_wgrad(x, du, dwt, dbias, N, Cin, H, W, ps, C0, S(stream));
+}
+int sm3_dwconv7_fwd(const float* x, const float* wt, const float* bias, const float* resid, float* y, int32_t N,
+                    int32_t H, int32_t W, int32_t C, void* stream) {
+  return dwconv7_fwd(x, wt, bias, resid, y, N, H, W, C, S(stream));
+}
+int sm3_dwconv7_wgrad(const float* x, const float* dy, float* dwt, float* dbias, int32_t N, int32_t H, int32_t W,
+                      int32_t C, void* stream) {
+  return dwconv7_wgrad(x, dy, dwt, dbias, N, H, W, C, S(stream));
+}
+
+int sm3_moe_router_blocks(int32_t T) { return router_blocks(T); }
+int sm3_moe_router(const sm3_router_args* a, void* stream) {
+  if (!a) { set_last_error("sm3_moe_router: null args"); return SM3_ERR_INVALID_ARG; }
+  RouterArgs r{};
+  r.v = a->v; r.wp = a->proj_weight; r.bp = a->proj_bias; r.sim = a->sim_matrix; r.temperature = a->temperature;
+  r.w_noise = a->w_noise; r.noise = a->noise;
+  r.T = a->T; r.C = a->C; r.P = a->P; r.E = a->E; r.k = a->k;
+  r.top_idx = a->top_idx; r.top_gate = a->top_gate; r.logits = a->logits; r.top_vals = a->top_vals; r.p_out = a->p_out;
+  r.partials = a->partials; r.nblocks = router_blocks(a->T);
+  return moe_router(r, S(stream));
+}
+int sm3_moe_plan(const sm3_plan_args* a, void* stream) {
+  if (!a) { set_last_error("sm3_moe_plan: null args"); return SM3_ERR_INVALID_ARG; }
+  PlanArgs p{};
+  p.partials = a->partials; p.nblocks = router_blocks(a->T);
+  p.T = a->T; p.E = a->E; p.k = a->k; p.max_m_tiles = a->max_m_tiles;
+  p.importance = a->importance; p.load = a->load; p.loss = a->loss;
+  p.counts = a->counts; p.seg_begin = a->seg_begin; p.seg_end = a->seg_end; p.cursor = a->cursor;
+  p.tile_group = a->tile_group; p.num_m_tiles = a->num_m_tiles;
+  return moe_plan(p, S(stream));
+}
+int sm3_moe_assign(const int32_t* top_idx, int32_t T, int32_t k, int32_t E, const int32_t* seg_begin, int32_t* cursor,
+                   int32_t* slot_of, int32_t* pair_token, void* stream) {
+  return moe_assign(top_idx, T, k, E, seg_begin, cursor, slot_of, pair_token, S(stream));
+}
+int sm3_moe_combine(const float* o, const int32_t* slot_of, const int32_t* top_idx, const float* gate,
+                    const float* gamma, const float* resid, const float* row_scale, float* out, float* y_opt,
+                    int32_t T, int32_t C, int32_t k, void* stream) {
+  return moe_combine(o, slot_of, top_idx, gate, gamma, resid, row_scale, out, y_opt, T, C, k, S(stream));
+}
+
+int sm3_moe_combine_bwd(const float* dout, const float* o, const int32_t* slot_of, const int32_t* top_idx,
+                        const float* gate, const float* gamma, const float* row_scale, float* d_o, float* dgate,
+                        float* dgamma, int32_t T, int32_t C, int32_t k, void* stream) {
+  return moe_combine_bwd(dout, o, slot_of, top_idx, gate, gamma, row_scale, d_o, dgate, dgamma, T, C, k, S(stream));
+}
+int sm3_moe_router_bwd(const sm3_router_bwd_args* a, void* stream) {
+  if (!a) { set_last_error("sm3_moe_router_bwd: null args"); return SM3_ERR_INVALID_ARG; }
+  RouterBwdArgs r{};
+  r.p = a->p; r.sim = a->sim_matrix; r.temperature = a->temperature; r.top_idx = a->top_idx; r.top_gate = a->top_gate;
+  r.dgate = a->dgate; r.logits = a->logits; r.importance = a->importance; r.loss_scale = a->loss_scale;
+  r.T = a->T; r.P = a->P; r.E = a->E; r.k = a->k; r.dp = a->dp; r.dsim_hat = a->dsim_hat; r.dtemperature = a->dtemperature;
+  return moe_router_bwd(r, S(stream));
+}
+int sm3_moe_router_bwd_finalize(const float* dsim_hat, const float* sim, float* dsim, int32_t P, int32_t E, void* stream) {
+  return moe_router_bwd_finalize(dsim_hat, sim, dsim, P, E, S(stream));
+}
+int sm3_colsum(const float* a, const float* b, const float* rs, const int32_t* seg_begin, const int32_t* seg_end,
+               int32_t G, float* out, int64_t rows, int32_t C, void* stream) {
+  return colsum(a, b, rs, seg_begin, seg_end, G, out, rows, C, S(stream));
+}
+int sm3_gather_sum(const float* src, const int32_t* slot_of, const float* add, float* out, int32_t T, int32_t C,
+                   int32_t k, void* stream) {
+  return gather_sum(src, slot_of, add, out, T, C, k, S(stream));
+}
+int sm3_scale_rows(const float* x, const float* rs, const float* cs, float* out, int64_t rows, int32_t C, void* stream) {
+  return scale_rows(x, rs, cs, out, rows, C, S(stream));
+}
+
+}  // extern "C"

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
+#include "../../include/sm3det_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "sm3det_b200 kernels are written for sm_100a only"
@@ -11,13 +12,7 @@
 namespace sm3 {
 
 // ---- error plumbing (thread-local message, C ABI returns negative codes) -------------------
-enum : int {
-  SM3_OK = 0,
-  SM3_ERR_INVALID_ARG = -1,
-  SM3_ERR_UNSUPPORTED_SHAPE = -2,
-  SM3_ERR_CUDA = -3,
-  SM3_ERR_WORKSPACE = -4,
-};
+// error codes: SM3_OK / SM3_ERR_* come from the public header
 
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError() -> SM3_ERR_CUDA (+ message)
@@ -59,3 +54,23 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
 }
 
 }  // namespace sm3
+
+// dispatch a kernel templated on V = C/32 (channels per lane)
+#define SM3_V_DISPATCH(V_, ...)                                          \
+  switch (V_) {                                                           \
+    case 1: { constexpr int V = 1; __VA_ARGS__; } break;                         \
+    case 2: { constexpr int V = 2; __VA_ARGS__; } break;                         \
+    case 3: { constexpr int V = 3; __VA_ARGS__; } break;                         \
+    case 4: { constexpr int V = 4; __VA_ARGS__; } break;                         \
+    case 5: { constexpr int V = 5; __VA_ARGS__; } break;                         \
+    case 6: { constexpr int V = 6; __VA_ARGS__; } break;                         \
+    case 8: { constexpr int V = 8; __VA_ARGS__; } break;                         \
+    case 10: { constexpr int V = 10; __VA_ARGS__; } break;                       \
+    case 12: { constexpr int V = 12; __VA_ARGS__; } break;                       \
+    case 16: { constexpr int V = 16; __VA_ARGS__; } break;                       \
+    case 20: { constexpr int V = 20; __VA_ARGS__; } break;                       \
+    case 24: { constexpr int V = 24; __VA_ARGS__; } break;                       \
+    case 32: { constexpr int V = 32; __VA_ARGS__; } break;                       \
+    default: ::sm3::set_last_error("unsupported channel count (C/32=%d)", V_); return SM3_ERR_UNSUPPORTED_SHAPE; \
+  }
+

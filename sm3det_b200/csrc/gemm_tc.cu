@@ -32,8 +32,9 @@ int launch(Params p, cudaStream_t stream) {
   if (!b_mn) SM3_REQUIRE(p.b_smn % 4 == 0 && p.K % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: K-major B needs K%%4==0, ldb%%4==0");
   else       SM3_REQUIRE(p.b_sk % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major B needs ldb%%4==0");
   SM3_REQUIRE(!(p.a_row_index && a_mn), SM3_ERR_INVALID_ARG, "gemm: row gather needs K-major A");
+  SM3_REQUIRE(!(p.b_k_index && !b_mn), SM3_ERR_INVALID_ARG, "gemm: k gather needs MN-major B");
   SM3_REQUIRE(p.ldd % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: ldd%%4");
-  if (p.epi & (EPI_GELU)) SM3_REQUIRE(!p.aux_out || (aligned16(p.aux_out) && p.ld_aux % 4 == 0), SM3_ERR_INVALID_ARG, "gemm: aux_out");
+  if (p.epi & (EPI_GELU | EPI_AUXSTORE)) SM3_REQUIRE(!p.aux_out || (aligned16(p.aux_out) && p.ld_aux % 4 == 0), SM3_ERR_INVALID_ARG, "gemm: aux_out");
   if (p.epi & EPI_DGELU) SM3_REQUIRE(p.aux_in && aligned16(p.aux_in) && p.ld_aux % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: aux_in");
   if (p.epi & EPI_BIAS) SM3_REQUIRE(p.bias && aligned16(p.bias) && p.bias_group_stride % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: bias");
   if (p.epi & EPI_COLSCALE) SM3_REQUIRE(p.col_scale && aligned16(p.col_scale), SM3_ERR_INVALID_ARG, "gemm: col_scale");

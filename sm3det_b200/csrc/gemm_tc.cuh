@@ -24,10 +24,10 @@ constexpr int MAX_BN = 256;
 constexpr int STAGES = 4;
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
-constexpr int NUM_PROD_WARPS = 8;
+constexpr int NUM_PROD_WARPS = 7;
 constexpr int FIRST_PROD_WARP = 5;
-constexpr int NUM_THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;  // 416
-constexpr int MAX_UNITS = 6;     // producer units per warp per k-block ((128+256)/8/8)
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;  // 384 = 12 warps (register file is allocated in groups of 4 warps)
+constexpr int MAX_UNITS = 7;     // producer units per warp per k-block: ceil((128+256)/8 / 7)
 
 constexpr uint32_t OFF_A_HI = 0;
 constexpr uint32_t OFF_A_LO = 8192;
@@ -48,6 +48,7 @@ enum Epi : int {
   EPI_ROWSCALE = 16,  // acc *= row_scale[m]
   EPI_RESID = 32,     // acc += resid[m,n]
   EPI_ATOMIC = 64,    // atomicAdd(D, acc) instead of store
+  EPI_AUXSTORE = 128, // aux_out[m,n] = acc (after bias), e.g. the pre-layer-scale FFN output
 };
 
 struct Params {
@@ -55,6 +56,7 @@ struct Params {
   const float* A; long long a_smn, a_sk;
   const float* B; long long b_smn, b_sk; long long b_group_stride;
   const int* a_row_index;   // optional gather of A rows (K-major A only); -1 -> zero row
+  const int* b_k_index;     // optional gather of B along the reduction index (MN-major B only); -1 -> zero
   int M, N, K, BN;
   // schedule
   int sched;
@@ -245,7 +247,7 @@ __device__ __forceinline__ UnitMap make_unit_map(const Params& p, bool a_mn, boo
   return um;
 }
 
-__global__ void __maxnreg__(144) gemm_bf16x3_kernel(const __grid_constant__ Params p) {
+__global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -307,6 +309,12 @@ __global__ void __maxnreg__(144) gemm_bf16x3_kernel(const __grid_constant__ Para
             const float4 b = ldg_f4(bias + col0 + i);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
           }
+        }
+        if ((p.epi & EPI_AUXSTORE) && p.aux_out) {
+          float* arow = p.aux_out + (long long)row * p.ld_aux + tl.n0 + col0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(arow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         if (p.epi & EPI_GELU) {
           if (p.aux_out) {
@@ -453,7 +461,9 @@ __global__ void __maxnreg__(144) gemm_bf16x3_kernel(const __grid_constant__ Para
           for (int h = 0; h < 2; ++h) {
             const int k = k0 + (pi >> 2) * 8 + (pi & 3) + 4 * h;
             if (k >= it.tl.k_end) continue;
-            r[i][h] = ldg_f4(base + (long long)k * s_k + (mn0 + mnl));
+            long long kk = k;
+            if (!is_a && p.b_k_index) { kk = __ldg(p.b_k_index + k); if (kk < 0) continue; }
+            r[i][h] = ldg_f4(base + kk * s_k + (mn0 + mnl));
           }
         }
       }

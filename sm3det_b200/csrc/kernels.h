@@ -1,0 +1,105 @@
+// Internal C++ launcher declarations (one per kernel family).  The public C ABI in
+// include/sm3det_b200.h (capi.cu) forwards to these.  All pointers are device pointers owned by
+// the caller; every launcher is stream-ordered, never allocates and never synchronises.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sm3 {
+
+const char* last_error();
+
+// norm.cu ----------------------------------------------------------------------------------------
+int layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, long long T, int C,
+                  float eps, int out_mode, int H, int W, cudaStream_t stream);
+int layernorm_bwd(const float* dy, const float* x, const float* stats, const float* w, float* dx, float* dw,
+                  float* db, long long T, int C, int in_mode, int H, int W, int dx_accum, cudaStream_t stream);
+int stem_fwd(const float* x, const float* wt, const float* bias, const float* lnw, const float* lnb, float* y,
+             float* conv_out, float* stats, int N, int Cin, int H, int W, int ps, int C0, float eps,
+             cudaStream_t stream);
+int stem_wgrad(const float* x, const float* du, float* dwt, float* dbias, int N, int Cin, int H, int W, int ps,
+               int C0, cudaStream_t stream);
+
+// stencil.cu -------------------------------------------------------------------------------------
+// wt: depthwise taps transposed to [49][C]
+int dwconv7_fwd(const float* x, const float* wt, const float* bias, const float* resid, float* y, int N, int H, int W,
+                int C, cudaStream_t stream);
+// dx (+)= corr(dy, flipped taps); the forward kernel is reused with flipped taps by the caller.
+int dwconv7_wgrad(const float* x, const float* dy, float* dwt, float* dbias, int N, int H, int W, int C,
+                  cudaStream_t stream);
+
+// moe.cu -----------------------------------------------------------------------------------------
+struct RouterArgs {
+  const float* v;        // [T,C] LN output
+  const float* wp;       // [P,C] cosine_projector.weight
+  const float* bp;       // [P]
+  const float* sim;      // [P,E] sim_matrix (un-normalised)
+  const float* temperature;  // [1]
+  const float* w_noise;  // [C,E] or null
+  const float* noise;    // [T,E] standard-normal draws or null (null => clean logits)
+  int T, C, P, E, k;
+  // outputs
+  int* top_idx;          // [T,k]  (-1 => dropped pair, gate underflowed to 0)
+  float* top_gate;       // [T,k]
+  float* logits;         // [T,E] optional (clean logits; needed by backward)
+  float* top_vals;       // [T,k+1] optional: selected (noisy) logits incl. the (k+1)-th threshold
+  float* p_out;          // [T,P] optional: projection Wp v + bp (saved for backward)
+  float* partials;       // [nblocks][3E] per-block importance / load / hard-count partial sums (workspace)
+  int nblocks;           // filled by router_blocks()
+};
+int router_blocks(int T);
+int moe_router(const RouterArgs& a, cudaStream_t stream);
+
+struct PlanArgs {
+  const float* partials; int nblocks;   // from the router
+  int T, E, k, max_m_tiles;
+  // outputs
+  float* importance;     // [E]
+  float* load;           // [E]
+  float* loss;           // [1]  = 1e-2 * (cv2(importance) + cv2(load))
+  int* counts;           // [E] pairs per expert (hard count of gate > 0)
+  int* seg_begin;        // [E] first slot of expert e (multiple of 128)
+  int* seg_end;          // [E] seg_begin + counts
+  int* cursor;           // [E] zeroed (used by moe_assign)
+  int* tile_group;       // [max_m_tiles]
+  int* num_m_tiles;      // [1]
+};
+int moe_plan(const PlanArgs& a, cudaStream_t stream);
+
+// pair (t,j) -> slot; writes pair_token[slot] = t (caller pre-fills pair_token with -1)
+int moe_assign(const int* top_idx, int T, int k, int E, const int* seg_begin, int* cursor, int* slot_of,
+               int* pair_token, cudaStream_t stream);
+
+// out[t,:] = resid[t,:] + rowscale[t] * gamma * sum_j gate[t,j] * o[slot_of[t,j],:]   (fixed j order)
+int moe_combine(const float* o, const int* slot_of, const int* top_idx, const float* gate, const float* gamma, const float* resid,
+                const float* row_scale, float* out, float* y_opt, int T, int C, int k, cudaStream_t stream);
+
+int moe_combine_bwd(const float* dout, const float* o, const int* slot_of, const int* top_idx, const float* gate,
+                    const float* gamma, const float* row_scale, float* d_o, float* dgate, float* dgamma, int T, int C,
+                    int k, cudaStream_t stream);
+
+struct RouterBwdArgs {
+  const float* p;            // [T,P] saved projection (pre-normalisation, incl. bias)
+  const float* sim;          // [P,E]
+  const float* temperature;  // [1]
+  const int* top_idx; const float* top_gate;   // [T,k]
+  const float* dgate;        // [T,k] from moe_combine_bwd
+  const float* logits;       // [T,E] clean logits saved by the router
+  const float* importance;   // [E]
+  const float* loss_scale;   // [1] device scalar: upstream grad of this layer's loss (or null)
+  int T, P, E, k;
+  float* dp;                 // [T,P] out
+  float* dsim_hat;           // [P,E] accumulated (pre-zeroed)
+  float* dtemperature;       // [1]  accumulated
+};
+int moe_router_bwd(const RouterBwdArgs& a, cudaStream_t stream);
+int moe_router_bwd_finalize(const float* dsim_hat, const float* sim, float* dsim, int P, int E, cudaStream_t stream);
+
+// reduce.cu --------------------------------------------------------------------------------------
+int colsum(const float* a, const float* b, const float* rs, const int* seg_begin, const int* seg_end, int G,
+           float* out, long long rows, int C, cudaStream_t stream);
+int gather_sum(const float* src, const int* slot_of, const float* add, float* out, int T, int C, int k,
+               cudaStream_t stream);
+int scale_rows(const float* x, const float* rs, const float* cs, float* out, long long rows, int C,
+               cudaStream_t stream);
+
+}  // namespace sm3

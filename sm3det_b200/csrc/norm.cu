@@ -1,0 +1,363 @@
+// LayerNorm-over-channels kernels (NHWC tokens) and the patchify stem, forward and backward.
+//
+// Replaces (reference convnext_moe.py): LayerNorm2d.forward :34-47 in all three places it is used --
+// the block norm after the depthwise conv (:351, channel_last), the downsample norms (:549-551) and
+// the per-stage output norms (:811-817, channel_first incl. the NHWC->NCHW permute+contiguous) --
+// and the 4x4/s4 stem Conv2d (:532-536 / :787-791).  F.layer_norm semantics: biased variance,
+// y = (x-mean)*rsqrt(var+eps)*w + b.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sm3 {
+
+// ------------------------------------------------------------------------------------------------
+// One warp per token.  lane holds channels lane, lane+32, ...  (C % 32 == 0, C <= 32*MAXV)
+constexpr int LN_MAXV = 32;  // C <= 1024
+
+enum LnOut : int { LN_OUT_NHWC = 0, LN_OUT_PATCH2 = 1, LN_OUT_NCHW = 2 };
+
+template <int V>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ b, float* __restrict__ y,
+                                                    float* __restrict__ stats, int T, int C, float eps,
+                                                    int out_mode, int H, int W) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= T) return;
+  const float* xr = x + (long long)warp * C;
+  float v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { v[i] = __ldg(xr + lane + 32 * i); s += v[i]; }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  if (stats && lane == 0) { stats[2 * (long long)warp] = mean; stats[2 * (long long)warp + 1] = rstd; }
+  float* yr;
+  if (out_mode == LN_OUT_PATCH2) {
+    // token (n,h,w) -> row (n, h/2, w/2), column block (h%2)*2 + (w%2)
+    const int wq = warp % W, hq = (warp / W) % H, n = warp / (W * H);
+    const long long row = ((long long)n * (H / 2) + hq / 2) * (W / 2) + wq / 2;
+    yr = y + row * (4LL * C) + (long long)((hq & 1) * 2 + (wq & 1)) * C;
+  } else {
+    yr = y + (long long)warp * C;
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = lane + 32 * i;
+    yr[c] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+  }
+}
+
+// LN + NHWC->NCHW: block = 32 consecutive tokens (same image row segment), 8 warps (4 tokens each).
+template <int V>
+__global__ void __launch_bounds__(256) ln_fwd_nchw_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, float* __restrict__ y,
+                                                         float* __restrict__ stats, int T, int C, float eps, int HW) {
+  extern __shared__ float tile[];  // [C][33]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t0 = (long long)blockIdx.x * 32;
+  for (int tt = warp; tt < 32; tt += 8) {
+    const long long t = t0 + tt;
+    if (t >= T) break;
+    const float* xr = x + t * C;
+    float v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { v[i] = __ldg(xr + lane + 32 * i); s += v[i]; }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (stats && lane == 0) { stats[2 * t] = mean; stats[2 * t + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = lane + 32 * i;
+      tile[c * 33 + tt] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+    }
+  }
+  __syncthreads();
+  // HW % 32 == 0 is required (H, W multiples of 32 upstream => every level has HW % 32 == 0 unless
+  // the level is smaller than 32 tokens; handled by the generic bound check below)
+  for (int c = warp; c < C; c += 8) {
+    const long long t = t0 + lane;
+    if (t < T) {
+      const long long n = t / HW, hw = t % HW;
+      y[(n * C + c) * HW + hw] = tile[c * 33 + lane];
+    }
+  }
+}
+
+int layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, long long T, int C,
+                  float eps, int out_mode, int H, int W, cudaStream_t stream) {
+  SM3_REQUIRE(x && w && b && y && T > 0, SM3_ERR_INVALID_ARG, "layernorm_fwd: null/empty argument");
+  SM3_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, SM3_ERR_UNSUPPORTED_SHAPE, "layernorm_fwd: C=%d must be a multiple of 32 <= 1024", C);
+  SM3_REQUIRE(T < (1LL << 31), SM3_ERR_UNSUPPORTED_SHAPE, "layernorm_fwd: too many tokens");
+  const int V_ = C / 32;
+  if (out_mode == LN_OUT_NCHW) {
+    SM3_REQUIRE(H > 0 && W > 0, SM3_ERR_INVALID_ARG, "layernorm_fwd: NCHW output needs H, W");
+    const int blocks = (int)((T + 31) / 32);
+    const size_t smem = (size_t)C * 33 * sizeof(float);
+    SM3_V_DISPATCH(V_, {
+      cudaFuncSetAttribute(ln_fwd_nchw_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      ln_fwd_nchw_kernel<V><<<blocks, 256, smem, stream>>>(x, w, b, y, stats, (int)T, C, eps, H * W);
+    });
+  } else {
+    if (out_mode == LN_OUT_PATCH2)
+      SM3_REQUIRE(H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, SM3_ERR_INVALID_ARG, "layernorm_fwd: patch output needs even H, W");
+    const int blocks = (int)((T + 7) / 8);
+    SM3_V_DISPATCH(V_, (ln_fwd_kernel<V><<<blocks, 256, 0, stream>>>(x, w, b, y, stats, (int)T, C, eps, out_mode, H, W)));
+  }
+  return check_launch("layernorm_fwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward.  dy is read through the same three layouts the forward wrote (in_mode); dx is NHWC.
+//   xhat = (x-mean)*rstd ; g = dy*w ; dx = rstd*(g - mean_c(g) - xhat*mean_c(g*xhat))
+//   dw += sum_t dy*xhat ; db += sum_t dy     (per-block partials in registers -> atomics per block)
+// If dx_accum != 0 the result is added to dx (residual branches meeting at one tensor).
+template <int V>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                    const float* __restrict__ stats, const float* __restrict__ w,
+                                                    float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                                    int T, int C, int in_mode, int H, int W, int dx_accum,
+                                                    int tokens_per_warp) {
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float adw[V], adb[V], wv[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { adw[i] = 0.f; adb[i] = 0.f; wv[i] = __ldg(w + lane + 32 * i); }
+  const long long tb = (long long)gwarp * tokens_per_warp;
+  for (int k = 0; k < tokens_per_warp; ++k) {
+    const long long t = tb + k;
+    if (t >= T) break;
+    const float mean = __ldg(stats + 2 * t), rstd = __ldg(stats + 2 * t + 1);
+    const float* xr = x + t * C;
+    float g[V], xh[V];
+    float s1 = 0.f, s2 = 0.f;
+    const int HW = H * W;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = lane + 32 * i;
+      float d;
+      if (in_mode == LN_OUT_NCHW) {
+        const long long n = t / HW, hw = t % HW;
+        d = __ldg(dy + (n * C + c) * HW + hw);
+      } else if (in_mode == LN_OUT_PATCH2) {
+        const int wq = (int)(t % W), hq = (int)((t / W) % H); const long long n = t / HW;
+        const long long row = (n * (H / 2) + hq / 2) * (W / 2) + wq / 2;
+        d = __ldg(dy + row * (4LL * C) + (long long)((hq & 1) * 2 + (wq & 1)) * C + c);
+      } else {
+        d = __ldg(dy + t * C + c);
+      }
+      xh[i] = (__ldg(xr + c) - mean) * rstd;
+      adw[i] += d * xh[i];
+      adb[i] += d;
+      g[i] = d * wv[i];
+      s1 += g[i];
+      s2 += g[i] * xh[i];
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    float* dxr = dx + t * C;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = lane + 32 * i;
+      const float r = rstd * (g[i] - s1 - xh[i] * s2);
+      dxr[c] = dx_accum ? dxr[c] + r : r;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    atomicAdd(dw + lane + 32 * i, adw[i]);
+    atomicAdd(db + lane + 32 * i, adb[i]);
+  }
+}
+
+int layernorm_bwd(const float* dy, const float* x, const float* stats, const float* w, float* dx, float* dw,
+                  float* db, long long T, int C, int in_mode, int H, int W, int dx_accum, cudaStream_t stream) {
+  SM3_REQUIRE(dy && x && stats && w && dx && dw && db && T > 0, SM3_ERR_INVALID_ARG, "layernorm_bwd: null/empty argument");
+  SM3_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, SM3_ERR_UNSUPPORTED_SHAPE, "layernorm_bwd: C=%d", C);
+  const int V_ = C / 32;
+  // ~ 8 warps/block, enough warps to fill the GPU, >= 16 tokens per warp to amortise the param atomics
+  long long warps = (long long)num_sms() * 32;
+  int tpw = (int)((T + warps - 1) / warps);
+  if (tpw < 16) tpw = 16;
+  warps = (T + tpw - 1) / tpw;
+  const int blocks = (int)((warps + 7) / 8);
+  SM3_V_DISPATCH(V_, (ln_bwd_kernel<V><<<blocks, 256, 0, stream>>>(dy, x, stats, w, dx, dw, db, (int)T, C, in_mode, H, W, dx_accum, tpw)));
+  return check_launch("layernorm_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: y[n,ho,wo,:] = LN( conv4x4s4(x)[n,:,ho,wo] )   x NCHW [N,Cin,H,W] -> NHWC [N,H/ps,W/ps,C0]
+// One warp computes 4 output pixels at a time; weights transposed in smem [K][C0], K = Cin*ps*ps.
+template <int V>
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wt /*[K][C0]*/,
+                                                      const float* __restrict__ bias, const float* __restrict__ lnw,
+                                                      const float* __restrict__ lnb, float* __restrict__ y,
+                                                      float* __restrict__ conv_out, float* __restrict__ stats,
+                                                      int N, int Cin, int H, int W, int ps, int C0, float eps) {
+  extern __shared__ float smem[];
+  const int K = Cin * ps * ps;
+  float* s_w = smem;                 // [K][C0]
+  float* s_p = smem + K * C0;        // [32 pixels][K+1]
+  const int Ho = H / ps, Wo = W / ps;
+  const long long P = (long long)N * Ho * Wo;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < K * C0; i += blockDim.x) s_w[i] = __ldg(wt + i);
+  const long long p0 = (long long)blockIdx.x * 32;
+  // gather 32 patches: element (pix, k=(c,i,j)) = x[n, c, ho*ps+i, wo*ps+j]
+  for (int idx = threadIdx.x; idx < 32 * K; idx += blockDim.x) {
+    const int k = idx / 32, pix = idx % 32;   // consecutive threads -> consecutive pixels (strided by ps in w)
+    const long long p = p0 + pix;
+    float val = 0.f;
+    if (p < P) {
+      const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho); const long long n = p / ((long long)Wo * Ho);
+      const int j = k % ps, i = (k / ps) % ps, c = k / (ps * ps);
+      val = __ldg(x + ((n * Cin + c) * H + ho * ps + i) * W + wo * ps + j);
+    }
+    s_p[pix * (K + 1) + k] = val;
+  }
+  __syncthreads();
+  // warp handles pixels warp*4 .. warp*4+3
+  float acc[4][V];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[q][i] = __ldg(bias + lane + 32 * i);
+  const float* pp = s_p + (warp * 4) * (K + 1);
+  for (int k = 0; k < K; ++k) {
+    float wv[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) wv[i] = s_w[k * C0 + lane + 32 * i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float pv = pp[q * (K + 1) + k];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[q][i] = fmaf(pv, wv[i], acc[q][i]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long p = p0 + warp * 4 + q;
+    if (p >= P) break;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += acc[q][i];
+    const float mean = warp_sum(s) / (float)C0;
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { const float d = acc[q][i] - mean; qq += d * d; }
+    const float rstd = rsqrtf(warp_sum(qq) / (float)C0 + eps);
+    if (stats && lane == 0) { stats[2 * p] = mean; stats[2 * p + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = lane + 32 * i;
+      if (conv_out) conv_out[p * C0 + c] = acc[q][i];
+      y[p * C0 + c] = (acc[q][i] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+    }
+  }
+}
+
+int stem_fwd(const float* x, const float* wt, const float* bias, const float* lnw, const float* lnb, float* y,
+             float* conv_out, float* stats, int N, int Cin, int H, int W, int ps, int C0, float eps,
+             cudaStream_t stream) {
+  SM3_REQUIRE(x && wt && bias && lnw && lnb && y, SM3_ERR_INVALID_ARG, "stem_fwd: null argument");
+  SM3_REQUIRE(H % ps == 0 && W % ps == 0, SM3_ERR_UNSUPPORTED_SHAPE, "stem_fwd: H,W must be multiples of the patch size");
+  SM3_REQUIRE(C0 % 32 == 0 && C0 <= 512, SM3_ERR_UNSUPPORTED_SHAPE, "stem_fwd: C0=%d must be a multiple of 32 <= 512", C0);
+  const int K = Cin * ps * ps;
+  const size_t smem = ((size_t)K * C0 + 32 * (K + 1)) * sizeof(float);
+  SM3_REQUIRE(smem <= 200 * 1024, SM3_ERR_UNSUPPORTED_SHAPE, "stem_fwd: patch weights do not fit shared memory");
+  const long long P = (long long)N * (H / ps) * (W / ps);
+  const int blocks = (int)((P + 31) / 32);
+  const int V_ = C0 / 32;
+  SM3_V_DISPATCH(V_, {
+    cudaFuncSetAttribute(stem_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    stem_fwd_kernel<V><<<blocks, 256, smem, stream>>>(x, wt, bias, lnw, lnb, y, conv_out, stats, N, Cin, H, W, ps, C0, eps);
+  });
+  return check_launch("stem_fwd");
+}
+
+// Stem weight gradient: dWt[k][c] += sum_p patch[p][k] * du[p][c] ; dbias[c] += sum_p du[p][c]
+// (du = gradient w.r.t. the conv output, NHWC).  Block = 256 pixels chunk, thread (k-slice, c).
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du,
+                                                        float* __restrict__ dwt, float* __restrict__ dbias, int N,
+                                                        int Cin, int H, int W, int ps, int C0, int pix_per_block) {
+  extern __shared__ float smem[];
+  const int K = Cin * ps * ps;
+  float* s_p = smem;             // [32][K+1]
+  float* s_d = smem + 32 * (K + 1);  // [32][C0]
+  const int Ho = H / ps, Wo = W / ps;
+  const long long P = (long long)N * Ho * Wo;
+  const long long pb = (long long)blockIdx.x * pix_per_block;
+  // each thread owns outputs (k, c) for idx = tid, tid+256, ... < K*C0 (+ bias row k = K)
+  const int total = (K + 1) * C0;
+  constexpr int MAXO = 32;
+  float acc[MAXO];
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) acc[o] = 0.f;
+  for (long long p0 = pb; p0 < pb + pix_per_block && p0 < P; p0 += 32) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * K; idx += blockDim.x) {
+      const int k = idx / 32, pix = idx % 32;
+      const long long p = p0 + pix;
+      float val = 0.f;
+      if (p < P && p < pb + pix_per_block) {
+        const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho); const long long n = p / ((long long)Wo * Ho);
+        const int j = k % ps, i = (k / ps) % ps, c = k / (ps * ps);
+        val = __ldg(x + ((n * Cin + c) * H + ho * ps + i) * W + wo * ps + j);
+      }
+      s_p[pix * (K + 1) + k] = val;
+    }
+    for (int idx = threadIdx.x; idx < 32 * C0; idx += blockDim.x) {
+      const int pix = idx / C0, c = idx % C0;
+      const long long p = p0 + pix;
+      s_d[idx] = (p < P && p < pb + pix_per_block) ? __ldg(du + p * C0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      const int idx = threadIdx.x + o * 256;
+      if (idx >= total) break;
+      const int k = idx / C0, c = idx % C0;
+      float a = 0.f;
+      if (k < K) {
+#pragma unroll 8
+        for (int pix = 0; pix < 32; ++pix) a = fmaf(s_p[pix * (K + 1) + k], s_d[pix * C0 + c], a);
+      } else {
+#pragma unroll 8
+        for (int pix = 0; pix < 32; ++pix) a += s_d[pix * C0 + c];
+      }
+      acc[o] += a;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) {
+    const int idx = threadIdx.x + o * 256;
+    if (idx >= total) break;
+    const int k = idx / C0, c = idx % C0;
+    if (k < K) atomicAdd(dwt + k * C0 + c, acc[o]);
+    else atomicAdd(dbias + c, acc[o]);
+  }
+}
+
+int stem_wgrad(const float* x, const float* du, float* dwt, float* dbias, int N, int Cin, int H, int W, int ps,
+               int C0, cudaStream_t stream) {
+  SM3_REQUIRE(x && du && dwt && dbias, SM3_ERR_INVALID_ARG, "stem_wgrad: null argument");
+  const int K = Cin * ps * ps;
+  SM3_REQUIRE((K + 1) * C0 <= 32 * 256, SM3_ERR_UNSUPPORTED_SHAPE, "stem_wgrad: (K+1)*C0=%d exceeds 8192", (K + 1) * C0);
+  const long long P = (long long)N * (H / ps) * (W / ps);
+  int blocks = num_sms() * 2;
+  long long ppb = (P + blocks - 1) / blocks;
+  ppb = (ppb + 31) / 32 * 32;
+  blocks = (int)((P + ppb - 1) / ppb);
+  const size_t smem = ((size_t)32 * (K + 1) + 32 * C0) * sizeof(float);
+  stem_wgrad_kernel<<<blocks, 256, smem, stream>>>(x, du, dwt, dbias, N, Cin, H, W, ps, C0, (int)ppb);
+  return check_launch("stem_wgrad");
+}
+
+}  // namespace sm3

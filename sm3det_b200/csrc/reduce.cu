@@ -1,0 +1,106 @@
+// Small HBM-bound helpers of the backward pass: column reductions (bias / layer-scale gradients),
+// the token-major gather-sum that mirrors the dispatch gather (autograd's index-backward of
+// x[_batch_index], reference convnext_moe.py:265, done without atomics), and a row/col scaling pass.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sm3 {
+
+// out[g][c] += sum_{r in [seg_begin[g], seg_end[g])} a[r,c] * (b ? b[r,c] : 1) * (rs ? rs[r] : 1)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                    const float* __restrict__ rs, const int* __restrict__ seg_begin,
+                                                    const int* __restrict__ seg_end, float* __restrict__ out,
+                                                    long long rows, int C, int chunks) {
+  const int g = blockIdx.z;
+  long long r0 = 0, r1 = rows;
+  if (seg_begin) { r0 = __ldg(seg_begin + g); r1 = __ldg(seg_end + g); }
+  const long long len = r1 - r0;
+  if (len <= 0) return;
+  const long long per = (len + chunks - 1) / chunks;
+  const long long cb = r0 + (long long)blockIdx.x * per;
+  const long long ce = min(r1, cb + per);
+  const int c = (blockIdx.y * 64 + (threadIdx.x & 63));
+  const int rl = threadIdx.x >> 6;  // 4 row lanes
+  const bool col_ok = c < C;
+  float acc = 0.f;
+  for (long long r = cb + rl; col_ok && r < ce; r += 4) {
+    float v = __ldg(a + r * C + c);
+    if (b) v *= __ldg(b + r * C + c);
+    if (rs) v *= __ldg(rs + r);
+    acc += v;
+  }
+  __shared__ float s[4][64];
+  s[rl][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    const float t = s[0][threadIdx.x] + s[1][threadIdx.x] + s[2][threadIdx.x] + s[3][threadIdx.x];
+    if (cb < ce && col_ok) atomicAdd(out + (long long)g * C + c, t);
+  }
+}
+
+int colsum(const float* a, const float* b, const float* rs, const int* seg_begin, const int* seg_end, int G,
+           float* out, long long rows, int C, cudaStream_t stream) {
+  SM3_REQUIRE(a && out && G >= 1 && C >= 1, SM3_ERR_INVALID_ARG, "colsum: bad argument");
+  SM3_REQUIRE((seg_begin == nullptr) == (seg_end == nullptr), SM3_ERR_INVALID_ARG, "colsum: seg_begin/seg_end");
+  const int gy = (C + 63) / 64;
+  long long chunks = (long long)num_sms() * 8 / ((long long)gy * G);
+  if (chunks < 1) chunks = 1;
+  if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
+  if (chunks < 1) chunks = 1;
+  dim3 grid((unsigned)chunks, (unsigned)gy, (unsigned)G);
+  colsum_kernel<<<grid, 256, 0, stream>>>(a, b, rs, seg_begin, seg_end, out, rows, C, (int)chunks);
+  return check_launch("colsum");
+}
+
+// out[t,:] = (add ? add[t,:] : 0) + sum_j src[slot_of[t,j], :]   (slot < 0 skipped)
+__global__ void __launch_bounds__(256) gather_sum_kernel(const float* __restrict__ src, const int* __restrict__ slot_of,
+                                                        const float* __restrict__ add, float* __restrict__ out,
+                                                        long long total, int C, int k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int Q = C >> 2;
+  const long long t = i / Q;
+  const int c = (int)(i % Q) * 4;
+  float4 y = add ? ldg_f4(add + t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < k; ++j) {
+    const int s = __ldg(slot_of + t * k + j);
+    if (s < 0) continue;
+    const float4 v = ldg_f4(src + (long long)s * C + c);
+    y.x += v.x; y.y += v.y; y.z += v.z; y.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + t * C + c) = y;
+}
+
+int gather_sum(const float* src, const int* slot_of, const float* add, float* out, int T, int C, int k,
+               cudaStream_t stream) {
+  SM3_REQUIRE(src && slot_of && out && C % 4 == 0, SM3_ERR_INVALID_ARG, "gather_sum: bad argument");
+  const long long total = (long long)T * (C / 4);
+  gather_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, slot_of, add, out, total, C, k);
+  return check_launch("gather_sum");
+}
+
+// out[r,c] = x[r,c] * (rs ? rs[r] : 1) * (cs ? cs[c] : 1)
+__global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ rs,
+                                                        const float* __restrict__ cs, float* __restrict__ out,
+                                                        long long total, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int Q = C >> 2;
+  const long long r = i / Q;
+  const int c = (int)(i % Q) * 4;
+  float4 v = ldg_f4(x + r * C + c);
+  const float s = rs ? __ldg(rs + r) : 1.0f;
+  float4 m = cs ? ldg_f4(cs + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  v.x *= s * m.x; v.y *= s * m.y; v.z *= s * m.z; v.w *= s * m.w;
+  *reinterpret_cast<float4*>(out + r * C + c) = v;
+}
+
+int scale_rows(const float* x, const float* rs, const float* cs, float* out, long long rows, int C,
+               cudaStream_t stream) {
+  SM3_REQUIRE(x && out && C % 4 == 0, SM3_ERR_INVALID_ARG, "scale_rows: bad argument");
+  const long long total = rows * (C / 4);
+  scale_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, rs, cs, out, total, C);
+  return check_launch("scale_rows");
+}
+
+}  // namespace sm3

@@ -1,0 +1,160 @@
+// 7x7 depthwise convolution on NHWC fp32 tensors (padding 3, stride 1), forward / dgrad / wgrad.
+//
+// Replaces nn.Conv2d(C, C, 7, padding=3, groups=C) of ConvNeXtBlock (reference convnext_moe.py
+// :311-312, applied :347) and autograd's depthwise dgrad/wgrad.  NHWC end-to-end removes the two
+// full-tensor permute copies per block (:350, :358).  Taps are passed transposed as wt[49][C] so a
+// warp reads 32 consecutive channel-quads (512 B) per tap.
+//
+// Forward: a thread owns 4 channels x WS consecutive output columns of one row, slides a
+// (WS+6)-wide register window over the 7 input rows: 7*(WS+6) float4 loads for 49*WS*4 FMAs.
+// dgrad is the same kernel on dy with the taps flipped (the caller passes wt_flipped).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sm3 {
+
+constexpr int DW_WS = 8;
+
+__global__ void __launch_bounds__(256) dwconv7_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                         const float* __restrict__ bias, const float* __restrict__ resid,
+                                                         float* __restrict__ y, int N, int H, int W, int C, int strips,
+                                                         long long total) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= total) return;
+  const int Q = C >> 2;
+  const int q = (int)(tid % Q);
+  long long r = tid / Q;
+  const int s = (int)(r % strips); r /= strips;
+  const int h = (int)(r % H);
+  const int n = (int)(r / H);
+  const int w0 = s * DW_WS;
+  const int c = q * 4;
+
+  float4 acc[DW_WS];
+  const float4 b = bias ? ldg_f4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int o = 0; o < DW_WS; ++o) acc[o] = b;
+
+  const float* xn = x + (long long)n * H * W * C + c;
+#pragma unroll 1
+  for (int i = 0; i < 7; ++i) {
+    const int hi = h + i - 3;
+    if (hi < 0 || hi >= H) continue;
+    float4 wv[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) wv[j] = ldg_f4(wt + (i * 7 + j) * C + c);
+    const float* xr = xn + (long long)hi * W * C;
+#pragma unroll
+    for (int jj = 0; jj < DW_WS + 6; ++jj) {
+      const int wi = w0 + jj - 3;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (wi >= 0 && wi < W) xv = ldg_f4(xr + (long long)wi * C);
+#pragma unroll
+      for (int o = 0; o < DW_WS; ++o) {
+        const int j = jj - o;
+        if (j >= 0 && j < 7) {
+          acc[o].x = fmaf(xv.x, wv[j].x, acc[o].x);
+          acc[o].y = fmaf(xv.y, wv[j].y, acc[o].y);
+          acc[o].z = fmaf(xv.z, wv[j].z, acc[o].z);
+          acc[o].w = fmaf(xv.w, wv[j].w, acc[o].w);
+        }
+      }
+    }
+  }
+  const long long rowoff = (((long long)n * H + h) * W) * C + c;
+  float* yr = y + rowoff;
+#pragma unroll
+  for (int o = 0; o < DW_WS; ++o)
+    if (w0 + o < W) {
+      float4 v = acc[o];
+      if (resid) { const float4 r = ldg_f4(resid + rowoff + (long long)(w0 + o) * C); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+      *reinterpret_cast<float4*>(yr + (long long)(w0 + o) * C) = v;
+    }
+}
+
+int dwconv7_fwd(const float* x, const float* wt, const float* bias, const float* resid, float* y, int N, int H, int W,
+                int C, cudaStream_t stream) {
+  SM3_REQUIRE(x && wt && y, SM3_ERR_INVALID_ARG, "dwconv7_fwd: null argument");
+  SM3_REQUIRE(C % 4 == 0 && N > 0 && H > 0 && W > 0, SM3_ERR_UNSUPPORTED_SHAPE, "dwconv7_fwd: C=%d must be a multiple of 4", C);
+  const int strips = (W + DW_WS - 1) / DW_WS;
+  const long long total = (long long)N * H * strips * (C / 4);
+  const long long blocks = (total + 255) / 256;
+  SM3_REQUIRE(blocks < (1LL << 31), SM3_ERR_UNSUPPORTED_SHAPE, "dwconv7_fwd: tensor too large");
+  dwconv7_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, wt, bias, resid, y, N, H, W, C, strips, total);
+  return check_launch("dwconv7_fwd");
+}
+
+// wgrad: dwt[i*7+j][c] += sum_{n,h,w} x[n,h+i-3,w+j-3,c] * dy[n,h,w,c] ; dbias[c] += sum dy
+// Thread = (channel quad, tap row i) for a band of output rows; sliding 7-wide x window along w.
+__global__ void __launch_bounds__(224) dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           float* __restrict__ dwt, float* __restrict__ dbias, int N,
+                                                           int H, int W, int C, int rows_per_band, int bands_per_img) {
+  const int ql = threadIdx.x & 31;
+  const int i = threadIdx.x >> 5;               // tap row 0..6
+  const int q = blockIdx.y * 32 + ql;
+  if (q * 4 >= C) return;
+  const int c = q * 4;
+  const int n = blockIdx.x / bands_per_img;
+  const int h0 = (blockIdx.x % bands_per_img) * rows_per_band;
+  const int h1 = min(H, h0 + rows_per_band);
+  float4 acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* xn = x + (long long)n * H * W * C + c;
+  const float* dn = dy + (long long)n * H * W * C + c;
+  for (int h = h0; h < h1; ++h) {
+    const int hi = h + i - 3;
+    if (hi < 0 || hi >= H) continue;       // (bias is accumulated by the i == 3 role, always in range)
+    const float* xr = xn + (long long)hi * W * C;
+    const float* dr = dn + (long long)h * W * C;
+    float4 win[7];                          // x[hi, w-3 .. w+3]
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int wi = j - 3;
+      win[j] = (wi >= 0 && wi < W) ? ldg_f4(xr + (long long)wi * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int w = 0; w < W; ++w) {
+      const float4 d = ldg_f4(dr + (long long)w * C);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        acc[j].x = fmaf(win[j].x, d.x, acc[j].x); acc[j].y = fmaf(win[j].y, d.y, acc[j].y);
+        acc[j].z = fmaf(win[j].z, d.z, acc[j].z); acc[j].w = fmaf(win[j].w, d.w, acc[j].w);
+      }
+      if (i == 3) { accb.x += d.x; accb.y += d.y; accb.z += d.z; accb.w += d.w; }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+      const int wn = w + 4;
+      win[6] = (wn < W) ? ldg_f4(xr + (long long)wn * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    float* p = dwt + (i * 7 + j) * C + c;
+    atomicAdd(p, acc[j].x); atomicAdd(p + 1, acc[j].y); atomicAdd(p + 2, acc[j].z); atomicAdd(p + 3, acc[j].w);
+  }
+  if (i == 3 && dbias) {
+    atomicAdd(dbias + c, accb.x); atomicAdd(dbias + c + 1, accb.y);
+    atomicAdd(dbias + c + 2, accb.z); atomicAdd(dbias + c + 3, accb.w);
+  }
+}
+
+int dwconv7_wgrad(const float* x, const float* dy, float* dwt, float* dbias, int N, int H, int W, int C,
+                  cudaStream_t stream) {
+  SM3_REQUIRE(x && dy && dwt, SM3_ERR_INVALID_ARG, "dwconv7_wgrad: null argument");
+  SM3_REQUIRE(C % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "dwconv7_wgrad: C=%d must be a multiple of 4", C);
+  const int gy = (C / 4 + 31) / 32;
+  // enough bands to fill the GPU ~4x, at least 1 row per band
+  long long want = (long long)num_sms() * 4 / gy;
+  if (want < 1) want = 1;
+  int bands_per_img = (int)((want + N - 1) / N);
+  if (bands_per_img > H) bands_per_img = H;
+  if (bands_per_img < 1) bands_per_img = 1;
+  const int rows_per_band = (H + bands_per_img - 1) / bands_per_img;
+  bands_per_img = (H + rows_per_band - 1) / rows_per_band;
+  dim3 grid((unsigned)(N * bands_per_img), (unsigned)gy);
+  dwconv7_wgrad_kernel<<<grid, 224, 0, stream>>>(x, dy, dwt, dbias, N, H, W, C, rows_per_band, bands_per_img);
+  return check_launch("dwconv7_wgrad");
+}
+
+}  // namespace sm3

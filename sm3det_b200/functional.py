@@ -1,0 +1,289 @@
+"""autograd.Function wrappers: one per fused stage of the backbone, forward and hand-written backward.
+
+Each Function only sequences C-ABI kernel calls (sm3det_b200.ops); tensors stay NHWC fp32 between
+stages.  What each one replaces in the reference (mmrotate/models/backbones/convnext_moe.py):
+  StemFn        dataset_stems['single'] + downsample_layers[0]            :783-791, :800-806
+  DownsampleFn  Sequential(LayerNorm2d, Conv2d(2, stride 2))              :549-558, :806
+  DenseBlockFn  ConvNeXtBlock._inner_forward with FFN                     :343-372, :397-405
+  MoEBlockFn    ConvNeXtBlock._inner_forward with MoE_layer               :343-372, :226-293
+  OutNormFn     norm{i}(x) channel_first incl. permute+contiguous         :811-817, :34-47
+Backward follows SURVEY.md Appendix F (what autograd derives for the reference).
+
+The only torch arithmetic left in this file is O(#parameters) glue on weight-sized tensors
+(transposing 7x7 taps, flipping them for dgrad, multiplying a [C] vector by gamma).
+"""
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import (EPI_AUXSTORE, EPI_COLSCALE, EPI_DGELU, EPI_GELU, EPI_RESID, EPI_ROWSCALE, LN_NCHW, LN_NHWC, LN_PATCH2)
+
+
+def _zeros_like_param(p):
+    return torch.zeros(p.shape, device=p.device, dtype=torch.float32)
+
+
+def _taps(dww):            # [C,1,7,7] -> [49][C]
+    return dww.reshape(dww.shape[0], 49).t().contiguous()
+
+
+def _taps_flipped(dww):    # correlation taps for dgrad
+    return dww.flip(2, 3).reshape(dww.shape[0], 49).t().contiguous()
+
+
+class StemFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, lnw, lnb, eps, ps):
+        C0 = w.shape[0]
+        wt = w.reshape(C0, -1).t().contiguous()
+        train = any(ctx.needs_input_grad)
+        x = x.contiguous().float()
+        y, conv, stats = ops.stem_fwd(x, wt, b, lnw, lnb, eps, ps, save=train)
+        if train:
+            ctx.save_for_backward(x, conv, stats, lnw)
+            ctx.ps = ps
+            ctx.wshape = tuple(w.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, conv, stats, lnw = ctx.saved_tensors
+        dy = dy.contiguous()
+        C0 = lnw.shape[0]
+        T = conv.numel() // C0
+        dlnw, dlnb = _zeros_like_param(lnw), _zeros_like_param(lnw)
+        du = ops.layernorm_bwd(dy, conv, stats, lnw, dlnw, dlnb, tokens=T, C=C0)
+        K = ctx.wshape[1] * ctx.wshape[2] * ctx.wshape[3]
+        dwt = torch.zeros((K, C0), device=x.device, dtype=torch.float32)
+        db = torch.zeros((C0,), device=x.device, dtype=torch.float32)
+        ops.stem_wgrad(x, du, dwt, db, ctx.ps)
+        dw = dwt.t().reshape(ctx.wshape).contiguous()
+        return None, dw, db, dlnw, dlnb, None, None
+
+
+class DownsampleFn(Function):
+    @staticmethod
+    def forward(ctx, x, lnw, lnb, w, b, eps):
+        N, H, W, C = x.shape
+        Co = w.shape[0]
+        T = N * H * W
+        train = any(ctx.needs_input_grad)
+        xn = torch.empty((T // 4, 4 * C), device=x.device, dtype=torch.float32)
+        _, stats = ops.layernorm_fwd(x, lnw, lnb, eps, tokens=T, C=C, out=xn, out_mode=LN_PATCH2, H=H, W=W,
+                                     save_stats=train)
+        w2 = w.permute(0, 2, 3, 1).reshape(Co, 4 * C).contiguous()      # [Co, (kh, kw, ci)]
+        y = ops.linear_fwd(xn, w2, b)
+        if train:
+            ctx.save_for_backward(x, stats, xn, lnw, w2)
+            ctx.dims = (N, H, W, C, Co)
+        return y.view(N, H // 2, W // 2, Co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, xn, lnw, w2 = ctx.saved_tensors
+        N, H, W, C, Co = ctx.dims
+        T = N * H * W
+        dy2 = dy.contiguous().view(T // 4, Co)
+        dxn = ops.linear_dgrad(dy2, w2)
+        dw2 = torch.zeros_like(w2)
+        ops.linear_wgrad(dy2, xn, dw2)
+        db = torch.zeros((Co,), device=x.device, dtype=torch.float32)
+        ops.colsum(dy2, db, rows=T // 4, Cc=Co)
+        dlnw, dlnb = _zeros_like_param(lnw), _zeros_like_param(lnw)
+        dx = ops.layernorm_bwd(dxn, x, stats, lnw, dlnw, dlnb, tokens=T, C=C, in_mode=LN_PATCH2, H=H, W=W)
+        dw = dw2.view(Co, 2, 2, C).permute(0, 3, 1, 2).contiguous()
+        return dx.view(N, H, W, C), dlnw, dlnb, dw, db, None
+
+
+class OutNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        N, H, W, C = x.shape
+        T = N * H * W
+        train = any(ctx.needs_input_grad)
+        y = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
+        _, stats = ops.layernorm_fwd(x, w, b, eps, tokens=T, C=C, out=y, out_mode=LN_NCHW, H=H, W=W, save_stats=train)
+        if train:
+            ctx.save_for_backward(x, stats, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, w = ctx.saved_tensors
+        N, H, W, C = x.shape
+        dw, db = _zeros_like_param(w), _zeros_like_param(w)
+        dx = ops.layernorm_bwd(dy.contiguous(), x, stats, w, dw, db, tokens=N * H * W, C=C, in_mode=LN_NCHW, H=H, W=W)
+        return dx.view(N, H, W, C), dw, db, None
+
+
+def _block_front(x, dww, dwb, lnw, lnb, eps, train):
+    N, H, W, C = x.shape
+    u = ops.dwconv7(x, _taps(dww), dwb)
+    v, stats = ops.layernorm_fwd(u, lnw, lnb, eps, tokens=N * H * W, C=C, save_stats=train)
+    return u, v.view(N * H * W, C), stats
+
+
+def _block_front_bwd(dv, dout, x, u, stats, dww, lnw):
+    """LN backward -> depthwise dgrad (+ shortcut gradient) and the depthwise/LN parameter grads."""
+    N, H, W, C = x.shape
+    T = N * H * W
+    dlnw, dlnb = _zeros_like_param(lnw), _zeros_like_param(lnw)
+    du = ops.layernorm_bwd(dv, u, stats, lnw, dlnw, dlnb, tokens=T, C=C).view(N, H, W, C)
+    dx = ops.dwconv7(du, _taps_flipped(dww), None, resid=dout)
+    ddwt = torch.zeros((49, C), device=x.device, dtype=torch.float32)
+    ddwb = torch.zeros((C,), device=x.device, dtype=torch.float32)
+    ops.dwconv7_wgrad(x, du, ddwt, ddwb)
+    ddww = ddwt.t().reshape(C, 1, 7, 7).contiguous()
+    return dx, ddww, ddwb, dlnw, dlnb
+
+
+class DenseBlockFn(Function):
+    @staticmethod
+    def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps):
+        N, H, W, C = x.shape
+        T = N * H * W
+        train = any(ctx.needs_input_grad)
+        u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
+        h = torch.empty((T, 4 * C), device=x.device, dtype=torch.float32) if train else None
+        a = ops.linear_fwd(v, w1, b1, epilogue=EPI_GELU, aux_out=h)
+        y2 = torch.empty((T, C), device=x.device, dtype=torch.float32) if train else None
+        epi = EPI_COLSCALE | EPI_RESID | (EPI_ROWSCALE if row_scale is not None else 0) | (EPI_AUXSTORE if train else 0)
+        out = ops.linear_fwd(a, w2, b2, epilogue=epi, aux_out=y2, col_scale=gamma, row_scale=row_scale,
+                             resid=x.view(T, C))
+        if train:
+            ctx.save_for_backward(x, u, stats, v, h, a, y2, dww, lnw, w1, w2, gamma, row_scale)
+        return out.view(N, H, W, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, u, stats, v, h, a, y2, dww, lnw, w1, w2, gamma, rs = ctx.saved_tensors
+        N, H, W, C = x.shape
+        T = N * H * W
+        dout = dout.contiguous()
+        dz = dout.view(T, C)
+        dev = x.device
+        dgamma = torch.zeros((C,), device=dev, dtype=torch.float32)
+        ops.colsum(dz, dgamma, rows=T, Cc=C, b=y2, row_scale=rs)
+        csum = torch.zeros((C,), device=dev, dtype=torch.float32)
+        ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
+        db2 = csum * gamma
+        w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
+        dh = ops.linear_dgrad(dz, w2g, epilogue=EPI_DGELU | (EPI_ROWSCALE if rs is not None else 0), aux_in=h,
+                              row_scale=rs)
+        dzs = dz if rs is None else ops.scale_rows(dz, row_scale=rs)
+        dw2 = torch.zeros_like(w2)
+        ops.linear_wgrad(dzs, a, dw2, row_scale=gamma)
+        dw1 = torch.zeros_like(w1)
+        ops.linear_wgrad(dh, v, dw1)
+        db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
+        ops.colsum(dh, db1, rows=T, Cc=4 * C)
+        dv = ops.linear_dgrad(dh, w1)
+        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
+        return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None
+
+
+def stack_expert_params(params):
+    """Make E same-shaped parameters views of one contiguous [E, ...] buffer (grouped-GEMM layout).
+
+    Parameter objects (and therefore optimizer state, named_parameters() and state_dict keys) are
+    untouched; only ``.data`` is re-pointed.  No-op when they are already adjacent in memory.
+    """
+    base = params[0]
+    step = base.numel() * base.element_size()
+    if all(p.is_contiguous() and p.data_ptr() == base.data_ptr() + i * step for i, p in enumerate(params)):
+        return
+    with torch.no_grad():
+        flat = torch.stack([p.data for p in params]).contiguous()
+        for i, p in enumerate(params):
+            p.data = flat[i]
+
+
+class MoEBlockFn(Function):
+    """x -> dwconv -> LN -> router/plan/assign -> grouped expert GEMMs -> combine (+gamma, +shortcut)."""
+
+    @staticmethod
+    def forward(ctx, x, dww, dwb, lnw, lnb, gamma, wp, bp, sim, tau, w_noise, row_scale, noise, eps, E, k, record,
+                *experts):
+        N, H, W, C = x.shape
+        T = N * H * W
+        w1s, b1s, w2s, b2s = experts[0:E], experts[E:2 * E], experts[2 * E:3 * E], experts[3 * E:4 * E]
+        train = any(ctx.needs_input_grad)
+        u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
+        r = ops.moe_router(v, wp, bp, sim, tau, T=T, Cc=C, E=E, k=k, w_noise=w_noise, noise=noise, save=train)
+        plan = ops.moe_plan(r['partials'], T=T, E=E, k=k)
+        slot_of, pair_token = ops.moe_assign(r['top_idx'], plan, T=T, E=E, k=k)
+        R = plan['max_rows']
+        grouped = (plan['tile_group'], plan['num_m_tiles'])
+        h = torch.empty((R, 4 * C), device=x.device, dtype=torch.float32) if train else None
+        a = ops.linear_fwd(v, w1s[0], b1s[0], epilogue=EPI_GELU, aux_out=h, row_index=pair_token, rows=R,
+                           grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=4 * C)
+        o = ops.linear_fwd(a, w2s[0], b2s[0], rows=R, grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=C)
+        out, y = ops.moe_combine(o, slot_of, r['top_idx'], r['top_gate'], gamma, x.view(T, C), row_scale, T=T, Cc=C,
+                                 k=k, want_y=record is not None)
+        if record is not None:
+            record.append(dict(v=v, top_idx=r['top_idx'], top_gate=r['top_gate'], importance=plan['importance'],
+                               load=plan['load'], loss=plan['loss'], y=y, counts=plan['counts']))
+        if train:
+            if noise is not None:
+                ctx.noisy = True
+            else:
+                ctx.noisy = False
+            ctx.save_for_backward(x, u, stats, v, h, a, o, dww, lnw, gamma, wp, sim, tau, row_scale, r['top_idx'],
+                                  r['top_gate'], r['logits'], r['p'], slot_of, pair_token, plan['importance'],
+                                  plan['seg_begin'], plan['seg_end'], plan['tile_group'], plan['num_m_tiles'],
+                                  w1s[0], w2s[0])
+            ctx.E, ctx.k, ctx.R = E, k, R
+            ctx.has_noise_param = w_noise is not None
+        return out.view(N, H, W, C), plan['loss'].reshape(())
+
+    @staticmethod
+    def backward(ctx, dout, dloss):
+        (x, u, stats, v, h, a, o, dww, lnw, gamma, wp, sim, tau, rs, top_idx, top_gate, logits, p, slot_of, pair_token,
+         importance, seg_begin, seg_end, tile_group, num_m_tiles, w1, w2) = ctx.saved_tensors
+        if ctx.noisy:
+            raise NotImplementedError('sm3det_b200: backward through noisy gating is not implemented yet; '
+                                      'construct the backbone with noisy_gating=False for training')
+        E, k, R = ctx.E, ctx.k, ctx.R
+        N, H, W, C = x.shape
+        T = N * H * W
+        dev = x.device
+        dout = dout.contiguous()
+        dz = dout.view(T, C)
+        grouped = (tile_group, num_m_tiles)
+        segs = (seg_begin, seg_end)
+        # combine / layer scale / shortcut
+        d_o = torch.zeros((R, C), device=dev, dtype=torch.float32)
+        dgamma = torch.zeros((C,), device=dev, dtype=torch.float32)
+        dgate = ops.moe_combine_bwd(dz, o, slot_of, top_idx, top_gate, gamma, rs, d_o, dgamma, T=T, Cc=C, k=k)
+        # experts (grouped over the padded expert segments)
+        dh = torch.zeros((R, 4 * C), device=dev, dtype=torch.float32)
+        ops.linear_dgrad(d_o, w2, epilogue=EPI_DGELU, aux_in=h, out=dh, grouped=grouped, w_group_stride=4 * C * C)
+        dw2s = torch.zeros((E, C, 4 * C), device=dev, dtype=torch.float32)
+        ops.linear_wgrad(d_o, a, dw2s, rows=R, segs=segs, num_groups=E)
+        db2s = torch.zeros((E, C), device=dev, dtype=torch.float32)
+        ops.colsum(d_o, db2s, rows=R, Cc=C, segs=segs, groups=E)
+        dw1s = torch.zeros((E, 4 * C, C), device=dev, dtype=torch.float32)
+        ops.linear_wgrad(dh, v, dw1s, rows=R, x_row_index=pair_token, segs=segs, num_groups=E)
+        db1s = torch.zeros((E, 4 * C), device=dev, dtype=torch.float32)
+        ops.colsum(dh, db1s, rows=R, Cc=4 * C, segs=segs, groups=E)
+        dxp = torch.zeros((R, C), device=dev, dtype=torch.float32)
+        ops.linear_dgrad(dh, w1, out=dxp, grouped=grouped, w_group_stride=4 * C * C)
+        # router
+        P = wp.shape[0]
+        dtau = torch.zeros((1,), device=dev, dtype=torch.float32)
+        dsim = torch.zeros((P, E), device=dev, dtype=torch.float32)
+        lscale = dloss.reshape(1).contiguous().float()
+        dp = ops.moe_router_bwd(p, sim, tau, top_idx, top_gate, dgate, logits, importance, lscale, dsim, dtau, T=T,
+                                E=E, k=k)
+        dwp = torch.zeros_like(wp)
+        ops.linear_wgrad(dp, v, dwp)
+        dbp = torch.zeros((P,), device=dev, dtype=torch.float32)
+        ops.colsum(dp, dbp, rows=T, Cc=P)
+        dv_r = ops.linear_dgrad(dp, wp)
+        dv = ops.gather_sum(dxp, slot_of, dv_r, T=T, Cc=C, k=k)
+        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
+        dwn = torch.zeros((C, E), device=dev, dtype=torch.float32) if ctx.has_noise_param else None
+        grads_e = [dw1s[e] for e in range(E)] + [db1s[e] for e in range(E)] + [dw2s[e] for e in range(E)] + \
+                  [db2s[e] for e in range(E)]
+        return (dx, ddww, ddwb, dlnw, dlnb, dgamma, dwp, dbp, dsim, dtau, dwn, None, None, None, None, None, None,
+                *grads_e)

@@ -1,0 +1,282 @@
+"""Thin, allocation-only wrappers around the C-ABI kernels (one Python function per entry point).
+
+PyTorch is used here for device memory (``torch.empty``), the current CUDA stream and nothing else;
+all arithmetic happens in ``libsm3det_b200.so``.  Every wrapper validates that its tensors are
+fp32/int32, contiguous and on the current CUDA device, then passes raw pointers.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+SCHED_DENSE, SCHED_GROUPED, SCHED_SPLITK = 0, 1, 2
+EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_COLSCALE, EPI_ROWSCALE, EPI_RESID, EPI_ATOMIC, EPI_AUXSTORE = 1, 2, 4, 8, 16, 32, 64, 128
+LN_NHWC, LN_PATCH2, LN_NCHW = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor], dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('sm3det_b200 ops need CUDA tensors (no CPU fallback exists)')
+    if t.dtype != dtype:
+        raise TypeError(f'expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError('expected a contiguous tensor')
+    return t.data_ptr()
+
+
+def _pi(t):
+    return _p(t, torch.int32)
+
+
+def num_sms() -> int:
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a_row_index=None, b_k_index=None,
+         sched=SCHED_DENSE, k_splits=1, num_groups=1, tile_group=None, num_m_tiles=None, seg_begin=None,
+         seg_end=None, d_group_stride=0, bias=None, bias_group_stride=0, epilogue=0, aux_out=None, aux_in=None,
+         ld_aux=0, col_scale=None, row_scale=None, resid=None, ld_resid=0, tile_n=0):
+    lib = _lib.load()
+    a = _lib.GemmArgs()
+    a.A = _p(A); a.a_stride_mn = a_smn; a.a_stride_k = a_sk
+    a.B = _p(B); a.b_stride_mn = b_smn; a.b_stride_k = b_sk; a.b_group_stride = b_group_stride
+    a.a_row_index = _pi(a_row_index); a.b_k_index = _pi(b_k_index)
+    a.M, a.N, a.K = M, N, K
+    a.tile_n = tile_n; a.sched = sched; a.k_splits = k_splits; a.num_groups = num_groups
+    a.tile_group = _pi(tile_group); a.num_m_tiles = _pi(num_m_tiles)
+    a.seg_begin = _pi(seg_begin); a.seg_end = _pi(seg_end)
+    a.D = _p(D); a.ldd = ldd; a.d_group_stride = d_group_stride
+    a.bias = _p(bias); a.bias_group_stride = bias_group_stride
+    a.epilogue = epilogue
+    a.aux_out = _p(aux_out); a.aux_in = _p(aux_in); a.ld_aux = ld_aux
+    a.col_scale = _p(col_scale); a.row_scale = _p(row_scale)
+    a.resid = _p(resid); a.ld_resid = ld_resid
+    _lib.check(lib.sm3_gemm(C.byref(a), _stream()), 'sm3_gemm')
+    return D
+
+
+def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale=None, row_scale=None, resid=None,
+               row_index=None, rows=None, grouped=None, w_group_stride=0, bias_group_stride=0):
+    """out[M,N] = epi(x[M,K] @ w[N,K]^T).  grouped = (tile_group, num_m_tiles) for expert segments."""
+    K = x.shape[-1]
+    N = w.shape[-2]
+    M = rows if rows is not None else x.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    epi = epilogue | (EPI_BIAS if bias is not None else 0)
+    kw = {}
+    if grouped is not None:
+        kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
+    gemm(A=x, a_smn=K, a_sk=1, B=w, b_smn=K, b_sk=1, b_group_stride=w_group_stride, M=M, N=N, K=K, D=out, ldd=N,
+         a_row_index=row_index, bias=bias, bias_group_stride=bias_group_stride, epilogue=epi, aux_out=aux_out,
+         ld_aux=N, col_scale=col_scale, row_scale=row_scale, resid=resid, ld_resid=N, **kw)
+    return out
+
+
+def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, resid=None, grouped=None,
+                 w_group_stride=0):
+    """dx[M,K] = epi(dy[M,N] @ w[N,K])   (w used as an MN-major B operand; no transposed copy)."""
+    M, N = dy.shape
+    K = w.shape[-1]
+    if out is None:
+        out = torch.empty((M, K), device=dy.device, dtype=torch.float32)
+    kw = {}
+    if grouped is not None:
+        kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
+    gemm(A=dy, a_smn=N, a_sk=1, B=w, b_smn=1, b_sk=K, b_group_stride=w_group_stride, M=M, N=K, K=N, D=out, ldd=K,
+         epilogue=epilogue, aux_in=aux_in, ld_aux=K, row_scale=row_scale, resid=resid, ld_resid=K, **kw)
+    return out
+
+
+def linear_wgrad(dy, x, dw, *, rows=None, x_row_index=None, row_scale=None, segs=None, num_groups=1):
+    """dw[g][N,K] += dy[rows_g, N]^T @ x[rows_g, K]  (split-K with fp32 atomics; dw must be pre-zeroed).
+
+    row_scale (optional, [N]) scales the rows of dw (e.g. layer-scale gamma folded into the epilogue).
+    segs = (seg_begin, seg_end) device int32 arrays selecting each group's row range.
+    """
+    R = rows if rows is not None else dy.shape[0]
+    N = dy.shape[1]
+    K = x.shape[1]
+    tiles = ((N + 127) // 128) * max(1, K // 256 if K % 256 == 0 else 1) * num_groups
+    splits = max(1, min(64, (2 * num_sms()) // max(1, tiles)))
+    if R < 4096:
+        splits = max(1, min(splits, R // 512 + 1))
+    epi = EPI_ATOMIC | (EPI_ROWSCALE if row_scale is not None else 0)
+    gemm(A=dy, a_smn=1, a_sk=N, B=x, b_smn=1, b_sk=K, M=N, N=K, K=R, D=dw, ldd=K, d_group_stride=N * K,
+         b_k_index=x_row_index, sched=SCHED_SPLITK, k_splits=splits, num_groups=num_groups,
+         seg_begin=None if segs is None else segs[0], seg_end=None if segs is None else segs[1],
+         epilogue=epi, row_scale=row_scale)
+    return dw
+
+
+def layernorm_fwd(x, w, b, eps, *, tokens, C, out=None, out_mode=LN_NHWC, H=0, W=0, save_stats=False):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty_like(x)
+    stats = torch.empty((tokens, 2), device=x.device, dtype=torch.float32) if save_stats else None
+    _lib.check(lib.sm3_layernorm_fwd(_p(x), _p(w), _p(b), _p(out), _p(stats), tokens, C, float(eps), out_mode, H, W,
+                                     _stream()), 'sm3_layernorm_fwd')
+    return out, stats
+
+
+def layernorm_bwd(dy, x, stats, w, dw, db, *, tokens, C, in_mode=LN_NHWC, H=0, W=0, dx=None, accumulate=False):
+    lib = _lib.load()
+    if dx is None:
+        dx = torch.empty((tokens, C), device=x.device, dtype=torch.float32)
+    _lib.check(lib.sm3_layernorm_bwd(_p(dy), _p(x), _p(stats), _p(w), _p(dx), _p(dw), _p(db), tokens, C, in_mode, H, W,
+                                     1 if accumulate else 0, _stream()), 'sm3_layernorm_bwd')
+    return dx
+
+
+def stem_fwd(x, wt, bias, lnw, lnb, eps, ps, *, save=False):
+    lib = _lib.load()
+    N, Cin, H, W = x.shape
+    C0 = wt.shape[1]
+    y = torch.empty((N, H // ps, W // ps, C0), device=x.device, dtype=torch.float32)
+    conv = torch.empty_like(y) if save else None
+    stats = torch.empty((N * (H // ps) * (W // ps), 2), device=x.device, dtype=torch.float32) if save else None
+    _lib.check(lib.sm3_stem_fwd(_p(x), _p(wt), _p(bias), _p(lnw), _p(lnb), _p(y), _p(conv), _p(stats), N, Cin, H, W,
+                                ps, C0, float(eps), _stream()), 'sm3_stem_fwd')
+    return y, conv, stats
+
+
+def stem_wgrad(x, du, dwt, dbias, ps):
+    lib = _lib.load()
+    N, Cin, H, W = x.shape
+    _lib.check(lib.sm3_stem_wgrad(_p(x), _p(du), _p(dwt), _p(dbias), N, Cin, H, W, ps, dwt.shape[1], _stream()),
+               'sm3_stem_wgrad')
+
+
+def dwconv7(x, wt, bias=None, resid=None, out=None):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.sm3_dwconv7_fwd(_p(x), _p(wt), _p(bias), _p(resid), _p(out), N, H, W, Cc, _stream()), 'sm3_dwconv7_fwd')
+    return out
+
+
+def dwconv7_wgrad(x, dy, dwt, dbias):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    _lib.check(lib.sm3_dwconv7_wgrad(_p(x), _p(dy), _p(dwt), _p(dbias), N, H, W, Cc, _stream()), 'sm3_dwconv7_wgrad')
+
+
+def moe_router(v, wp, bp, sim, tau, *, T, Cc, E, k, w_noise=None, noise=None, save=False):
+    lib = _lib.load()
+    P = wp.shape[0]
+    dev = v.device
+    a = _lib.RouterArgs()
+    top_idx = torch.empty((T, k), device=dev, dtype=torch.int32)
+    top_gate = torch.empty((T, k), device=dev, dtype=torch.float32)
+    logits = torch.empty((T, E), device=dev, dtype=torch.float32) if save else None
+    p_out = torch.empty((T, P), device=dev, dtype=torch.float32) if save else None
+    m = min(k + 1, E)
+    top_vals = torch.empty((T, m), device=dev, dtype=torch.float32) if (save and noise is not None) else None
+    nb = lib.sm3_moe_router_blocks(T)
+    partials = torch.empty((nb, 3 * E), device=dev, dtype=torch.float32)
+    a.v = _p(v); a.proj_weight = _p(wp); a.proj_bias = _p(bp); a.sim_matrix = _p(sim); a.temperature = _p(tau)
+    a.w_noise = _p(w_noise) if noise is not None else None
+    a.noise = _p(noise)
+    a.T, a.C, a.P, a.E, a.k = T, Cc, P, E, k
+    a.top_idx = _pi(top_idx); a.top_gate = _p(top_gate); a.logits = _p(logits); a.top_vals = _p(top_vals)
+    a.p_out = _p(p_out); a.partials = _p(partials)
+    _lib.check(lib.sm3_moe_router(C.byref(a), _stream()), 'sm3_moe_router')
+    return dict(top_idx=top_idx, top_gate=top_gate, logits=logits, p=p_out, top_vals=top_vals, partials=partials)
+
+
+def moe_plan(partials, *, T, E, k):
+    lib = _lib.load()
+    dev = partials.device
+    max_tiles = (T * k + 127) // 128 + E
+    f = torch.empty(2 * E + 1, device=dev, dtype=torch.float32)
+    i = torch.empty(4 * E + max_tiles + 1, device=dev, dtype=torch.int32)
+    importance, load, loss = f[:E], f[E:2 * E], f[2 * E:2 * E + 1]
+    counts, seg_begin, seg_end, cursor = i[:E], i[E:2 * E], i[2 * E:3 * E], i[3 * E:4 * E]
+    tile_group = i[4 * E:4 * E + max_tiles]
+    num_m_tiles = i[4 * E + max_tiles:]
+    a = _lib.PlanArgs()
+    a.partials = _p(partials); a.T, a.E, a.k, a.max_m_tiles = T, E, k, max_tiles
+    a.importance = importance.data_ptr(); a.load = load.data_ptr(); a.loss = loss.data_ptr()
+    a.counts = counts.data_ptr(); a.seg_begin = seg_begin.data_ptr(); a.seg_end = seg_end.data_ptr()
+    a.cursor = cursor.data_ptr(); a.tile_group = tile_group.data_ptr(); a.num_m_tiles = num_m_tiles.data_ptr()
+    _lib.check(lib.sm3_moe_plan(C.byref(a), _stream()), 'sm3_moe_plan')
+    return dict(importance=importance, load=load, loss=loss, counts=counts, seg_begin=seg_begin, seg_end=seg_end,
+                cursor=cursor, tile_group=tile_group, num_m_tiles=num_m_tiles, max_rows=max_tiles * 128)
+
+
+def moe_assign(top_idx, plan, *, T, E, k):
+    lib = _lib.load()
+    dev = top_idx.device
+    slot_of = torch.empty((T, k), device=dev, dtype=torch.int32)
+    pair_token = torch.full((plan['max_rows'],), -1, device=dev, dtype=torch.int32)
+    _lib.check(lib.sm3_moe_assign(_pi(top_idx), T, k, E, plan['seg_begin'].data_ptr(), plan['cursor'].data_ptr(),
+                                  _pi(slot_of), _pi(pair_token), _stream()), 'sm3_moe_assign')
+    return slot_of, pair_token
+
+
+def moe_combine(o, slot_of, top_idx, gate, gamma, resid, row_scale, *, T, Cc, k, want_y=False):
+    lib = _lib.load()
+    out = torch.empty((T, Cc), device=o.device, dtype=torch.float32)
+    y = torch.empty((T, Cc), device=o.device, dtype=torch.float32) if want_y else None
+    _lib.check(lib.sm3_moe_combine(_p(o), _pi(slot_of), _pi(top_idx), _p(gate), _p(gamma), _p(resid), _p(row_scale),
+                                   _p(out), _p(y), T, Cc, k, _stream()), 'sm3_moe_combine')
+    return out, y
+
+
+def moe_combine_bwd(dout, o, slot_of, top_idx, gate, gamma, row_scale, d_o, dgamma, *, T, Cc, k):
+    lib = _lib.load()
+    dgate = torch.empty((T, k), device=o.device, dtype=torch.float32)
+    _lib.check(lib.sm3_moe_combine_bwd(_p(dout), _p(o), _pi(slot_of), _pi(top_idx), _p(gate), _p(gamma), _p(row_scale),
+                                       _p(d_o), _p(dgate), _p(dgamma), T, Cc, k, _stream()), 'sm3_moe_combine_bwd')
+    return dgate
+
+
+def moe_router_bwd(p, sim, tau, top_idx, top_gate, dgate, logits, importance, loss_scale, dsim, dtau, *, T, E, k):
+    lib = _lib.load()
+    P = p.shape[1]
+    dp = torch.empty_like(p)
+    dsim_hat = torch.zeros((P, E), device=p.device, dtype=torch.float32)
+    a = _lib.RouterBwdArgs()
+    a.p = _p(p); a.sim_matrix = _p(sim); a.temperature = _p(tau); a.top_idx = _pi(top_idx); a.top_gate = _p(top_gate)
+    a.dgate = _p(dgate); a.logits = _p(logits); a.importance = importance.data_ptr(); a.loss_scale = _p(loss_scale)
+    a.T, a.P, a.E, a.k = T, P, E, k
+    a.dp = _p(dp); a.dsim_hat = _p(dsim_hat); a.dtemperature = _p(dtau)
+    _lib.check(lib.sm3_moe_router_bwd(C.byref(a), _stream()), 'sm3_moe_router_bwd')
+    _lib.check(lib.sm3_moe_router_bwd_finalize(_p(dsim_hat), _p(sim), _p(dsim), P, E, _stream()),
+               'sm3_moe_router_bwd_finalize')
+    return dp
+
+
+def colsum(a, out, *, rows, Cc, b=None, row_scale=None, segs=None, groups=1):
+    lib = _lib.load()
+    _lib.check(lib.sm3_colsum(_p(a), _p(b), _p(row_scale), None if segs is None else segs[0].data_ptr(),
+                              None if segs is None else segs[1].data_ptr(), groups, _p(out), rows, Cc, _stream()),
+               'sm3_colsum')
+    return out
+
+
+def gather_sum(src, slot_of, add, *, T, Cc, k, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((T, Cc), device=src.device, dtype=torch.float32)
+    _lib.check(lib.sm3_gather_sum(_p(src), _pi(slot_of), _p(add), _p(out), T, Cc, k, _stream()), 'sm3_gather_sum')
+    return out
+
+
+def scale_rows(x, row_scale=None, col_scale=None, out=None):
+    lib = _lib.load()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.sm3_scale_rows(_p(x), _p(row_scale), _p(col_scale), _p(out), rows, Cc, _stream()), 'sm3_scale_rows')
+    return out

@@ -93,7 +93,7 @@ static void run(const Case& c) {
   p.tile_group = dtg; p.num_m_tiles_dev = dnmt;
   int* dsb = segb.empty() ? nullptr : dev(segb); int* dse = sege.empty() ? nullptr : dev(sege);
   p.seg_begin = dsb; p.seg_end = dse;
-  float* dD = dev(D); p.D = dD; p.ldd = N; p.d_group_stride = (long long)M * N;
+  float* dD = dev(D); p.D = dD; p.ldd = N; p.d_group_stride = (c.sched == SCHED_SPLITK) ? (long long)M * N : 0;
   float* dbias = dev(bias); p.bias = dbias; p.bias_group_stride = (c.sched == SCHED_GROUPED) ? N : 0;
   p.epi = c.epi;
   float* dauxo = dev(AUXO); float* daux = dev(aux);
@@ -142,7 +142,7 @@ static void run(const Case& c) {
       const double err = fabs(got - acc);
       if (err > max_err) { max_err = err; }
       if (fabs(acc) > max_ref) max_ref = fabs(acc);
-      if (err > 1e-3 * (1.0 + fabs(acc))) { if (nbad == 0) { bad_m = m; bad_n = n; } nbad++; }
+      if (err > 1e-4 * (1.0 + fabs(acc)) + 2e-7 * sqrt((double)K) * 30.0) { if (nbad == 0) { bad_m = m; bad_n = n; } nbad++; }
       if (c.epi & EPI_GELU) max_aux_err = std::max(max_aux_err, fabs((double)AUXO[(size_t)m * N + n] - pre));
     }
   }
@@ -184,6 +184,8 @@ static void bench(const char* name, int M, int N, int K, bool a_mn, bool b_mn, i
 
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && std::string(argv[1]) == "quick";
+  const bool only_bench = argc > 1 && std::string(argv[1]) == "bench";
+  const int bench_idx = argc > 2 ? atoi(argv[2]) : -1;
   std::vector<Case> cases;
   auto add = [&](Case c) { cases.push_back(c); };
   { Case c; c.name = "nt_int_128x32x32";   c.M = 128; c.N = 32;  c.K = 32;  c.ints = true; add(c); }
@@ -205,17 +207,19 @@ int main(int argc, char** argv) {
   { Case c; c.name = "tn_f32_wgrad_groups"; c.M = 96; c.N = 384; c.K = 4000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 3; c.groups = 4; c.epi = EPI_ATOMIC; add(c); }
   { Case c; c.name = "grouped_nt_gelu";    c.M = 1024; c.N = 384; c.K = 96; c.sched = SCHED_GROUPED; c.groups = 3; c.gather = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
   { Case c; c.name = "grouped_nn";         c.M = 640; c.N = 96; c.K = 384; c.sched = SCHED_GROUPED; c.groups = 4; c.b_mn = true; add(c); }
-  for (auto& c : cases) run(c);
+  if (!only_bench) for (auto& c : cases) run(c);
   if (!quick) {
-    bench("ffn1 stage2 (gelu)", 32768, 1536, 384, false, false, EPI_BIAS | EPI_GELU);
-    bench("ffn2 stage2", 32768, 384, 1536, false, false, EPI_BIAS);
-    bench("ffn1 stage0 (gelu)", 524288, 384, 96, false, false, EPI_BIAS | EPI_GELU);
-    bench("ffn2 stage0", 524288, 96, 384, false, false, EPI_BIAS);
-    bench("ffn1 stage3", 8192, 3072, 768, false, false, EPI_BIAS);
-    bench("ffn2 stage3", 8192, 768, 3072, false, false, EPI_BIAS);
-    bench("dgrad stage2 (NN)", 32768, 384, 1536, false, true, 0);
-    bench("wgrad stage2 (TN)", 1536, 384, 32768, true, true, EPI_ATOMIC, SCHED_SPLITK, 16);
-    bench("square 8192", 8192, 8192, 8192, false, false, 0);
+    int bi = 0;
+#define B_(...) do { if (bench_idx < 0 || bench_idx == bi) bench(__VA_ARGS__); ++bi; } while (0)
+    B_("ffn1 stage2 (gelu)", 32768, 1536, 384, false, false, EPI_BIAS | EPI_GELU);
+    B_("ffn2 stage2", 32768, 384, 1536, false, false, EPI_BIAS);
+    B_("ffn1 stage0 (gelu)", 524288, 384, 96, false, false, EPI_BIAS | EPI_GELU);
+    B_("ffn2 stage0", 524288, 96, 384, false, false, EPI_BIAS);
+    B_("ffn1 stage3", 8192, 3072, 768, false, false, EPI_BIAS);
+    B_("ffn2 stage3", 8192, 768, 3072, false, false, EPI_BIAS);
+    B_("dgrad stage2 (NN)", 32768, 384, 1536, false, true, 0);
+    B_("wgrad stage2 (TN)", 1536, 384, 32768, true, true, EPI_ATOMIC, SCHED_SPLITK, 16);
+    B_("square 8192", 8192, 8192, 8192, false, false, 0);
   }
   printf("SUMMARY: %d failed of %zu\n", g_fail, cases.size());
   return g_fail ? 1 : 0;

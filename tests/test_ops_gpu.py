@@ -1,0 +1,209 @@
+"""GPU parity of each C-ABI kernel against plain torch fp32 on the CPU (oracle arithmetic)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from sm3det_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize('C', [32, 96, 192, 384, 768, 1024])
+def test_layernorm_modes(ops, C):
+    g = torch.Generator().manual_seed(C)
+    N, H, W = 2, 6, 8
+    x = torch.randn(N, H, W, C, generator=g) * 2 + 0.5
+    w, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    ref = F.layer_norm(x, (C,), w, b, 1e-6)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    T = N * H * W
+    y, stats = ops.layernorm_fwd(xd, wd, bd, 1e-6, tokens=T, C=C, save_stats=True)
+    assert rel(y, ref) < 1e-5
+    # NCHW output
+    y2 = torch.empty(N, C, H, W, device='cuda')
+    ops.layernorm_fwd(xd, wd, bd, 1e-6, tokens=T, C=C, out=y2, out_mode=ops.LN_NCHW, H=H, W=W)
+    assert rel(y2, ref.permute(0, 3, 1, 2)) < 1e-5
+    # 2x2 patch output
+    y3 = torch.empty(T // 4, 4 * C, device='cuda')
+    ops.layernorm_fwd(xd, wd, bd, 1e-6, tokens=T, C=C, out=y3, out_mode=ops.LN_PATCH2, H=H, W=W)
+    refp = ref.view(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(T // 4, 4 * C)
+    assert rel(y3, refp) < 1e-5
+    # backward (all three gradient layouts)
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    out = F.layer_norm(xr, (C,), wr, br, 1e-6)
+    dy = torch.randn(N, H, W, C, generator=g)
+    out.backward(dy)
+    for mode, dyl in ((ops.LN_NHWC, dy), (ops.LN_NCHW, dy.permute(0, 3, 1, 2).contiguous()),
+                      (ops.LN_PATCH2, dy.view(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(T // 4, 4 * C).contiguous())):
+        dw = torch.zeros(C, device='cuda'); db = torch.zeros(C, device='cuda')
+        dx = ops.layernorm_bwd(dyl.cuda(), xd, stats, wd, dw, db, tokens=T, C=C, in_mode=mode, H=H, W=W)
+        assert rel(dx.view(N, H, W, C), xr.grad) < 2e-5, mode
+        assert rel(dw, wr.grad) < 2e-5 and rel(db, br.grad) < 2e-5, mode
+
+
+@pytest.mark.parametrize('C,H,W', [(32, 8, 8), (96, 25, 13), (192, 7, 50), (384, 16, 16), (768, 1, 3)])
+def test_dwconv7(ops, C, H, W):
+    g = torch.Generator().manual_seed(C + H)
+    N = 2
+    x = torch.randn(N, C, H, W, generator=g, requires_grad=True)
+    w = (torch.randn(C, 1, 7, 7, generator=g) * 0.2).requires_grad_(True)
+    b = (torch.randn(C, generator=g) * 0.1).requires_grad_(True)
+    ref = F.conv2d(x, w, b, padding=3, groups=C)
+    dy = torch.randn(N, C, H, W, generator=g)
+    ref.backward(dy)
+    xh = x.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    wt = w.detach().reshape(C, 49).t().contiguous().cuda()
+    y = ops.dwconv7(xh, wt, b.detach().cuda())
+    assert rel(y.permute(0, 3, 1, 2), ref) < 1e-5
+    dyh = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    wtf = w.detach().flip(2, 3).reshape(C, 49).t().contiguous().cuda()
+    res = torch.randn(N, H, W, C, generator=g)
+    dx = ops.dwconv7(dyh, wtf, None, resid=res.cuda())
+    assert rel(dx.cpu() - res, x.grad.permute(0, 2, 3, 1)) < 1e-5
+    dwt = torch.zeros(49, C, device='cuda'); dbb = torch.zeros(C, device='cuda')
+    ops.dwconv7_wgrad(xh, dyh, dwt, dbb)
+    assert rel(dwt.t().reshape(C, 1, 7, 7), w.grad) < 2e-5
+    assert rel(dbb, b.grad) < 2e-5
+
+
+@pytest.mark.parametrize('C0', [32, 96, 128])
+def test_stem(ops, C0):
+    g = torch.Generator().manual_seed(C0)
+    N, H, W = 2, 64, 96
+    x = torch.randn(N, 3, H, W, generator=g)
+    w = (torch.randn(C0, 3, 4, 4, generator=g) * 0.2).requires_grad_(True)
+    b = (torch.randn(C0, generator=g) * 0.1).requires_grad_(True)
+    lw = (torch.rand(C0, generator=g) + 0.5).requires_grad_(True); lb = (torch.randn(C0, generator=g) * 0.1).requires_grad_(True)
+    u = F.conv2d(x, w, b, stride=4)
+    ref = F.layer_norm(u.permute(0, 2, 3, 1), (C0,), lw, lb, 1e-6)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    wt = w.detach().reshape(C0, -1).t().contiguous().cuda()
+    y, conv, stats = ops.stem_fwd(x.cuda(), wt, b.detach().cuda(), lw.detach().cuda(), lb.detach().cuda(), 1e-6, 4, save=True)
+    assert rel(y, ref) < 1e-5
+    assert rel(conv, u.permute(0, 2, 3, 1)) < 1e-5
+    T = N * (H // 4) * (W // 4)
+    dlw = torch.zeros(C0, device='cuda'); dlb = torch.zeros(C0, device='cuda')
+    du = ops.layernorm_bwd(dy.cuda(), conv, stats, lw.detach().cuda(), dlw, dlb, tokens=T, C=C0)
+    dwt = torch.zeros(48, C0, device='cuda'); dbb = torch.zeros(C0, device='cuda')
+    ops.stem_wgrad(x.cuda(), du, dwt, dbb, 4)
+    assert rel(dwt.t().reshape(C0, 3, 4, 4), w.grad) < 2e-5
+    assert rel(dbb, b.grad) < 2e-5 and rel(dlw, lw.grad) < 2e-5 and rel(dlb, lb.grad) < 2e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 384, 96), (1000, 96, 384), (130, 768, 3072), (64, 256, 128)])
+def test_linear_fwd_dgrad_wgrad(ops, M, N, K):
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g, requires_grad=True)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).requires_grad_(True)
+    b = (torch.randn(N, generator=g) * 0.1).requires_grad_(True)
+    h = F.linear(x, w, b)
+    ref = F.gelu(h)
+    dy = torch.randn(M, N, generator=g)
+    ref.backward(dy)
+    xd, wd, bd = x.detach().cuda(), w.detach().cuda(), b.detach().cuda()
+    hbuf = torch.empty(M, N, device='cuda')
+    y = ops.linear_fwd(xd, wd, bd, epilogue=ops.EPI_GELU, aux_out=hbuf)
+    assert rel(y, ref) < 5e-5 and rel(hbuf, h) < 5e-5
+    # dgrad with fused GELU'
+    dh_ref = torch.autograd.grad(F.gelu(h.detach().requires_grad_(True)), [], allow_unused=True) if False else None
+    hd = h.detach().clone().requires_grad_(True)
+    F.gelu(hd).backward(dy)
+    dh = hd.grad
+    dx = ops.linear_dgrad(dh.cuda(), wd)
+    assert rel(dx, x.grad) < 5e-5
+    ident = torch.eye(N)
+    dh_gpu = ops.linear_dgrad(dy.cuda(), ident.cuda().contiguous(), epilogue=ops.EPI_DGELU, aux_in=hbuf)
+    assert rel(dh_gpu, dh) < 5e-5
+    dw = torch.zeros(N, K, device='cuda')
+    ops.linear_wgrad(dh.cuda(), xd, dw)
+    assert rel(dw, w.grad) < 5e-5
+    db = torch.zeros(N, device='cuda')
+    ops.colsum(dh.cuda(), db, rows=M, Cc=N)
+    assert rel(db, b.grad) < 2e-5
+
+
+@pytest.mark.parametrize('C,E,k,T', [(96, 4, 2, 500), (384, 8, 2, 4096), (768, 8, 3, 1000), (128, 6, 1, 777), (64, 2, 2, 256),
+                                      (512, 16, 2, 2048)])
+@pytest.mark.parametrize('tau', [math.log(2.0), math.log(10.0), 5.0])
+def test_router_matches_oracle_bit_exact(ops, C, E, k, T, tau):
+    from oracle.convnext_moe_oracle import OracleConfig, noisy_top_k_gating, cv_squared
+    g = torch.Generator().manual_seed(C * E + k)
+    P = min(C // 2, 256)
+    v = torch.randn(T, C, generator=g)
+    sd = {'w_gate.cosine_projector.weight': torch.randn(P, C, generator=g) / math.sqrt(C),
+          'w_gate.cosine_projector.bias': torch.randn(P, generator=g) * 0.05,
+          'w_gate.sim_matrix': torch.randn(P, E, generator=g), 'w_gate.temperature': torch.tensor([tau]),
+          'w_noise': torch.zeros(C, E)}
+    cfg = OracleConfig(num_experts=E, top_k=k)
+    gates, load, info = noisy_top_k_gating(v, sd, '', cfg, train=False)
+    r = ops.moe_router(v.cuda(), sd['w_gate.cosine_projector.weight'].cuda(), sd['w_gate.cosine_projector.bias'].cuda(),
+                       sd['w_gate.sim_matrix'].cuda(), sd['w_gate.temperature'].cuda(), T=T, Cc=C, E=E, k=k, save=True)
+    idx = r['top_idx'].cpu().long()
+    ref_idx = info['top_idx']
+    mism = (idx != ref_idx).any(dim=1)
+    # fp32 summation order differs from MKL's: only (k)-vs-(k+1) near-ties (margin < 1e-5 * scale) may flip
+    if mism.any():
+        top = info['logits'].topk(min(k + 1, E), dim=-1).values
+        gaps = (top[:, :-1] - top[:, 1:]).min(dim=1).values
+        assert (gaps[mism] < 1e-5 * math.exp(min(tau, math.log(100)))).all(), f'{int(mism.sum())} real routing mismatches'
+        assert mism.sum() <= 2
+    ok = ~mism
+    assert (r['top_gate'].cpu()[ok] - info['top_gates'][ok]).abs().max() < 2e-6
+    assert rel(r['logits'], info['logits']) < 2e-6
+    plan = ops.moe_plan(r['partials'], T=T, E=E, k=k)
+    imp = gates.sum(0)
+    loss = (cv_squared(imp) + cv_squared(load)) * 1e-2
+    if not mism.any():
+        assert rel(plan['importance'], imp) < 1e-5
+        assert torch.equal(plan['counts'].cpu().long(), load)
+        assert abs(plan['loss'].item() - loss.item()) <= 1e-5 * abs(loss.item()) + 1e-9
+    # dispatch plan invariants
+    slot_of, pair_token = ops.moe_assign(r['top_idx'], plan, T=T, E=E, k=k)
+    sb, se, cnt = plan['seg_begin'].cpu(), plan['seg_end'].cpu(), plan['counts'].cpu()
+    assert (sb % 128 == 0).all() and torch.equal(se - sb, cnt)
+    so, pt = slot_of.cpu().long(), pair_token.cpu().long()
+    assert (pt[so.flatten()] == torch.arange(T).repeat_interleave(k)).all()
+    for e in range(E):
+        assert ((so >= sb[e]) & (so < se[e])).sum() == cnt[e]
+        assert (idx[(so >= sb[e]) & (so < se[e])] == e).all()
+    assert (pt >= 0).sum() == T * k
+    ntile = plan['num_m_tiles'].item()
+    tg = plan['tile_group'].cpu()[:ntile]
+    assert ntile == sum((int(c) + 127) // 128 for c in cnt)
+    for t in range(ntile):
+        assert sb[tg[t]] <= t * 128 < sb[tg[t]] + ((cnt[tg[t]] + 127) // 128) * 128
+
+
+def test_router_noisy_soft_load(ops):
+    from oracle.convnext_moe_oracle import OracleConfig, noisy_top_k_gating, cv_squared
+    g = torch.Generator().manual_seed(3)
+    C, E, k, T = 96, 4, 2, 1000
+    P = C // 2
+    v = torch.randn(T, C, generator=g)
+    sd = {'w_gate.cosine_projector.weight': torch.randn(P, C, generator=g) / math.sqrt(C),
+          'w_gate.cosine_projector.bias': torch.randn(P, generator=g) * 0.05,
+          'w_gate.sim_matrix': torch.randn(P, E, generator=g), 'w_gate.temperature': torch.tensor([math.log(10.)]),
+          'w_noise': torch.randn(C, E, generator=g) * 0.05}
+    noise = torch.randn(T, E, generator=g)
+    cfg = OracleConfig(num_experts=E, top_k=k)
+    gates, load, info = noisy_top_k_gating(v, sd, '', cfg, train=True, noise=noise)
+    r = ops.moe_router(v.cuda(), sd['w_gate.cosine_projector.weight'].cuda(), sd['w_gate.cosine_projector.bias'].cuda(),
+                       sd['w_gate.sim_matrix'].cuda(), sd['w_gate.temperature'].cuda(), T=T, Cc=C, E=E, k=k,
+                       w_noise=sd['w_noise'].cuda(), noise=noise.cuda(), save=True)
+    assert torch.equal(r['top_idx'].cpu().long(), info['top_idx'])
+    plan = ops.moe_plan(r['partials'], T=T, E=E, k=k)
+    assert rel(plan['load'], load) < 1e-5
+    loss = (cv_squared(gates.sum(0)) + cv_squared(load)) * 1e-2
+    assert abs(plan['loss'].item() - loss.item()) <= 1e-5 * abs(loss.item())
