@@ -57,18 +57,25 @@ int launch(Params p, cudaStream_t stream) {
   } else {
     SM3_REQUIRE(false, SM3_ERR_INVALID_ARG, "gemm: bad schedule %d", p.sched);
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-  });
-  // per-device attribute: set again cheaply if another device is current (idempotent)
-  if (attr_err != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return SM3_ERR_CUDA; }
-  cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  // 32-bit element offsets inside the kernel: every operand must span < 2^32 floats (16 GiB)
+  {
+    const long long a_ext = a_mn ? (long long)p.K * p.a_sk : (long long)(p.a_row_index ? (1LL << 31) / (p.a_smn ? p.a_smn : 1) : p.M) * p.a_smn;
+    const long long b_ext = b_mn ? (long long)(p.b_k_index ? 1 : p.K) * p.b_sk + p.N : (long long)p.N * p.b_smn;
+    SM3_REQUIRE(a_ext < (1LL << 32) && b_ext < (1LL << 32), SM3_ERR_UNSUPPORTED_SHAPE, "gemm: operand larger than 2^32 elements");
+  }
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   if (grid < 1) grid = 1;
-  gemm_bf16x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+#define SM3_GEMM_LAUNCH(AMN, BMN)                                                                                   \
+  do {                                                                                                              \
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES); \
+    gemm_bf16x3_kernel<AMN, BMN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);                                     \
+  } while (0)
+  if (!a_mn && !b_mn) SM3_GEMM_LAUNCH(false, false);
+  else if (!a_mn && b_mn) SM3_GEMM_LAUNCH(false, true);
+  else if (a_mn && b_mn) SM3_GEMM_LAUNCH(true, true);
+  else SM3_REQUIRE(false, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major A with K-major B is not instantiated");
+#undef SM3_GEMM_LAUNCH
   return check_launch("gemm_bf16x3_kernel");
 }
 

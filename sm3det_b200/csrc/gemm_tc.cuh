@@ -235,18 +235,13 @@ __device__ __forceinline__ void split4(const float4& x, uint32_t& h01, uint32_t&
   l23 = __byte_perm(r2, r3, 0x7632);
 }
 
-// Producer unit bookkeeping: unit u of a k-block -> which operand and where.
-struct UnitMap {
-  int units_a, units_b, segs_b;   // per k-block
-};
-__device__ __forceinline__ UnitMap make_unit_map(const Params& p, bool a_mn, bool b_mn) {
-  UnitMap um;
-  um.units_a = 16;  // 128 rows / 8 (K-major) or 16 k-pairs x 1 segment (MN-major)
-  um.segs_b = (p.BN + 127) / 128;
-  um.units_b = b_mn ? 16 * um.segs_b : p.BN / 8;
-  return um;
-}
-
+// ---------------------------------------------------------------------------------------------
+// Kernel.  Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer (one elected lane),
+// 5-11 producers.  A k-block of an operand is cut into "units" of 8 rows x 32 k (K-major) or
+// 2 k-rows x 128 mn (MN-major); unit u of a k-block belongs to producer warp u % 7.  All per-tile
+// address arithmetic is hoisted: a thread keeps one 32-bit element offset per (unit, half) and
+// advances it by a constant per k-block.
+template <bool A_MN, bool B_MN>
 __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -258,8 +253,6 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
   const uint32_t tmem_slot = bar_base + 96u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool a_mn = (p.a_smn == 1 && p.a_sk != 1);
-  const bool b_mn = (p.b_smn == 1 && p.b_sk != 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), NUM_PROD_WARPS); mbar_init(empty_bar(s), 1); }
@@ -368,10 +361,10 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
   } else if (warp == MMA_WARP) {
     // ============================== MMA ISSUER ============================================
     if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(p.BN, a_mn, b_mn);
+      const uint32_t idesc = make_instr_desc(p.BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-      const uint32_t a_kstep = a_mn ? 2u * MN_SBO_BYTES : 32u;   // advance 16 k per UMMA
-      const uint32_t b_kstep = b_mn ? 2u * MN_SBO_BYTES : 32u;
+      constexpr uint32_t a_kstep = A_MN ? 2u * MN_SBO_BYTES : 32u;   // advance 16 k per UMMA
+      constexpr uint32_t b_kstep = B_MN ? 2u * MN_SBO_BYTES : 32u;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const Tile tl = decode_tile(p, t);
         const int nkb = tl.nkb();
@@ -385,10 +378,10 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           const uint32_t sb = smem_base + stage * STAGE_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t ahi = make_smem_desc(sb + OFF_A_HI + j * a_kstep, a_mn);
-            const uint64_t alo = make_smem_desc(sb + OFF_A_LO + j * a_kstep, a_mn);
-            const uint64_t bhi = make_smem_desc(sb + OFF_B_HI + j * b_kstep, b_mn);
-            const uint64_t blo = make_smem_desc(sb + OFF_B_LO + j * b_kstep, b_mn);
+            const uint64_t ahi = make_smem_desc(sb + OFF_A_HI + j * a_kstep, A_MN);
+            const uint64_t alo = make_smem_desc(sb + OFF_A_LO + j * a_kstep, A_MN);
+            const uint64_t bhi = make_smem_desc(sb + OFF_B_HI + j * b_kstep, B_MN);
+            const uint64_t blo = make_smem_desc(sb + OFF_B_LO + j * b_kstep, B_MN);
             tc_mma(tmem_d, alo, bhi, idesc, (kb > 0 || j > 0) ? 1u : 0u);
             tc_mma(tmem_d, ahi, blo, idesc, 1u);
             tc_mma(tmem_d, ahi, bhi, idesc, 1u);
@@ -403,85 +396,126 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
   } else {
     // ============================== PRODUCERS =============================================
     const int wq = warp - FIRST_PROD_WARP;
-    const UnitMap um = make_unit_map(p, a_mn, b_mn);
     const int sub = lane >> 3, f4 = lane & 7;
     const bool odd = lane & 1;
+    constexpr int units_a = 16;
+    const int segs_b = (p.BN + 127) / 128;
+    const int units_b = B_MN ? 16 * segs_b : p.BN / 8;
+    const int units = units_a + units_b;
+    // lane-constant parts of the shared-memory store offsets
+    const uint32_t st_k = (uint32_t)((2 * sub + (odd ? 1 : 0)) * 64 + ((((uint32_t)f4 >> 1) ^ (uint32_t)sub) << 4));
+    const uint32_t cc = (uint32_t)(lane >> 1) & 7u, g_lane = (uint32_t)lane >> 4;
 
-    // Iterator over (tile, kb) with nkb > 0
-    struct It { int t, kb, nkb; Tile tl; bool valid; };
-    auto first_from = [&](int t) {
-      It it; it.kb = 0; it.valid = false; it.t = t; it.nkb = 0;
-      for (; it.t < ntiles; it.t += gridDim.x) {
-        it.tl = decode_tile(p, it.t);
-        it.nkb = it.tl.nkb();
-        if (it.nkb > 0) { it.valid = true; break; }
-      }
-      return it;
-    };
-    auto next_of = [&](const It& c) {
-      if (c.kb + 1 < c.nkb) { It n = c; n.kb = c.kb + 1; return n; }
-      return first_from(c.t + gridDim.x);
-    };
+    // per-tile state
+    uint32_t off[MAX_UNITS][2];     // element offsets from the operand base (A) / group base (B)
+    uint32_t vmask = 0;             // bit (2i+h): row / mn range valid
+    const float* baseB = p.B;
+    int t_cur = blockIdx.x - gridDim.x, kb_cur = 0, nkb_cur = 0, k_begin = 0, k_end = 0;
+    const uint32_t adv_a = A_MN ? (uint32_t)(BK * p.a_sk) : (uint32_t)BK;
+    const uint32_t adv_b = B_MN ? (uint32_t)(BK * p.b_sk) : (uint32_t)BK;
 
-    // issue the global loads of one k-block for this thread's units
-    auto load_kb = [&](float4 (&r)[MAX_UNITS][2], const It& it) {
-      const int k0 = it.tl.k_begin + it.kb * BK;
+    auto setup_tile = [&](const Tile& tl) {
+      k_begin = tl.k_begin; k_end = tl.k_end;
+      baseB = p.B + (long long)tl.group * p.b_group_stride;
+      vmask = 0;
 #pragma unroll
       for (int i = 0; i < MAX_UNITS; ++i) {
-        r[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        r[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int u = wq + NUM_PROD_WARPS * i;
-        const bool is_a = u < um.units_a;
-        const int ul = is_a ? u : u - um.units_a;
-        if (!is_a && ul >= um.units_b) continue;
-        const bool mn = is_a ? a_mn : b_mn;
-        const float* base = is_a ? p.A : p.B + (long long)it.tl.group * p.b_group_stride;
-        const long long s_mn = is_a ? p.a_smn : p.b_smn;
-        const long long s_k = is_a ? p.a_sk : p.b_sk;
-        const int mn0 = is_a ? it.tl.m0 : it.tl.n0;
-        const int mn_lim = is_a ? p.M : p.N;
-        if (!mn) {
-          const int k = k0 + 4 * f4;
-          if (k + 4 > it.tl.k_end) continue;
+        off[i][0] = 0; off[i][1] = 0;
+        if (u >= units) continue;
+        const bool is_a = u < units_a;
+        const int ul = is_a ? u : u - units_a;
+        if (is_a ? !A_MN : !B_MN) {
+          const int mn0 = is_a ? tl.m0 : tl.n0;
+          const int mn_lim = is_a ? p.M : p.N;
+          const long long s_mn = is_a ? p.a_smn : p.b_smn;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int row = mn0 + 8 * ul + 2 * sub + h;
             if (row >= mn_lim) continue;
             long long ridx = row;
             if (is_a && p.a_row_index) { ridx = __ldg(p.a_row_index + row); if (ridx < 0) continue; }
-            r[i][h] = ldg_f4(base + ridx * s_mn + k);
+            off[i][h] = (uint32_t)(ridx * s_mn + tl.k_begin + 4 * f4);
+            vmask |= 1u << (2 * i + h);
           }
         } else {
-          const int segs = is_a ? 1 : um.segs_b;
-          const int pi = ul / segs, seg = ul - pi * segs;
+          const int segs = is_a ? 1 : segs_b;
+          const int pi = (segs == 2) ? (ul >> 1) : ul, seg = (segs == 2) ? (ul & 1) : 0;
           const int mnl = seg * 128 + 4 * lane;
+          const int mn0 = is_a ? tl.m0 : tl.n0;
           const int tile_w = is_a ? BM : p.BN;
+          const int mn_lim = is_a ? p.M : p.N;
           if (mnl + 4 > tile_w || mn0 + mnl + 4 > mn_lim) continue;
+          const long long s_k = is_a ? p.a_sk : p.b_sk;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int k = k0 + (pi >> 2) * 8 + (pi & 3) + 4 * h;
-            if (k >= it.tl.k_end) continue;
-            long long kk = k;
-            if (!is_a && p.b_k_index) { kk = __ldg(p.b_k_index + k); if (kk < 0) continue; }
-            r[i][h] = ldg_f4(base + kk * s_k + (mn0 + mnl));
+            const int koff = (pi >> 2) * 8 + (pi & 3) + 4 * h;
+            off[i][h] = (uint32_t)((long long)(tl.k_begin + koff) * s_k + mn0 + mnl);
+            vmask |= 1u << (2 * i + h);
           }
         }
       }
     };
+    // advance (t_cur, kb_cur) to the next k-block with work; returns false at the end
+    auto advance = [&]() -> bool {
+      if (kb_cur + 1 < nkb_cur) { ++kb_cur; return true; }
+      for (t_cur += gridDim.x; t_cur < ntiles; t_cur += gridDim.x) {
+        const Tile tl = decode_tile(p, t_cur);
+        nkb_cur = tl.nkb();
+        if (nkb_cur > 0) { kb_cur = 0; setup_tile(tl); return true; }
+      }
+      return false;
+    };
 
-    // split + exchange + store one k-block into its smem stage
+    // issue the global loads of the current k-block, then step the offsets to the next one
+    const bool b_gather = B_MN && (p.b_k_index != nullptr);
+    auto load_kb = [&](float4 (&r)[MAX_UNITS][2]) {
+      const int k0 = k_begin + kb_cur * BK;
+      const bool kin = (k0 + 4 * f4 + 4 <= k_end);          // K-major operands: this lane's 4 k values
+#pragma unroll
+      for (int i = 0; i < MAX_UNITS; ++i) {
+        r[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int u = wq + NUM_PROD_WARPS * i;
+        if (u >= units) continue;
+        const bool is_a = u < units_a;
+        const float* base = is_a ? p.A : baseB;
+        if (is_a ? !A_MN : !B_MN) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (((vmask >> (2 * i + h)) & 1u) && kin) r[i][h] = ldg_f4(base + off[i][h]);
+        } else {
+          const int ul = is_a ? u : u - units_a;
+          const int pi = (!is_a && segs_b == 2) ? (ul >> 1) : ul;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = k0 + (pi >> 2) * 8 + (pi & 3) + 4 * h;
+            if (!((vmask >> (2 * i + h)) & 1u) || k >= k_end) continue;
+            if (!is_a && b_gather) {
+              const int kk = __ldg(p.b_k_index + k);
+              if (kk >= 0) r[i][h] = ldg_f4(base + (long long)kk * p.b_sk + off[i][h]);
+            } else {
+              r[i][h] = ldg_f4(base + off[i][h]);
+            }
+          }
+        }
+        const uint32_t adv = is_a ? adv_a : ((!is_a && b_gather) ? 0u : adv_b);
+        off[i][0] += adv; off[i][1] += adv;
+      }
+    };
+
+    // split + pair exchange + store one k-block into its smem stage
     auto store_kb = [&](const float4 (&r)[MAX_UNITS][2], uint32_t sb) {
 #pragma unroll
       for (int i = 0; i < MAX_UNITS; ++i) {
         const int u = wq + NUM_PROD_WARPS * i;
-        const bool is_a = u < um.units_a;
-        const int ul = is_a ? u : u - um.units_a;
-        if (!is_a && ul >= um.units_b) continue;
-        const bool mn = is_a ? a_mn : b_mn;
+        if (u >= units) continue;
+        const bool is_a = u < units_a;
+        const int ul = is_a ? u : u - units_a;
         uint32_t hA0, hA1, lA0, lA1, hB0, hB1, lB0, lB1;
         split4(r[i][0], hA0, hA1, lA0, lA1);
         split4(r[i][1], hB0, hB1, lB0, lB1);
-        // even lane keeps part 0 (needs the odd lane's part-0 half); odd lane keeps part 1
+        // even lane keeps half 0 (needs the odd lane's half-0 part); odd lane keeps half 1
         const uint32_t s0 = odd ? hA0 : hB0, s1 = odd ? hA1 : hB1;
         const uint32_t s2 = odd ? lA0 : lB0, s3 = odd ? lA1 : lB1;
         const uint32_t q0 = __shfl_xor_sync(0xffffffffu, s0, 1);
@@ -491,18 +525,18 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
         uint4 hi, lo;
         if (!odd) { hi = make_uint4(hA0, hA1, q0, q1); lo = make_uint4(lA0, lA1, q2, q3); }
         else      { hi = make_uint4(q0, q1, hB0, hB1); lo = make_uint4(q2, q3, lB0, lB1); }
-        uint32_t off;
-        if (!mn) {
-          const uint32_t row = 8u * ul + 2u * sub + (odd ? 1u : 0u);
-          off = kmajor_sw64_offset(row, (uint32_t)f4 >> 1);
+        uint32_t o;
+        if (is_a ? !A_MN : !B_MN) {
+          o = (uint32_t)ul * 512u + st_k;
         } else {
-          const int segs = is_a ? 1 : um.segs_b;
-          const int pi = ul / segs, seg = ul - pi * segs;
-          const uint32_t k = (uint32_t)((pi >> 2) * 8 + (pi & 3) + (odd ? 4 : 0));
-          off = mnmajor_sw128_offset(k, (uint32_t)(seg * 16 + (lane >> 1)));
+          const int segs = is_a ? 1 : segs_b;
+          const uint32_t pi = (segs == 2) ? (uint32_t)(ul >> 1) : (uint32_t)ul;
+          const uint32_t seg = (segs == 2) ? (uint32_t)(ul & 1) : 0u;
+          const uint32_t k7 = (pi & 3u) + (odd ? 4u : 0u);
+          o = (seg * 2u + g_lane) * 4096u + (pi >> 2) * 1024u + k7 * 128u + ((cc ^ k7) << 4);
         }
-        const uint32_t dst_hi = sb + (is_a ? OFF_A_HI : OFF_B_HI) + off;
-        const uint32_t dst_lo = sb + (is_a ? OFF_A_LO : OFF_B_LO) + off;
+        const uint32_t dst_hi = sb + (is_a ? OFF_A_HI : OFF_B_HI) + o;
+        const uint32_t dst_lo = sb + (is_a ? OFF_A_LO : OFF_B_LO) + o;
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
                      ::"r"(dst_hi), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
@@ -521,19 +555,17 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     };
 
     float4 r0[MAX_UNITS][2], r1[MAX_UNITS][2];
-    It it = first_from(blockIdx.x);
-    if (it.valid) {
-      load_kb(r0, it);
+    if (advance()) {
+      load_kb(r0);
       while (true) {
-        It n1 = next_of(it);
-        if (n1.valid) load_kb(r1, n1);
+        const bool more1 = advance();
+        if (more1) load_kb(r1);
         publish(r0);
-        if (!n1.valid) break;
-        It n2 = next_of(n1);
-        if (n2.valid) load_kb(r0, n2);
+        if (!more1) break;
+        const bool more2 = advance();
+        if (more2) load_kb(r0);
         publish(r1);
-        if (!n2.valid) break;
-        it = n2;
+        if (!more2) break;
       }
     }
   }

@@ -21,10 +21,10 @@ int router_blocks(int T) { return (T + RT - 1) / RT; }
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float normal_cdf(float v) { return 0.5f * (1.0f + erff(v * 0.70710678118654752440f)); }
 
-template <int PJ>  // P = 32 * PJ
+template <int PJ>  // padded projection width 32 * PJ >= a.P
 __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int soft_load) {
   extern __shared__ float smem[];
-  const int P = 32 * PJ, E = a.E, C = a.C, k = a.k;
+  const int P = 32 * PJ, PR = a.P, E = a.E, C = a.C, k = a.k;   // PR = real width; padding columns are zero
   float* s_p = smem;                         // [RT][P+1]   projected tokens
   float* s_sim = s_p + RT * (P + 1);         // [E][P+1]    column-normalised sim matrix
   float* s_a = s_sim + E * (P + 1);          // [RT][R_KC+1]
@@ -36,9 +36,9 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
   // ---- normalised sim matrix: S[:,e] / max(||S[:,e]||, 1e-12)   (F.normalize(dim=0), :103) -----
   for (int e = warp; e < E; e += 8) {
     float ss = 0.f;
-    for (int p = lane; p < P; p += 32) { const float s = __ldg(a.sim + p * E + e); ss += s * s; }
+    for (int p = lane; p < PR; p += 32) { const float s = __ldg(a.sim + p * E + e); ss += s * s; }
     const float inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
-    for (int p = lane; p < P; p += 32) s_sim[e * (P + 1) + p] = __ldg(a.sim + p * E + e) * inv;
+    for (int p = lane; p < P; p += 32) s_sim[e * (P + 1) + p] = (p < PR) ? __ldg(a.sim + p * E + e) * inv : 0.f;
   }
 
   // ---- projection: p[t, :] = Wp v[t] + bp  (fp32 FMA; thread tile 8 tokens x PJ outputs) --------
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
     }
     for (int idx = tid; idx < P * R_KC; idx += 256) {
       const int p = idx / R_KC, kk = idx % R_KC;
-      s_b[kk * (P + 1) + p] = __ldg(a.wp + (long long)p * C + k0 + kk);
+      s_b[kk * (P + 1) + p] = (p < PR) ? __ldg(a.wp + (long long)p * C + k0 + kk) : 0.f;
     }
     __syncthreads();
 #pragma unroll 4
@@ -74,13 +74,14 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
   }
 #pragma unroll
   for (int j = 0; j < PJ; ++j) {
-    const float bj = __ldg(a.bp + lane + 32 * j);
+    const bool pin = lane + 32 * j < PR;
+    const float bj = pin ? __ldg(a.bp + lane + 32 * j) : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float pv = acc[i][j] + bj;
+      const float pv = pin ? acc[i][j] + bj : 0.f;
       s_p[(warp * 8 + i) * (P + 1) + lane + 32 * j] = pv;
       const long long t = t0 + warp * 8 + i;
-      if (a.p_out && t < a.T) a.p_out[t * P + lane + 32 * j] = pv;
+      if (a.p_out && pin && t < a.T) a.p_out[t * PR + lane + 32 * j] = pv;
     }
   }
   __syncthreads();
@@ -198,11 +199,11 @@ int moe_router(const RouterArgs& a, cudaStream_t stream) {
               SM3_ERR_INVALID_ARG, "moe_router: null argument");
   SM3_REQUIRE(a.E >= 1 && a.E <= R_MAXE && a.k >= 1 && a.k <= R_MAXK && a.k <= a.E, SM3_ERR_UNSUPPORTED_SHAPE,
               "moe_router: E=%d k=%d unsupported (E<=16, k<=8, k<=E)", a.E, a.k);
-  SM3_REQUIRE(a.P % 32 == 0 && a.P >= 32 && a.P <= 256 && a.C % R_KC == 0, SM3_ERR_UNSUPPORTED_SHAPE,
-              "moe_router: P=%d C=%d unsupported (P multiple of 32 <= 256, C multiple of 32)", a.P, a.C);
+  SM3_REQUIRE(a.P % 4 == 0 && a.P >= 4 && a.P <= 256 && a.C % R_KC == 0, SM3_ERR_UNSUPPORTED_SHAPE,
+              "moe_router: P=%d C=%d unsupported (P multiple of 4 <= 256, C multiple of 32)", a.P, a.C);
   SM3_REQUIRE(!a.noise || a.w_noise, SM3_ERR_INVALID_ARG, "moe_router: noise needs w_noise");
   const int soft = (a.noise && a.k < a.E) ? 1 : 0;
-  const int P = a.P, E = a.E;
+  const int P = (a.P + 31) / 32 * 32, E = a.E;
   const size_t smem = sizeof(float) * ((size_t)RT * (P + 1) + (size_t)E * (P + 1) + RT * (R_KC + 1) + (size_t)R_KC * (P + 1) + 8 * 3 * R_MAXE);
   const int blocks = router_blocks(a.T);
 #define SM3_ROUTER_CASE(PJ)                                                                                   \
@@ -428,7 +429,7 @@ int moe_combine_bwd(const float* dout, const float* o, const int* slot_of, const
 template <int PJ>
 __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs a, int tokens_per_warp) {
   extern __shared__ float smem[];
-  const int P = 32 * PJ, E = a.E, k = a.k;
+  const int P = 32 * PJ, PR = a.P, E = a.E, k = a.k;
   float* s_sim = smem;                 // [E][P+1] normalised
   float* s_dsim = s_sim + E * (P + 1); // [E][P+1] block accumulator
   __shared__ float s_cimp[R_MAXE];
@@ -436,9 +437,9 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = warp; e < E; e += 8) {
     float ss = 0.f;
-    for (int p = lane; p < P; p += 32) { const float s = __ldg(a.sim + p * E + e); ss += s * s; }
+    for (int p = lane; p < PR; p += 32) { const float s = __ldg(a.sim + p * E + e); ss += s * s; }
     const float inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
-    for (int p = lane; p < P; p += 32) { s_sim[e * (P + 1) + p] = __ldg(a.sim + p * E + e) * inv; s_dsim[e * (P + 1) + p] = 0.f; }
+    for (int p = lane; p < P; p += 32) { s_sim[e * (P + 1) + p] = (p < PR) ? __ldg(a.sim + p * E + e) * inv : 0.f; s_dsim[e * (P + 1) + p] = 0.f; }
   }
   if (tid == 0) {
     s_dtau = 0.f;
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
     if (t >= a.T) break;
     float pv[PJ]; float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < PJ; ++j) { pv[j] = __ldg(a.p + t * P + lane + 32 * j); ss += pv[j] * pv[j]; }
+    for (int j = 0; j < PJ; ++j) { pv[j] = (lane + 32 * j < PR) ? __ldg(a.p + t * PR + lane + 32 * j) : 0.f; ss += pv[j] * pv[j]; }
     const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
     const float inv = 1.0f / nrm;
 #pragma unroll
@@ -502,13 +503,13 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
     for (int i = 0; i < PJ; ++i) pd = fmaf(pv[i], dph[i], pd);
     pd = warp_sum(pd);
 #pragma unroll
-    for (int i = 0; i < PJ; ++i) a.dp[t * P + lane + 32 * i] = (dph[i] - pv[i] * pd) * inv;
+    for (int i = 0; i < PJ; ++i) if (lane + 32 * i < PR) a.dp[t * PR + lane + 32 * i] = (dph[i] - pv[i] * pd) * inv;
   }
   if (lane == 0 && unclamped) atomicAdd(&s_dtau, dtau);
   __syncthreads();
   for (int i = tid; i < E * P; i += 256) {
     const int e = i / P, p = i % P;
-    atomicAdd(a.dsim_hat + p * E + e, s_dsim[e * (P + 1) + p]);
+    if (p < PR) atomicAdd(a.dsim_hat + p * E + e, s_dsim[e * (P + 1) + p]);
   }
   if (tid == 0) atomicAdd(a.dtemperature, s_dtau);
 }
@@ -516,15 +517,16 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
 int moe_router_bwd(const RouterBwdArgs& a, cudaStream_t stream) {
   SM3_REQUIRE(a.p && a.sim && a.temperature && a.top_idx && a.top_gate && a.dgate && a.logits && a.importance && a.dp &&
               a.dsim_hat && a.dtemperature, SM3_ERR_INVALID_ARG, "moe_router_bwd: null argument");
-  SM3_REQUIRE(a.P % 32 == 0 && a.P <= 256 && a.E <= R_MAXE && a.k <= R_MAXK, SM3_ERR_UNSUPPORTED_SHAPE, "moe_router_bwd: shape");
-  const size_t smem = sizeof(float) * 2 * (size_t)a.E * (a.P + 1);
+  SM3_REQUIRE(a.P % 4 == 0 && a.P <= 256 && a.E <= R_MAXE && a.k <= R_MAXK, SM3_ERR_UNSUPPORTED_SHAPE, "moe_router_bwd: shape");
+  const int Ppad = (a.P + 31) / 32 * 32;
+  const size_t smem = sizeof(float) * 2 * (size_t)a.E * (Ppad + 1);
   long long warps = (long long)num_sms() * 16;
   int tpw = (int)((a.T + warps - 1) / warps);
   if (tpw < 4) tpw = 4;
   warps = ((long long)a.T + tpw - 1) / tpw;
   const int blocks = (int)((warps + 7) / 8);
 #define SM3_RB_CASE(PJ) case PJ: moe_router_bwd_kernel<PJ><<<blocks, 256, smem, stream>>>(a, tpw); break;
-  switch (a.P / 32) {
+  switch (Ppad / 32) {
     SM3_RB_CASE(1) SM3_RB_CASE(2) SM3_RB_CASE(3) SM3_RB_CASE(4) SM3_RB_CASE(5) SM3_RB_CASE(6) SM3_RB_CASE(7) SM3_RB_CASE(8)
     default: SM3_REQUIRE(false, SM3_ERR_UNSUPPORTED_SHAPE, "moe_router_bwd: P=%d", a.P);
   }

@@ -160,7 +160,9 @@ def test_router_matches_oracle_bit_exact(ops, C, E, k, T, tau):
         assert (gaps[mism] < 1e-5 * math.exp(min(tau, math.log(100)))).all(), f'{int(mism.sum())} real routing mismatches'
         assert mism.sum() <= 2
     ok = ~mism
-    assert (r['top_gate'].cpu()[ok] - info['top_gates'][ok]).abs().max() < 2e-6
+    scale = math.exp(min(tau, math.log(100)))
+    # gates = softmax of logits that reach +-scale: fp32 rounding of the logits (1e-7 * scale) carries through exp
+    assert (r['top_gate'].cpu()[ok] - info['top_gates'][ok]).abs().max() < 2e-6 + 3e-7 * scale
     assert rel(r['logits'], info['logits']) < 2e-6
     plan = ops.moe_plan(r['partials'], T=T, E=E, k=k)
     imp = gates.sum(0)
