@@ -210,7 +210,7 @@ class ConvNeXt_moe(BaseModule):
         self.stem_patch_size = stem_patch_size
         self.norm_eps = norm_cfg.get('eps', 1e-5)
 
-        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(self.depths))]
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(self.depths), device='cpu')]
         block_idx = 0
         self.downsample_layers = nn.ModuleList()
         stem = nn.Sequential(

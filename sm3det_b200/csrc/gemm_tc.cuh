@@ -414,6 +414,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     const uint32_t adv_a = A_MN ? (uint32_t)(BK * p.a_sk) : (uint32_t)BK;
     const uint32_t adv_b = B_MN ? (uint32_t)(BK * p.b_sk) : (uint32_t)BK;
 
+    const bool b_gather = B_MN && (p.b_k_index != nullptr);   // B rows come through an index (expert wgrad)
     auto setup_tile = [&](const Tile& tl) {
       k_begin = tl.k_begin; k_end = tl.k_end;
       baseB = p.B + (long long)tl.group * p.b_group_stride;
@@ -450,7 +451,8 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int koff = (pi >> 2) * 8 + (pi & 3) + 4 * h;
-            off[i][h] = (uint32_t)((long long)(tl.k_begin + koff) * s_k + mn0 + mnl);
+            off[i][h] = (!is_a && b_gather) ? (uint32_t)(mn0 + mnl)
+                                            : (uint32_t)((long long)(tl.k_begin + koff) * s_k + mn0 + mnl);
             vmask |= 1u << (2 * i + h);
           }
         }
@@ -468,7 +470,6 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     };
 
     // issue the global loads of the current k-block, then step the offsets to the next one
-    const bool b_gather = B_MN && (p.b_k_index != nullptr);
     auto load_kb = [&](float4 (&r)[MAX_UNITS][2]) {
       const int k0 = k_begin + kb_cur * BK;
       const bool kin = (k0 + 4 * f4 + 4 <= k_end);          // K-major operands: this lane's 4 k values
