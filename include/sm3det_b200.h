@@ -125,6 +125,7 @@ typedef struct sm3_router_args {
   const float* temperature; const float* w_noise; const float* noise;
   int32_t T, C, P, E, k;
   int32_t* top_idx; float* top_gate; float* logits; float* top_vals; float* p_out;
+  float* sigma; int32_t* top_idx_m;   /* optional, noisy gating: noise stddev [T,E], experts [T,min(k+1,E)] */
   float* partials;                 /* [sm3_moe_router_blocks(T)][3*E] workspace */
 } sm3_router_args;
 int sm3_moe_router_blocks(int32_t T);
@@ -162,6 +163,9 @@ typedef struct sm3_router_bwd_args {
   const float* importance; const float* loss_scale;
   int32_t T, P, E, k;
   float* dp; float* dsim_hat; float* dtemperature;
+  /* noisy gating (all NULL for clean gating): backward of :200-204 and _prob_in_top_k :152-174 */
+  const float* noise; const float* sigma; const float* top_vals; const int32_t* top_idx_m; const float* load;
+  float* dr;                          /* [T,32]: d(v @ w_noise), zero padded */
 } sm3_router_bwd_args;
 int sm3_moe_router_bwd(const sm3_router_bwd_args* args, void* stream);
 int sm3_moe_router_bwd_finalize(const float* dsim_hat, const float* sim_matrix, float* dsim, int32_t P, int32_t E,

@@ -41,6 +41,7 @@ class RouterArgs(C.Structure):
         ('temperature', c_f32p), ('w_noise', c_f32p), ('noise', c_f32p),
         ('T', C.c_int32), ('C', C.c_int32), ('P', C.c_int32), ('E', C.c_int32), ('k', C.c_int32),
         ('top_idx', c_i32p), ('top_gate', c_f32p), ('logits', c_f32p), ('top_vals', c_f32p), ('p_out', c_f32p),
+        ('sigma', c_f32p), ('top_idx_m', c_i32p),
         ('partials', c_f32p),
     ]
 
@@ -89,6 +90,8 @@ class RouterBwdArgs(C.Structure):
         ('importance', c_f32p), ('loss_scale', c_f32p),
         ('T', C.c_int32), ('P', C.c_int32), ('E', C.c_int32), ('k', C.c_int32),
         ('dp', c_f32p), ('dsim_hat', c_f32p), ('dtemperature', c_f32p),
+        ('noise', c_f32p), ('sigma', c_f32p), ('top_vals', c_f32p), ('top_idx_m', c_i32p), ('load', c_f32p),
+        ('dr', c_f32p),
     ]
 
 

@@ -73,7 +73,7 @@ int sm3_moe_router(const sm3_router_args* a, void* stream) {
   r.v = a->v; r.wp = a->proj_weight; r.bp = a->proj_bias; r.sim = a->sim_matrix; r.temperature = a->temperature;
   r.w_noise = a->w_noise; r.noise = a->noise;
   r.T = a->T; r.C = a->C; r.P = a->P; r.E = a->E; r.k = a->k;
-  r.top_idx = a->top_idx; r.top_gate = a->top_gate; r.logits = a->logits; r.top_vals = a->top_vals; r.p_out = a->p_out;
+  r.top_idx = a->top_idx; r.top_gate = a->top_gate; r.logits = a->logits; r.top_vals = a->top_vals; r.p_out = a->p_out; r.sigma = a->sigma; r.top_idx_m = a->top_idx_m;
   r.partials = a->partials; r.nblocks = router_blocks(a->T);
   return moe_router(r, S(stream));
 }
@@ -108,6 +108,7 @@ int sm3_moe_router_bwd(const sm3_router_bwd_args* a, void* stream) {
   r.p = a->p; r.sim = a->sim_matrix; r.temperature = a->temperature; r.top_idx = a->top_idx; r.top_gate = a->top_gate;
   r.dgate = a->dgate; r.logits = a->logits; r.importance = a->importance; r.loss_scale = a->loss_scale;
   r.T = a->T; r.P = a->P; r.E = a->E; r.k = a->k; r.dp = a->dp; r.dsim_hat = a->dsim_hat; r.dtemperature = a->dtemperature;
+  r.noise = a->noise; r.sigma = a->sigma; r.top_vals = a->top_vals; r.top_idx_m = a->top_idx_m; r.load = a->load; r.dr = a->dr;
   return moe_router_bwd(r, S(stream));
 }
 int sm3_moe_router_bwd_finalize(const float* dsim_hat, const float* sim, float* dsim, int32_t P, int32_t E, void* stream) {

@@ -43,6 +43,8 @@ struct RouterArgs {
   float* logits;         // [T,E] optional (clean logits; needed by backward)
   float* top_vals;       // [T,k+1] optional: selected (noisy) logits incl. the (k+1)-th threshold
   float* p_out;          // [T,P] optional: projection Wp v + bp (saved for backward)
+  float* sigma;          // [T,E] optional: noise stddev softplus(v w_noise)+0.01 (noisy gating)
+  int* top_idx_m;        // [T,min(k+1,E)] optional: all selected experts incl. the (k+1)-th
   float* partials;       // [nblocks][3E] per-block importance / load / hard-count partial sums (workspace)
   int nblocks;           // filled by router_blocks()
 };
@@ -86,6 +88,9 @@ struct RouterBwdArgs {
   const float* logits;       // [T,E] clean logits saved by the router
   const float* importance;   // [E]
   const float* loss_scale;   // [1] device scalar: upstream grad of this layer's loss (or null)
+  // noisy gating only (null for clean gating):
+  const float* noise; const float* sigma; const float* top_vals; const int* top_idx_m; const float* load;
+  float* dr;                 // [T,32] out: gradient w.r.t. v @ w_noise, zero padded to 32 columns
   int T, P, E, k;
   float* dp;                 // [T,P] out
   float* dsim_hat;           // [P,E] accumulated (pre-zeroed)

@@ -127,10 +127,11 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
       }
     }
     if (a.logits && lane < E) {
-      float cv = 0.f;
+      float cv = 0.f, sv = 1.f;
 #pragma unroll
-      for (int e = 0; e < R_MAXE; ++e) if (e == lane) cv = clean[e];
+      for (int e = 0; e < R_MAXE; ++e) if (e == lane) { cv = clean[e]; sv = sig[e]; }
       a.logits[t * E + lane] = cv;
+      if (a.sigma) a.sigma[t * E + lane] = sv;
     }
     // top-(k+1), ties -> lowest expert id
     int idx[R_MAXK + 1]; float val[R_MAXK + 1];
@@ -161,6 +162,10 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
       if (a.top_vals) {
 #pragma unroll
         for (int r = 0; r < R_MAXK + 1; ++r) if (r < m) a.top_vals[t * m + r] = val[r];
+      }
+      if (a.top_idx_m) {
+#pragma unroll
+        for (int r = 0; r < R_MAXK + 1; ++r) if (r < m) a.top_idx_m[t * m + r] = idx[r];
       }
     }
     // statistics for expert e = lane
@@ -420,21 +425,41 @@ int moe_combine_bwd(const float* dout, const float* o, const int* slot_of, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Router backward (clean gating).  Per token:
-//   dG_j   = dgate_j + loss_scale * 0.01 * dCV2/dimportance[idx_j]           (importance = sum_t gates)
-//   dval_j = g_j (dG_j - sum_i g_i dG_i)                                     (softmax over the k kept logits)
-//   dcos_e = dval * scale ; dtau += dval * logit (if tau <= ln 100)
+// Router backward.  Lane e of the token's warp owns expert e.  Per token:
+//   dG_j   = dgate_j + c_imp[idx_j]                    c_imp = up * 0.01 * dCV2/d importance
+//   dval_j = g_j (dG_j - sum_i g_i dG_i)               softmax over the k kept (noisy) logits
+//   noisy & k < E (soft load, _prob_in_top_k :152-174):  z_e = (l_e - thr_e) / sigma_e,
+//       dz_e = c_load[e] * pdf(z_e);  dl_e += dz_e / sigma_e;  dthr_e = -dz_e / sigma_e (flows into the
+//       (k+1)-th noisy value for experts inside the top-k, into the k-th for the others);
+//       dsigma_e = -dz_e z_e / sigma_e + eps_e * dnoisy_e;  dr_e = dsigma_e * sigmoid(r_e)
+//   dl_e  += dnoisy_e ; dcos_e = dl_e * scale ; dtau += dl_e * l_e (if tau <= ln 100)
 //   dphat  = sum_e dcos_e Shat[:,e] ; dShat[:,e] += dcos_e phat ; dp = (dphat - phat <phat,dphat>) / ||p||
-// dp [T,P] feeds two tensor-core GEMMs on the host side (dWp = dp^T v, dv += dp Wp) and a colsum (dbp).
+// dp [T,P] and dr [T,32] feed tensor-core GEMMs on the host side (dWp, dw_noise, dv) and a colsum (dbp).
+__device__ __forceinline__ void cv2_grad(const float* z, int E, float up, float* out /*smem [E]*/) {
+  float m = 0.f;
+  for (int e = 0; e < E; ++e) m += __ldg(z + e);
+  m /= (float)E;
+  float s2 = 0.f;
+  for (int e = 0; e < E; ++e) { const float d = __ldg(z + e) - m; s2 += d * d; }
+  if (E > 1) s2 /= (float)(E - 1);
+  const float den = m * m + 1e-10f;
+  for (int e = 0; e < E; ++e) {
+    float g = 0.f;
+    if (E > 1) g = 2.f * (__ldg(z + e) - m) / ((float)(E - 1) * den) - 2.f * m * s2 / ((float)E * den * den);
+    out[e] = up * 1e-2f * g;
+  }
+}
+
 template <int PJ>
 __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs a, int tokens_per_warp) {
   extern __shared__ float smem[];
   const int P = 32 * PJ, PR = a.P, E = a.E, k = a.k;
   float* s_sim = smem;                 // [E][P+1] normalised
   float* s_dsim = s_sim + E * (P + 1); // [E][P+1] block accumulator
-  __shared__ float s_cimp[R_MAXE];
+  __shared__ float s_cimp[R_MAXE], s_cload[R_MAXE];
   __shared__ float s_dtau;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool soft = (a.noise != nullptr) && (k < E);
   for (int e = warp; e < E; e += 8) {
     float ss = 0.f;
     for (int p = lane; p < PR; p += 32) { const float s = __ldg(a.sim + p * E + e); ss += s * s; }
@@ -443,25 +468,16 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
   }
   if (tid == 0) {
     s_dtau = 0.f;
-    // d(0.01*CV2(importance))/d importance_e, scaled by the upstream gradient of the layer loss
     const float up = a.loss_scale ? __ldg(a.loss_scale) : 0.f;
-    float m = 0.f;
-    for (int e = 0; e < E; ++e) m += __ldg(a.importance + e);
-    m /= (float)E;
-    float s2 = 0.f;
-    for (int e = 0; e < E; ++e) { const float d = __ldg(a.importance + e) - m; s2 += d * d; }
-    if (E > 1) s2 /= (float)(E - 1);
-    const float den = m * m + 1e-10f;
-    for (int e = 0; e < E; ++e) {
-      float g = 0.f;
-      if (E > 1) g = 2.f * (__ldg(a.importance + e) - m) / ((float)(E - 1) * den) - 2.f * m * s2 / ((float)E * den * den);
-      s_cimp[e] = up * 1e-2f * g;
-    }
+    cv2_grad(a.importance, E, up, s_cimp);
+    if (soft) cv2_grad(a.load, E, up, s_cload);
+    else for (int e = 0; e < E; ++e) s_cload[e] = 0.f;
   }
   __syncthreads();
   const float tau = __ldg(a.temperature);
   const bool unclamped = tau <= 4.605170185988092f;
   const float scale = expf(fminf(tau, 4.605170185988092f));
+  const int m = min(k + 1, E);
   float dtau = 0.f;
   const long long tb = ((long long)blockIdx.x * 8 + warp) * tokens_per_warp;
   for (int q = 0; q < tokens_per_warp; ++q) {
@@ -474,24 +490,55 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
     const float inv = 1.0f / nrm;
 #pragma unroll
     for (int j = 0; j < PJ; ++j) pv[j] *= inv;                 // phat
+    // --- gradient w.r.t. the (noisy) logit of expert `lane`
     float g[R_MAXK], dG[R_MAXK]; int idx[R_MAXK];
     float sdot = 0.f;
+    bool mine_in = false;
 #pragma unroll
     for (int j = 0; j < R_MAXK; ++j) if (j < k) {
-      idx[j] = __ldg(a.top_idx + t * k + j);
+      idx[j] = a.top_idx_m ? __ldg(a.top_idx_m + t * m + j) : __ldg(a.top_idx + t * k + j);
       g[j] = __ldg(a.top_gate + t * k + j);
-      dG[j] = __ldg(a.dgate + t * k + j) + (idx[j] >= 0 ? s_cimp[idx[j]] : 0.f);
+      dG[j] = __ldg(a.dgate + t * k + j) + s_cimp[idx[j] < 0 ? 0 : idx[j]];
       sdot += g[j] * dG[j];
+      mine_in = mine_in || (idx[j] == lane);
     }
+    float dnz = 0.f;
+#pragma unroll
+    for (int j = 0; j < R_MAXK; ++j) if (j < k && idx[j] == lane) dnz += g[j] * (dG[j] - sdot);
+    const float l_e = (lane < E) ? __ldg(a.logits + t * E + lane) : 0.f;
+    float dl = 0.f, dr = 0.f;
+    if (soft) {
+      const int idx_k = __ldg(a.top_idx_m + t * m + k);           // the (k+1)-th expert
+      const float thr_in = __ldg(a.top_vals + t * m + k), thr_out = __ldg(a.top_vals + t * m + k - 1);
+      float dthr = 0.f, dsig = 0.f, sg = 1.f, ep = 0.f;
+      if (lane < E) {
+        sg = __ldg(a.sigma + t * E + lane);
+        ep = __ldg(a.noise + t * E + lane);
+        const float z = (l_e - (mine_in ? thr_in : thr_out)) / sg;
+        const float dz = s_cload[lane] * 0.3989422804014327f * __expf(-0.5f * z * z);
+        dl = dz / sg;
+        dthr = -dz / sg;
+        dsig = -dz * z / sg;
+      }
+      const float sum_in = warp_sum(mine_in ? dthr : 0.f);
+      const float sum_out = warp_sum(mine_in ? 0.f : dthr);
+      if (lane == idx_k) dnz += sum_in;
+      if (lane == idx[k - 1]) dnz += sum_out;
+      if (lane < E) {
+        dsig += ep * dnz;
+        dr = dsig * (1.0f - __expf(-(sg - 1e-2f)));                // sigmoid(r) from softplus(r) = sigma - 0.01
+      }
+      if (a.dr) a.dr[t * 32 + lane] = (lane < E) ? dr : 0.f;
+    }
+    dl += dnz;
+    if (lane < E) dtau += dl * l_e;
+    // --- cosine-similarity backward
     float dph[PJ];
 #pragma unroll
     for (int j = 0; j < PJ; ++j) dph[j] = 0.f;
-#pragma unroll
-    for (int j = 0; j < R_MAXK; ++j) if (j < k && idx[j] >= 0) {
-      const float dval = g[j] * (dG[j] - sdot);
-      const int e = idx[j];
-      dtau += dval * __ldg(a.logits + t * E + e);
-      const float dcos = dval * scale;
+    for (int e = 0; e < E; ++e) {
+      const float dcos = __shfl_sync(0xffffffffu, dl, e) * scale;
+      if (dcos == 0.f) continue;
 #pragma unroll
       for (int i = 0; i < PJ; ++i) {
         dph[i] = fmaf(dcos, s_sim[e * (P + 1) + lane + 32 * i], dph[i]);
@@ -505,6 +552,7 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
 #pragma unroll
     for (int i = 0; i < PJ; ++i) if (lane + 32 * i < PR) a.dp[t * PR + lane + 32 * i] = (dph[i] - pv[i] * pd) * inv;
   }
+  dtau = warp_sum(dtau);
   if (lane == 0 && unclamped) atomicAdd(&s_dtau, dtau);
   __syncthreads();
   for (int i = tid; i < E * P; i += 256) {
@@ -517,6 +565,9 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
 int moe_router_bwd(const RouterBwdArgs& a, cudaStream_t stream) {
   SM3_REQUIRE(a.p && a.sim && a.temperature && a.top_idx && a.top_gate && a.dgate && a.logits && a.importance && a.dp &&
               a.dsim_hat && a.dtemperature, SM3_ERR_INVALID_ARG, "moe_router_bwd: null argument");
+  if (a.noise && a.k < a.E)
+    SM3_REQUIRE(a.sigma && a.top_vals && a.top_idx_m && a.load && a.dr, SM3_ERR_INVALID_ARG,
+                "moe_router_bwd: noisy gating needs sigma, top_vals, top_idx_m, load and dr");
   SM3_REQUIRE(a.P % 4 == 0 && a.P <= 256 && a.E <= R_MAXE && a.k <= R_MAXK, SM3_ERR_UNSUPPORTED_SHAPE, "moe_router_bwd: shape");
   const int Ppad = (a.P + 31) / 32 * 32;
   const size_t smem = sizeof(float) * 2 * (size_t)a.E * (Ppad + 1);

@@ -224,14 +224,12 @@ class MoEBlockFn(Function):
             record.append(dict(v=v, top_idx=r['top_idx'], top_gate=r['top_gate'], importance=plan['importance'],
                                load=plan['load'], loss=plan['loss'], y=y, counts=plan['counts']))
         if train:
-            if noise is not None:
-                ctx.noisy = True
-            else:
-                ctx.noisy = False
+            ctx.noisy = noise is not None and k < E
             ctx.save_for_backward(x, u, stats, v, h, a, o, dww, lnw, gamma, wp, sim, tau, row_scale, r['top_idx'],
                                   r['top_gate'], r['logits'], r['p'], slot_of, pair_token, plan['importance'],
                                   plan['seg_begin'], plan['seg_end'], plan['tile_group'], plan['num_m_tiles'],
-                                  w1s[0], w2s[0])
+                                  w1s[0], w2s[0], noise, r['sigma'], r['top_vals'], r['top_idx_m'], plan['load'],
+                                  w_noise)
             ctx.E, ctx.k, ctx.R = E, k, R
             ctx.has_noise_param = w_noise is not None
         return out.view(N, H, W, C), plan['loss'].reshape(())
@@ -239,10 +237,8 @@ class MoEBlockFn(Function):
     @staticmethod
     def backward(ctx, dout, dloss):
         (x, u, stats, v, h, a, o, dww, lnw, gamma, wp, sim, tau, rs, top_idx, top_gate, logits, p, slot_of, pair_token,
-         importance, seg_begin, seg_end, tile_group, num_m_tiles, w1, w2) = ctx.saved_tensors
-        if ctx.noisy:
-            raise NotImplementedError('sm3det_b200: backward through noisy gating is not implemented yet; '
-                                      'construct the backbone with noisy_gating=False for training')
+         importance, seg_begin, seg_end, tile_group, num_m_tiles, w1, w2, noise, sigma, top_vals, top_idx_m, load,
+         w_noise) = ctx.saved_tensors
         E, k, R = ctx.E, ctx.k, ctx.R
         N, H, W, C = x.shape
         T = N * H * W
@@ -273,16 +269,27 @@ class MoEBlockFn(Function):
         dtau = torch.zeros((1,), device=dev, dtype=torch.float32)
         dsim = torch.zeros((P, E), device=dev, dtype=torch.float32)
         lscale = dloss.reshape(1).contiguous().float()
-        dp = ops.moe_router_bwd(p, sim, tau, top_idx, top_gate, dgate, logits, importance, lscale, dsim, dtau, T=T,
-                                E=E, k=k)
+        noisy = dict(noise=noise, sigma=sigma, top_vals=top_vals, top_idx_m=top_idx_m, load=load) if ctx.noisy else None
+        dp, dr = ops.moe_router_bwd(p, sim, tau, top_idx, top_gate, dgate, logits, importance, lscale, dsim, dtau, T=T,
+                                    E=E, k=k, noisy=noisy)
         dwp = torch.zeros_like(wp)
         ops.linear_wgrad(dp, v, dwp)
         dbp = torch.zeros((P,), device=dev, dtype=torch.float32)
         ops.colsum(dp, dbp, rows=T, Cc=P)
         dv_r = ops.linear_dgrad(dp, wp)
+        dwn = None
+        if ctx.noisy:
+            # r = v @ w_noise is an [T,C]x[C,E] product with E < 32: run it as a 32-wide zero-padded GEMM pair
+            wn_t = torch.zeros((32, C), device=dev, dtype=torch.float32)
+            wn_t[:E] = w_noise.t()
+            dwn_t = torch.zeros((32, C), device=dev, dtype=torch.float32)
+            ops.linear_wgrad(dr, v, dwn_t)                             # [32,C] = dr^T v
+            dwn = dwn_t[:E].t().contiguous()
+            dv_r = ops.linear_dgrad(dr, wn_t, epilogue=EPI_RESID, resid=dv_r)
         dv = ops.gather_sum(dxp, slot_of, dv_r, T=T, Cc=C, k=k)
         dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
-        dwn = torch.zeros((C, E), device=dev, dtype=torch.float32) if ctx.has_noise_param else None
+        if dwn is None and ctx.has_noise_param:
+            dwn = torch.zeros((C, E), device=dev, dtype=torch.float32)
         grads_e = [dw1s[e] for e in range(E)] + [db1s[e] for e in range(E)] + [dw2s[e] for e in range(E)] + \
                   [db2s[e] for e in range(E)]
         return (dx, ddww, ddwb, dlnw, dlnb, dgamma, dwp, dbp, dsim, dtau, dwn, None, None, None, None, None, None,

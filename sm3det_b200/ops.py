@@ -180,7 +180,10 @@ def moe_router(v, wp, bp, sim, tau, *, T, Cc, E, k, w_noise=None, noise=None, sa
     logits = torch.empty((T, E), device=dev, dtype=torch.float32) if save else None
     p_out = torch.empty((T, P), device=dev, dtype=torch.float32) if save else None
     m = min(k + 1, E)
-    top_vals = torch.empty((T, m), device=dev, dtype=torch.float32) if (save and noise is not None) else None
+    noisy_save = save and noise is not None
+    top_vals = torch.empty((T, m), device=dev, dtype=torch.float32) if noisy_save else None
+    top_idx_m = torch.empty((T, m), device=dev, dtype=torch.int32) if noisy_save else None
+    sigma = torch.empty((T, E), device=dev, dtype=torch.float32) if noisy_save else None
     nb = lib.sm3_moe_router_blocks(T)
     partials = torch.empty((nb, 3 * E), device=dev, dtype=torch.float32)
     a.v = _p(v); a.proj_weight = _p(wp); a.proj_bias = _p(bp); a.sim_matrix = _p(sim); a.temperature = _p(tau)
@@ -188,9 +191,10 @@ def moe_router(v, wp, bp, sim, tau, *, T, Cc, E, k, w_noise=None, noise=None, sa
     a.noise = _p(noise)
     a.T, a.C, a.P, a.E, a.k = T, Cc, P, E, k
     a.top_idx = _pi(top_idx); a.top_gate = _p(top_gate); a.logits = _p(logits); a.top_vals = _p(top_vals)
-    a.p_out = _p(p_out); a.partials = _p(partials)
+    a.p_out = _p(p_out); a.partials = _p(partials); a.sigma = _p(sigma); a.top_idx_m = _pi(top_idx_m)
     _lib.check(lib.sm3_moe_router(C.byref(a), _stream()), 'sm3_moe_router')
-    return dict(top_idx=top_idx, top_gate=top_gate, logits=logits, p=p_out, top_vals=top_vals, partials=partials)
+    return dict(top_idx=top_idx, top_gate=top_gate, logits=logits, p=p_out, top_vals=top_vals, partials=partials,
+                sigma=sigma, top_idx_m=top_idx_m)
 
 
 def moe_plan(partials, *, T, E, k):
@@ -240,20 +244,27 @@ def moe_combine_bwd(dout, o, slot_of, top_idx, gate, gamma, row_scale, d_o, dgam
     return dgate
 
 
-def moe_router_bwd(p, sim, tau, top_idx, top_gate, dgate, logits, importance, loss_scale, dsim, dtau, *, T, E, k):
+def moe_router_bwd(p, sim, tau, top_idx, top_gate, dgate, logits, importance, loss_scale, dsim, dtau, *, T, E, k,
+                   noisy=None):
+    """noisy = dict(noise, sigma, top_vals, top_idx_m, load) for noisy gating; returns (dp, dr) with dr [T,32] or None."""
     lib = _lib.load()
     P = p.shape[1]
     dp = torch.empty_like(p)
+    dr = None
     dsim_hat = torch.zeros((P, E), device=p.device, dtype=torch.float32)
     a = _lib.RouterBwdArgs()
     a.p = _p(p); a.sim_matrix = _p(sim); a.temperature = _p(tau); a.top_idx = _pi(top_idx); a.top_gate = _p(top_gate)
     a.dgate = _p(dgate); a.logits = _p(logits); a.importance = importance.data_ptr(); a.loss_scale = _p(loss_scale)
     a.T, a.P, a.E, a.k = T, P, E, k
     a.dp = _p(dp); a.dsim_hat = _p(dsim_hat); a.dtemperature = _p(dtau)
+    if noisy is not None:
+        dr = torch.empty((T, 32), device=p.device, dtype=torch.float32)
+        a.noise = _p(noisy['noise']); a.sigma = _p(noisy['sigma']); a.top_vals = _p(noisy['top_vals'])
+        a.top_idx_m = _pi(noisy['top_idx_m']); a.load = noisy['load'].data_ptr(); a.dr = _p(dr)
     _lib.check(lib.sm3_moe_router_bwd(C.byref(a), _stream()), 'sm3_moe_router_bwd')
     _lib.check(lib.sm3_moe_router_bwd_finalize(_p(dsim_hat), _p(sim), _p(dsim), P, E, _stream()),
                'sm3_moe_router_bwd_finalize')
-    return dp
+    return dp, dr
 
 
 def colsum(a, out, *, rows, Cc, b=None, row_scale=None, segs=None, groups=1):

@@ -128,20 +128,30 @@ def test_list_input_and_plain_class():
     assert isinstance(r, tuple) and len(r) == 4 and torch.is_tensor(r[0])
 
 
-@pytest.mark.parametrize('name', ['mini_dense', 'mini_moe_e4k2_train_clean', 'mini2_moe_e8k2_train_clean'])
+@pytest.mark.parametrize('name', ['mini_dense', 'mini_moe_e4k2_train_clean', 'mini2_moe_e8k2_train_clean',
+                                  'mini_moe_e4k2_train_noisy', 'mini_moe_e8k3_noisy'])
 def test_backward_matches_oracle(name):
-    spec = CASES[name]
+    if name == 'mini_moe_e8k3_noisy':
+        spec = dict(CASES['mini_moe_e8k3_eval'], mode='train_noisy')
+    else:
+        spec = CASES[name]
     kw = dict(spec['kw'])
-    kw.setdefault('noisy_gating', False)
-    kw['noisy_gating'] = False
+    noisy = spec['mode'] == 'train_noisy'
+    if not noisy:
+        kw['noisy_gating'] = False
     cfg, sd, net = build(kw)
     n, h, w = spec['img']
     x = make_images(n, h, w, seed=1234)
     net.train()
+    noise = None
+    if noisy:
+        noise = make_noise(cfg, moe_token_counts(cfg, n, h, w))
+        for m, nz in zip([m for m in net.modules() if m.__class__.__name__ == 'MoE_layer'], noise):
+            m._injected_noise = nz
     rec_g, rec_c = [], []
     res_g = net(x.cuda(), record=rec_g)
     sdg = {k: (v.clone().requires_grad_(True) if 'ffn.mean' not in k and 'ffn.std' not in k else v) for k, v in sd.items()}
-    res_c = backbone_forward(sdg, cfg, x, train=True, record=rec_c)
+    res_c = backbone_forward(sdg, cfg, x, train=True, noise=noise, record=rec_c)
     has_loss = isinstance(res_c, tuple) and len(res_c) == 2 and isinstance(res_c[0], tuple)
     og, lg = res_g if has_loss else (res_g, None)
     oc, lc = res_c if has_loss else (res_c, None)
@@ -156,7 +166,7 @@ def test_backward_matches_oracle(name):
         if ref is None:
             ref = torch.zeros_like(sdg[pname])
         assert p.grad is not None, f'{pname}: every parameter must receive a (possibly zero) gradient (DDP)'
-        if 'w_noise' in pname:
+        if 'w_noise' in pname and not noisy:
             continue
         e = (p.grad.cpu() - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
         worst[pname] = e
