@@ -38,7 +38,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step')
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-images', type=int, default=2, help='images in the bounded CPU sample')
+    ap.add_argument('--cpu-images', type=int, default=1, help='images in the bounded CPU sample')
     return ap.parse_args()
 
 
@@ -93,11 +93,14 @@ def cpu_reference_step(sd, cfg, x):
 def time_cpu_reference(args, images, steps, warmup):
     from oracle.convnext_moe_oracle import OracleConfig, param_shapes
     from sm3det_b200.synth import make_images, make_state_dict
-    threads = os.cpu_count() or 1
+    # torch's CPU kernels stop scaling (and then collapse: 143 s/img at 128 threads vs 1.5 s at 16 on the 128-thread
+    # B200 host, profiles/r01_cpu_threads.txt) long before the box runs out of cores: use the best-performing count.
+    threads = int(os.environ.get('SM3_CPU_THREADS', min(16, os.cpu_count() or 1)))
     torch.set_num_threads(threads)
     cfg = OracleConfig(**MODEL_KW)
     sd = make_state_dict(param_shapes(cfg), 0, True)
     x = make_images(images, args.size, args.size, seed=1234)
+    cpu_reference_step(sd, cfg, make_images(1, 128, 128, seed=1))     # thread-pool / allocator warm-up, not timed
     for _ in range(warmup):
         cpu_reference_step(sd, cfg, x)
     t0 = time.perf_counter()
@@ -152,6 +155,11 @@ def gemm_roofline(net, x, peaks):
     finally:
         ops.gemm = orig
     tot_ms = sum(a.elapsed_time(b) for a, b, *_ in rec)
+    if os.environ.get('SM3_GEMM_TABLE'):
+        with open(os.environ['SM3_GEMM_TABLE'], 'w') as f:
+            for a, b, fl, M, N, K, sched in rec:
+                ms = a.elapsed_time(b)
+                f.write(f'M={M} N={N} K={K} sched={sched} ms={ms:.4f} tflops={fl / ms * 1e-9:.1f}\n')
     # grouped / split-K launches: M (or K) is the padded pair space; close enough for the aggregate (pad <= 1.5 %)
     tot_flops = sum(r[2] for r in rec)
     peak = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0

@@ -61,6 +61,8 @@ typedef struct sm3_gemm_args {
   const float* B; int64_t b_stride_mn, b_stride_k, b_group_stride;
   const int32_t* a_row_index;      /* optional row gather of A (K-major A); -1 = zero row */
   const int32_t* b_k_index;        /* optional gather of B along the reduction index (MN-major B) */
+  const uint16_t* b_packed;        /* optional pre-split weight image from sm3_gemm_pack_b (then B may be NULL) */
+  int64_t b_packed_group_stride;   /* bf16 elements between the packed images of consecutive groups */
   int32_t M, N, K;
   int32_t tile_n;                  /* 0 = auto */
   int32_t sched;
@@ -77,6 +79,13 @@ typedef struct sm3_gemm_args {
   const float* resid; int64_t ld_resid;
 } sm3_gemm_args;
 int sm3_gemm(const sm3_gemm_args* args, void* stream);
+/* Weights are constant across the tokens of a step: split them into bf16 hi/lo ONCE per optimizer step, already
+ * in the tile order / swizzle the kernel's shared-memory stages use, so the GEMM brings a whole k-block of B in
+ * with a single cp.async.bulk.  B(n,k) is read at B + n*stride_mn + k*stride_k (any majorness: the forward uses
+ * W[N,K], the dgrad the same storage as B(n=k', k=n')).  Output: sm3_gemm_packed_elems(N,K) bf16 per group. */
+int64_t sm3_gemm_packed_elems(int32_t N, int32_t K);
+int sm3_gemm_pack_b(const float* B, int64_t stride_mn, int64_t stride_k, int64_t group_stride, int32_t groups,
+                    int32_t N, int32_t K, uint16_t* out, void* stream);
 
 /* ---- LayerNorm over channels (F.layer_norm, eps inside rsqrt, biased variance) ---------------
  * Replaces LayerNorm2d.forward (convnext_moe.py:34-47) at :351 (block norm), :549-551 (downsample

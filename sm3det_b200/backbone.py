@@ -102,6 +102,29 @@ class MoE_layer(nn.Module):
         return w1 + b1 + w2 + b2
 
 
+class PackCache:
+    """Per-module cache of the pre-split (bf16 hi/lo, tile-ordered) weight images the GEMM bulk-copies.
+
+    An entry is rebuilt when any of its parameters changed in place (tensor version counters, which every
+    optimizer step / load_state_dict bumps) or moved (data_ptr); it lives and dies with the owning module.
+    """
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, name, params, transposed):
+        from . import ops
+        key = tuple(p._version for p in params) + (params[0].data_ptr(),)
+        hit = self._d.get((name, transposed))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            packed = ops.pack_weight(params[0], transposed=transposed, groups=len(params),
+                                     out=None if hit is None else hit[1][0])
+        self._d[(name, transposed)] = (key, packed)
+        return packed
+
+
 class ConvNeXtBlock(nn.Module):
     def __init__(self, in_channels, norm_cfg, mlp_ratio=4., MoE_cfg=None, drop_path_rate=0.,
                  layer_scale_init_value=1e-6):
@@ -119,6 +142,7 @@ class ConvNeXtBlock(nn.Module):
             raise NotImplementedError('sm3det_b200: layer_scale_init_value must be > 0 (gamma is fused in the epilogue)')
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones((in_channels)), requires_grad=True)
         self.drop_path_rate = float(drop_path_rate)
+        self._packs = PackCache()
 
     def _row_scale(self, x):
         """timm DropPath as a per-token scale (per-sample Bernoulli(keep) / keep), None when inactive."""
@@ -138,11 +162,16 @@ class ConvNeXtBlock(nn.Module):
         rs = self._row_scale(x)
         eps = self.norm.eps
         dw = self.depthwise_conv
+        grad = torch.is_grad_enabled()
+        pc = self._packs
         if self.MoE_cfg is None:
             f = self.ffn
+            w1, w2 = f.pointwise_conv1.weight, f.pointwise_conv2.weight
+            packs = {'w1': pc.get('w1', [w1], False), 'w2': pc.get('w2', [w2], False)}
+            if grad:
+                packs['w1_t'] = pc.get('w1', [w1], True)
             out = Fn.DenseBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias,
-                                        f.pointwise_conv1.weight, f.pointwise_conv1.bias, f.pointwise_conv2.weight,
-                                        f.pointwise_conv2.bias, self.gamma, rs, eps)
+                                        w1, f.pointwise_conv1.bias, w2, f.pointwise_conv2.bias, self.gamma, rs, eps, packs)
             return out, None
         m = self.ffn
         noise = None
@@ -153,9 +182,17 @@ class ConvNeXtBlock(nn.Module):
                 noise = torch.randn((T, m.num_experts), device=x.device, dtype=torch.float32)
             noise = noise.to(x.device, torch.float32).contiguous()
         g = m.w_gate
+        ep = m.expert_params()
+        E = m.num_experts
+        w1s, w2s = ep[0:E], ep[2 * E:3 * E]
+        packs = {'w1': pc.get('w1', w1s, False), 'w2': pc.get('w2', w2s, False)}
+        if grad:
+            packs['w1_t'] = pc.get('w1', w1s, True)
+            packs['w2_t'] = pc.get('w2', w2s, True)
+            packs['wp_t'] = pc.get('wp', [g.cosine_projector.weight], True)
         out, loss = Fn.MoEBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias, self.gamma,
                                         g.cosine_projector.weight, g.cosine_projector.bias, g.sim_matrix, g.temperature,
-                                        m.w_noise, rs, noise, eps, m.num_experts, m.k, record, *m.expert_params())
+                                        m.w_noise, rs, noise, eps, E, m.k, record, packs, *ep)
         return out, loss
 
 

@@ -26,6 +26,7 @@ int sm3_gemm(const sm3_gemm_args* a, void* stream) {
   p.A = a->A; p.a_smn = a->a_stride_mn; p.a_sk = a->a_stride_k;
   p.B = a->B; p.b_smn = a->b_stride_mn; p.b_sk = a->b_stride_k; p.b_group_stride = a->b_group_stride;
   p.a_row_index = a->a_row_index; p.b_k_index = a->b_k_index;
+  p.b_packed = a->b_packed; p.b_packed_group_stride = a->b_packed_group_stride;
   p.M = a->M; p.N = a->N; p.K = a->K; p.BN = a->tile_n;
   p.sched = a->sched; p.k_splits = a->k_splits; p.num_groups = a->num_groups;
   p.tile_group = a->tile_group; p.num_m_tiles_dev = a->num_m_tiles;
@@ -37,6 +38,12 @@ int sm3_gemm(const sm3_gemm_args* a, void* stream) {
   p.col_scale = a->col_scale; p.row_scale = a->row_scale;
   p.resid = a->resid; p.ld_resid = a->ld_resid;
   return gemm::launch(p, S(stream));
+}
+
+int64_t sm3_gemm_packed_elems(int32_t N, int32_t K) { return gemm::packed_elems(N, K); }
+int sm3_gemm_pack_b(const float* B, int64_t s_mn, int64_t s_k, int64_t group_stride, int32_t groups, int32_t N, int32_t K,
+                    uint16_t* out, void* stream) {
+  return gemm::pack_b(B, s_mn, s_k, group_stride, groups, N, K, out, S(stream));
 }
 
 int sm3_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int64_t T, int32_t C,

@@ -16,11 +16,68 @@ int pick_bn(int N) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+long long packed_elems(int N, int K) {
+  const long long kblocks = (K + BK - 1) / BK;
+  return (long long)N * kblocks * BK * 2;     // hi + lo planes, K padded to a multiple of 32
+}
+
+// one thread per 16-byte chunk (8 k-values of one row)
+__global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ B, long long s_mn, long long s_k,
+                                                    long long group_stride, int N, int K, int BN, uint16_t* __restrict__ out,
+                                                    long long chunks_per_group) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chunks_per_group) return;
+  const int g = blockIdx.y;
+  const int kblocks = (K + BK - 1) / BK;
+  // chunk index -> (row n fastest, then chunk c, then k-block): consecutive threads read consecutive rows
+  const int n = (int)(i % N);
+  const long long r = i / N;
+  const int c = (int)(r % 4), kb = (int)(r / 4);
+  const float* src = B + (long long)g * group_stride + (long long)n * s_mn;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) {
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = kb * BK + c * 8 + e + q;
+      v[q] = (k < K) ? __ldg(src + (long long)k * s_k) : 0.f;
+    }
+    const uint32_t u0 = __float_as_uint(v[0]), u1 = __float_as_uint(v[1]);
+    hi[e / 2] = __byte_perm(u0, u1, 0x7632);
+    const uint32_t r0 = __float_as_uint(v[0] - __uint_as_float(u0 & 0xFFFF0000u)) + 0x8000u;
+    const uint32_t r1 = __float_as_uint(v[1] - __uint_as_float(u1 & 0xFFFF0000u)) + 0x8000u;
+    lo[e / 2] = __byte_perm(r0, r1, 0x7632);
+  }
+  const int nt = n / BN, row = n % BN;
+  uint8_t* tile = reinterpret_cast<uint8_t*>(out + (long long)g * ((long long)N * kblocks * BK * 2)) +
+                  ((long long)nt * kblocks + kb) * ((long long)BN * 128);
+  const uint32_t o = kmajor_sw64_offset((uint32_t)row, (uint32_t)c);
+  *reinterpret_cast<uint4*>(tile + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(tile + (long long)BN * 64 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+int pack_b(const float* B, long long s_mn, long long s_k, long long group_stride, int groups, int N, int K,
+           uint16_t* out, cudaStream_t stream) {
+  SM3_REQUIRE(B && out && N > 0 && K > 0 && groups >= 1, SM3_ERR_INVALID_ARG, "gemm pack: bad argument");
+  const int BN = pick_bn(N);
+  SM3_REQUIRE(BN > 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm pack: N=%d has no tile width", N);
+  SM3_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, SM3_ERR_INVALID_ARG, "gemm pack: output must be 16B aligned");
+  const long long kblocks = (K + BK - 1) / BK;
+  const long long chunks = (long long)N * kblocks * 4;
+  dim3 grid((unsigned)((chunks + 255) / 256), (unsigned)groups);
+  pack_b_kernel<<<grid, 256, 0, stream>>>(B, s_mn, s_k, group_stride, N, K, BN, out, chunks);
+  return check_launch("pack_b_kernel");
+}
+
 int launch(Params p, cudaStream_t stream) {
+  if (p.b_packed && !p.B) p.B = reinterpret_cast<const float*>(p.b_packed);   // B itself is not read in packed mode
   SM3_REQUIRE(p.A && p.B && p.D, SM3_ERR_INVALID_ARG, "gemm: null operand");
   SM3_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0, SM3_ERR_INVALID_ARG, "gemm: bad shape %d %d %d", p.M, p.N, p.K);
   SM3_REQUIRE((p.a_smn == 1) != (p.a_sk == 1) || (p.a_smn == 1 && p.M == 1), SM3_ERR_INVALID_ARG,
               "gemm: A needs exactly one unit stride");
+  const bool packed = p.b_packed != nullptr;
+  if (packed) { p.b_smn = p.K; p.b_sk = 1; }     // the packed image is always K-major
   SM3_REQUIRE((p.b_smn == 1) != (p.b_sk == 1), SM3_ERR_INVALID_ARG, "gemm: B needs exactly one unit stride");
   const bool a_mn = (p.a_smn == 1 && p.a_sk != 1), b_mn = (p.b_smn == 1 && p.b_sk != 1);
   if (p.BN == 0) p.BN = pick_bn(p.N);
@@ -60,20 +117,27 @@ int launch(Params p, cudaStream_t stream) {
   // 32-bit element offsets inside the kernel: every operand must span < 2^32 floats (16 GiB)
   {
     const long long a_ext = a_mn ? (long long)p.K * p.a_sk : (long long)(p.a_row_index ? (1LL << 31) / (p.a_smn ? p.a_smn : 1) : p.M) * p.a_smn;
-    const long long b_ext = b_mn ? (long long)(p.b_k_index ? 1 : p.K) * p.b_sk + p.N : (long long)p.N * p.b_smn;
+    const long long b_ext = packed ? 0 : b_mn ? (long long)(p.b_k_index ? 1 : p.K) * p.b_sk + p.N : (long long)p.N * p.b_smn;
     SM3_REQUIRE(a_ext < (1LL << 32) && b_ext < (1LL << 32), SM3_ERR_UNSUPPORTED_SHAPE, "gemm: operand larger than 2^32 elements");
   }
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   if (grid < 1) grid = 1;
-#define SM3_GEMM_LAUNCH(AMN, BMN)                                                                                   \
-  do {                                                                                                              \
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES); \
-    gemm_bf16x3_kernel<AMN, BMN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);                                     \
+#define SM3_GEMM_LAUNCH(AMN, BMN, BPK)                                                                                   \
+  do {                                                                                                                   \
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<AMN, BMN, BPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES); \
+    gemm_bf16x3_kernel<AMN, BMN, BPK><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);                                     \
   } while (0)
-  if (!a_mn && !b_mn) SM3_GEMM_LAUNCH(false, false);
-  else if (!a_mn && b_mn) SM3_GEMM_LAUNCH(false, true);
-  else if (a_mn && b_mn) SM3_GEMM_LAUNCH(true, true);
+  if (packed) {
+    SM3_REQUIRE(!a_mn && p.sched != SCHED_SPLITK && p.BN == pick_bn(p.N), SM3_ERR_INVALID_ARG,
+                "gemm: packed B needs K-major A, a dense/grouped schedule and the default tile width");
+    SM3_REQUIRE((reinterpret_cast<uintptr_t>(p.b_packed) & 15u) == 0 && (p.b_packed_group_stride % 8) == 0,
+                SM3_ERR_INVALID_ARG, "gemm: packed B must be 16B aligned");
+    SM3_GEMM_LAUNCH(false, false, true);
+  }
+  else if (!a_mn && !b_mn) SM3_GEMM_LAUNCH(false, false, false);
+  else if (!a_mn && b_mn) SM3_GEMM_LAUNCH(false, true, false);
+  else if (a_mn && b_mn) SM3_GEMM_LAUNCH(true, true, false);
   else SM3_REQUIRE(false, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major A with K-major B is not instantiated");
 #undef SM3_GEMM_LAUNCH
   return check_launch("gemm_bf16x3_kernel");

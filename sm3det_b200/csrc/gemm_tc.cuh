@@ -57,6 +57,8 @@ struct Params {
   const float* B; long long b_smn, b_sk; long long b_group_stride;
   const int* a_row_index;   // optional gather of A rows (K-major A only); -1 -> zero row
   const int* b_k_index;     // optional gather of B along the reduction index (MN-major B only); -1 -> zero
+  // pre-split weights (see pack_b): tile-ordered bf16 hi/lo images brought in with one cp.async.bulk per k-block
+  const uint16_t* b_packed; long long b_packed_group_stride;   // stride in bf16 elements
   int M, N, K, BN;
   // schedule
   int sched;
@@ -241,7 +243,7 @@ __device__ __forceinline__ void split4(const float4& x, uint32_t& h01, uint32_t&
 // 2 k-rows x 128 mn (MN-major); unit u of a k-block belongs to producer warp u % 7.  All per-tile
 // address arithmetic is hoisted: a thread keeps one 32-bit element offset per (unit, half) and
 // advances it by a constant per k-block.
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool B_PACKED>
 __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -255,7 +257,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), NUM_PROD_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), NUM_PROD_WARPS + (B_PACKED ? 1 : 0)); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -380,8 +382,9 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           for (int j = 0; j < BK / 16; ++j) {
             const uint64_t ahi = make_smem_desc(sb + OFF_A_HI + j * a_kstep, A_MN);
             const uint64_t alo = make_smem_desc(sb + OFF_A_LO + j * a_kstep, A_MN);
+            const uint32_t b_lo_off = B_PACKED ? OFF_B_HI + (uint32_t)p.BN * 64u : OFF_B_LO;   // packed: lo follows hi
             const uint64_t bhi = make_smem_desc(sb + OFF_B_HI + j * b_kstep, B_MN);
-            const uint64_t blo = make_smem_desc(sb + OFF_B_LO + j * b_kstep, B_MN);
+            const uint64_t blo = make_smem_desc(sb + b_lo_off + j * b_kstep, B_MN);
             tc_mma(tmem_d, alo, bhi, idesc, (kb > 0 || j > 0) ? 1u : 0u);
             tc_mma(tmem_d, ahi, blo, idesc, 1u);
             tc_mma(tmem_d, ahi, bhi, idesc, 1u);
@@ -400,16 +403,18 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     const bool odd = lane & 1;
     constexpr int units_a = 16;
     const int segs_b = (p.BN + 127) / 128;
-    const int units_b = B_MN ? 16 * segs_b : p.BN / 8;
+    const int units_b = B_PACKED ? 0 : (B_MN ? 16 * segs_b : p.BN / 8);
     const int units = units_a + units_b;
     // lane-constant parts of the shared-memory store offsets
     const uint32_t st_k = (uint32_t)((2 * sub + (odd ? 1 : 0)) * 64 + ((((uint32_t)f4 >> 1) ^ (uint32_t)sub) << 4));
     const uint32_t cc = (uint32_t)(lane >> 1) & 7u, g_lane = (uint32_t)lane >> 4;
 
     // per-tile state
-    uint32_t off[MAX_UNITS][2];     // element offsets from the operand base (A) / group base (B)
+    constexpr int MU = B_PACKED ? 3 : MAX_UNITS;   // units per producer warp per k-block
+    uint32_t off[MU][2];            // element offsets from the operand base (A) / group base (B)
     uint32_t vmask = 0;             // bit (2i+h): row / mn range valid
     const float* baseB = p.B;
+    const uint16_t* packB = nullptr;   // packed B image of the current tile's first k-block
     int t_cur = blockIdx.x - gridDim.x, kb_cur = 0, nkb_cur = 0, k_begin = 0, k_end = 0;
     const uint32_t adv_a = A_MN ? (uint32_t)(BK * p.a_sk) : (uint32_t)BK;
     const uint32_t adv_b = B_MN ? (uint32_t)(BK * p.b_sk) : (uint32_t)BK;
@@ -418,9 +423,14 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     auto setup_tile = [&](const Tile& tl) {
       k_begin = tl.k_begin; k_end = tl.k_end;
       baseB = p.B + (long long)tl.group * p.b_group_stride;
+      if (B_PACKED) {
+        const long long kblocks = (p.K + BK - 1) / BK;
+        packB = p.b_packed + (long long)tl.group * p.b_packed_group_stride +
+                ((long long)(tl.n0 / p.BN) * kblocks) * (2LL * p.BN * BK);
+      }
       vmask = 0;
 #pragma unroll
-      for (int i = 0; i < MAX_UNITS; ++i) {
+      for (int i = 0; i < MU; ++i) {
         const int u = wq + NUM_PROD_WARPS * i;
         off[i][0] = 0; off[i][1] = 0;
         if (u >= units) continue;
@@ -470,11 +480,11 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     };
 
     // issue the global loads of the current k-block, then step the offsets to the next one
-    auto load_kb = [&](float4 (&r)[MAX_UNITS][2]) {
+    auto load_kb = [&](float4 (&r)[MU][2]) {
       const int k0 = k_begin + kb_cur * BK;
       const bool kin = (k0 + 4 * f4 + 4 <= k_end);          // K-major operands: this lane's 4 k values
 #pragma unroll
-      for (int i = 0; i < MAX_UNITS; ++i) {
+      for (int i = 0; i < MU; ++i) {
         r[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
         r[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int u = wq + NUM_PROD_WARPS * i;
@@ -506,9 +516,9 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     };
 
     // split + pair exchange + store one k-block into its smem stage
-    auto store_kb = [&](const float4 (&r)[MAX_UNITS][2], uint32_t sb) {
+    auto store_kb = [&](const float4 (&r)[MU][2], uint32_t sb) {
 #pragma unroll
-      for (int i = 0; i < MAX_UNITS; ++i) {
+      for (int i = 0; i < MU; ++i) {
         const int u = wq + NUM_PROD_WARPS * i;
         if (u >= units) continue;
         const bool is_a = u < units_a;
@@ -546,8 +556,17 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     };
 
     int stage = 0; uint32_t phase = 0;
-    auto publish = [&](const float4 (&r)[MAX_UNITS][2]) {
+    const uint16_t* pub_src = nullptr; int pub_kb = 0;   // packed-B source of the k-block the next publish() stores
+    auto publish = [&](const float4 (&r)[MU][2]) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (B_PACKED && wq == 0 && lane == 0) {
+        // one thread: arm the stage barrier with the byte count and start the bulk copy of B's hi|lo image
+        const uint32_t bytes = (uint32_t)p.BN * 128u;
+        const uint16_t* src = pub_src + (long long)pub_kb * (2LL * p.BN * BK);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_base + stage * STAGE_BYTES + OFF_B_HI), "l"(src), "r"(bytes), "r"(full_bar(stage)) : "memory");
+      }
       store_kb(r, smem_base + stage * STAGE_BYTES);
       fence_proxy_async_smem();
       __syncwarp();
@@ -555,17 +574,19 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     };
 
-    float4 r0[MAX_UNITS][2], r1[MAX_UNITS][2];
+    float4 r0[MU][2], r1[MU][2];
+    // publish() runs one k-block behind load_kb(): remember which packed image each register set belongs to
+    const uint16_t* src0 = nullptr; const uint16_t* src1 = nullptr; int kb0 = 0, kb1 = 0;
     if (advance()) {
-      load_kb(r0);
+      src0 = packB; kb0 = kb_cur; load_kb(r0);
       while (true) {
         const bool more1 = advance();
-        if (more1) load_kb(r1);
-        publish(r0);
+        if (more1) { src1 = packB; kb1 = kb_cur; load_kb(r1); }
+        pub_src = src0; pub_kb = kb0; publish(r0);
         if (!more1) break;
         const bool more2 = advance();
-        if (more2) load_kb(r0);
-        publish(r1);
+        if (more2) { src0 = packB; kb0 = kb_cur; load_kb(r0); }
+        pub_src = src1; pub_kb = kb1; publish(r1);
         if (!more2) break;
       }
     }
@@ -581,6 +602,12 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 }
 #endif  // __CUDACC__ && SM3_GEMM_KERNEL_IMPL
 
+// Pre-split a weight operand B(n,k) (element at ptr + n*s_mn + k*s_k, `groups` matrices `group_stride` apart) into
+// the tile-ordered bf16 image the kernel bulk-copies: [group][n_tile][k_block]{ hi[BN x 32] | lo[BN x 32] } with
+// each plane in the K-major SWIZZLE_64B canonical layout.  packed_elems(N, K) bf16 elements per group.
+long long packed_elems(int N, int K);
+int pack_b(const float* B, long long s_mn, long long s_k, long long group_stride, int groups, int N, int K,
+           uint16_t* out, cudaStream_t stream);
 // Host-side launcher (gemm_tc.cu): validates shapes, fills derived fields, launches on `stream`.
 int launch(Params p, cudaStream_t stream);
 // Picks the largest supported tile width that divides N (multiple of 32, <= 256); 0 if none.

@@ -72,7 +72,7 @@ class DownsampleFn(Function):
         _, stats = ops.layernorm_fwd(x, lnw, lnb, eps, tokens=T, C=C, out=xn, out_mode=LN_PATCH2, H=H, W=W,
                                      save_stats=train)
         w2 = w.permute(0, 2, 3, 1).reshape(Co, 4 * C).contiguous()      # [Co, (kh, kw, ci)]
-        y = ops.linear_fwd(xn, w2, b)
+        y = ops.linear_fwd(xn, w2, b)          # w2 is a per-call re-ordered copy: packed on the fly by the producers
         if train:
             ctx.save_for_backward(x, stats, xn, lnw, w2)
             ctx.dims = (N, H, W, C, Co)
@@ -139,19 +139,20 @@ def _block_front_bwd(dv, dout, x, u, stats, dww, lnw):
 
 class DenseBlockFn(Function):
     @staticmethod
-    def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps):
+    def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps, packs):
         N, H, W, C = x.shape
         T = N * H * W
         train = any(ctx.needs_input_grad)
         u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
         h = torch.empty((T, 4 * C), device=x.device, dtype=torch.float32) if train else None
-        a = ops.linear_fwd(v, w1, b1, epilogue=EPI_GELU, aux_out=h)
+        a = ops.linear_fwd(v, w1, b1, epilogue=EPI_GELU, aux_out=h, packed=packs.get('w1'))
         y2 = torch.empty((T, C), device=x.device, dtype=torch.float32) if train else None
         epi = EPI_COLSCALE | EPI_RESID | (EPI_ROWSCALE if row_scale is not None else 0) | (EPI_AUXSTORE if train else 0)
         out = ops.linear_fwd(a, w2, b2, epilogue=epi, aux_out=y2, col_scale=gamma, row_scale=row_scale,
-                             resid=x.view(T, C))
+                             resid=x.view(T, C), packed=packs.get('w2'))
         if train:
             ctx.save_for_backward(x, u, stats, v, h, a, y2, dww, lnw, w1, w2, gamma, row_scale)
+            ctx.packs = packs
         return out.view(N, H, W, C)
 
     @staticmethod
@@ -169,7 +170,7 @@ class DenseBlockFn(Function):
         db2 = csum * gamma
         w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
         dh = ops.linear_dgrad(dz, w2g, epilogue=EPI_DGELU | (EPI_ROWSCALE if rs is not None else 0), aux_in=h,
-                              row_scale=rs)
+                              row_scale=rs, packed=ops.pack_weight(w2g, transposed=True))
         dzs = dz if rs is None else ops.scale_rows(dz, row_scale=rs)
         dw2 = torch.zeros_like(w2)
         ops.linear_wgrad(dzs, a, dw2, row_scale=gamma)
@@ -177,9 +178,9 @@ class DenseBlockFn(Function):
         ops.linear_wgrad(dh, v, dw1)
         db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
         ops.colsum(dh, db1, rows=T, Cc=4 * C)
-        dv = ops.linear_dgrad(dh, w1)
+        dv = ops.linear_dgrad(dh, w1, packed=ctx.packs.get('w1_t'))
         dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
-        return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None
+        return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
 
 
 def stack_expert_params(params):
@@ -202,7 +203,7 @@ class MoEBlockFn(Function):
     """x -> dwconv -> LN -> router/plan/assign -> grouped expert GEMMs -> combine (+gamma, +shortcut)."""
 
     @staticmethod
-    def forward(ctx, x, dww, dwb, lnw, lnb, gamma, wp, bp, sim, tau, w_noise, row_scale, noise, eps, E, k, record,
+    def forward(ctx, x, dww, dwb, lnw, lnb, gamma, wp, bp, sim, tau, w_noise, row_scale, noise, eps, E, k, record, packs,
                 *experts):
         N, H, W, C = x.shape
         T = N * H * W
@@ -216,8 +217,9 @@ class MoEBlockFn(Function):
         grouped = (plan['tile_group'], plan['num_m_tiles'])
         h = torch.empty((R, 4 * C), device=x.device, dtype=torch.float32) if train else None
         a = ops.linear_fwd(v, w1s[0], b1s[0], epilogue=EPI_GELU, aux_out=h, row_index=pair_token, rows=R,
-                           grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=4 * C)
-        o = ops.linear_fwd(a, w2s[0], b2s[0], rows=R, grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=C)
+                           grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=4 * C, packed=packs.get('w1'))
+        o = ops.linear_fwd(a, w2s[0], b2s[0], rows=R, grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=C,
+                           packed=packs.get('w2'))
         out, y = ops.moe_combine(o, slot_of, r['top_idx'], r['top_gate'], gamma, x.view(T, C), row_scale, T=T, Cc=C,
                                  k=k, want_y=record is not None)
         if record is not None:
@@ -231,6 +233,7 @@ class MoEBlockFn(Function):
                                   w1s[0], w2s[0], noise, r['sigma'], r['top_vals'], r['top_idx_m'], plan['load'],
                                   w_noise)
             ctx.E, ctx.k, ctx.R = E, k, R
+            ctx.packs = packs
             ctx.has_noise_param = w_noise is not None
         return out.view(N, H, W, C), plan['loss'].reshape(())
 
@@ -253,7 +256,8 @@ class MoEBlockFn(Function):
         dgate = ops.moe_combine_bwd(dz, o, slot_of, top_idx, top_gate, gamma, rs, d_o, dgamma, T=T, Cc=C, k=k)
         # experts (grouped over the padded expert segments)
         dh = torch.zeros((R, 4 * C), device=dev, dtype=torch.float32)
-        ops.linear_dgrad(d_o, w2, epilogue=EPI_DGELU, aux_in=h, out=dh, grouped=grouped, w_group_stride=4 * C * C)
+        ops.linear_dgrad(d_o, w2, epilogue=EPI_DGELU, aux_in=h, out=dh, grouped=grouped, w_group_stride=4 * C * C,
+                         packed=ctx.packs.get('w2_t'))
         dw2s = torch.zeros((E, C, 4 * C), device=dev, dtype=torch.float32)
         ops.linear_wgrad(d_o, a, dw2s, rows=R, segs=segs, num_groups=E)
         db2s = torch.zeros((E, C), device=dev, dtype=torch.float32)
@@ -263,7 +267,7 @@ class MoEBlockFn(Function):
         db1s = torch.zeros((E, 4 * C), device=dev, dtype=torch.float32)
         ops.colsum(dh, db1s, rows=R, Cc=4 * C, segs=segs, groups=E)
         dxp = torch.zeros((R, C), device=dev, dtype=torch.float32)
-        ops.linear_dgrad(dh, w1, out=dxp, grouped=grouped, w_group_stride=4 * C * C)
+        ops.linear_dgrad(dh, w1, out=dxp, grouped=grouped, w_group_stride=4 * C * C, packed=ctx.packs.get('w1_t'))
         # router
         P = wp.shape[0]
         dtau = torch.zeros((1,), device=dev, dtype=torch.float32)
@@ -276,7 +280,7 @@ class MoEBlockFn(Function):
         ops.linear_wgrad(dp, v, dwp)
         dbp = torch.zeros((P,), device=dev, dtype=torch.float32)
         ops.colsum(dp, dbp, rows=T, Cc=P)
-        dv_r = ops.linear_dgrad(dp, wp)
+        dv_r = ops.linear_dgrad(dp, wp, packed=ctx.packs.get('wp_t'))
         dwn = None
         if ctx.noisy:
             # r = v @ w_noise is an [T,C]x[C,E] product with E < 32: run it as a 32-wide zero-padded GEMM pair
@@ -292,5 +296,5 @@ class MoEBlockFn(Function):
             dwn = torch.zeros((C, E), device=dev, dtype=torch.float32)
         grads_e = [dw1s[e] for e in range(E)] + [db1s[e] for e in range(E)] + [dw2s[e] for e in range(E)] + \
                   [db2s[e] for e in range(E)]
-        return (dx, ddww, ddwb, dlnw, dlnb, dgamma, dwp, dbp, dsim, dtau, dwn, None, None, None, None, None, None,
+        return (dx, ddww, ddwb, dlnw, dlnb, dgamma, dwp, dbp, dsim, dtau, dwn, None, None, None, None, None, None, None,
                 *grads_e)

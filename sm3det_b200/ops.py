@@ -43,10 +43,12 @@ def num_sms() -> int:
 def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a_row_index=None, b_k_index=None,
          sched=SCHED_DENSE, k_splits=1, num_groups=1, tile_group=None, num_m_tiles=None, seg_begin=None,
          seg_end=None, d_group_stride=0, bias=None, bias_group_stride=0, epilogue=0, aux_out=None, aux_in=None,
-         ld_aux=0, col_scale=None, row_scale=None, resid=None, ld_resid=0, tile_n=0):
+         ld_aux=0, col_scale=None, row_scale=None, resid=None, ld_resid=0, tile_n=0, b_packed=None,
+         b_packed_group_stride=0):
     lib = _lib.load()
     a = _lib.GemmArgs()
     a.A = _p(A); a.a_stride_mn = a_smn; a.a_stride_k = a_sk
+    a.b_packed = None if b_packed is None else _p(b_packed, torch.int16); a.b_packed_group_stride = b_packed_group_stride
     a.B = _p(B); a.b_stride_mn = b_smn; a.b_stride_k = b_sk; a.b_group_stride = b_group_stride
     a.a_row_index = _pi(a_row_index); a.b_k_index = _pi(b_k_index)
     a.M, a.N, a.K = M, N, K
@@ -63,8 +65,28 @@ def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a
     return D
 
 
+def pack_weight(w, *, transposed: bool, groups: int = 1, out=None):
+    """bf16 hi/lo tile image of a weight for the GEMM's B operand (sm3_gemm_pack_b) -> (buffer, elems_per_group).
+
+    w: [N,K] (or the first of `groups` adjacent [N,K] expert weights).  transposed=False packs B(n,k) = w[n,k]
+    (forward);  transposed=True packs B(n=k', k=n') = w[n',k'] (dgrad).  Callers cache the result per parameter
+    version (sm3det_b200.backbone.PackCache); this function never caches.
+    """
+    lib = _lib.load()
+    n_, k_ = w.shape[-2], w.shape[-1]
+    if transposed:
+        N, K, s_mn, s_k = k_, n_, 1, k_
+    else:
+        N, K, s_mn, s_k = n_, k_, k_, 1
+    per = lib.sm3_gemm_packed_elems(N, K)
+    if out is None or out.numel() != groups * per:
+        out = torch.empty((groups * per,), device=w.device, dtype=torch.int16)
+    _lib.check(lib.sm3_gemm_pack_b(_p(w), s_mn, s_k, n_ * k_, groups, N, K, out.data_ptr(), _stream()), 'sm3_gemm_pack_b')
+    return out, per
+
+
 def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale=None, row_scale=None, resid=None,
-               row_index=None, rows=None, grouped=None, w_group_stride=0, bias_group_stride=0):
+               row_index=None, rows=None, grouped=None, w_group_stride=0, bias_group_stride=0, packed=None):
     """out[M,N] = epi(x[M,K] @ w[N,K]^T).  grouped = (tile_group, num_m_tiles) for expert segments."""
     K = x.shape[-1]
     N = w.shape[-2]
@@ -75,6 +97,8 @@ def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale
     kw = {}
     if grouped is not None:
         kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
+    if packed is not None:
+        kw.update(b_packed=packed[0], b_packed_group_stride=packed[1])
     gemm(A=x, a_smn=K, a_sk=1, B=w, b_smn=K, b_sk=1, b_group_stride=w_group_stride, M=M, N=N, K=K, D=out, ldd=N,
          a_row_index=row_index, bias=bias, bias_group_stride=bias_group_stride, epilogue=epi, aux_out=aux_out,
          ld_aux=N, col_scale=col_scale, row_scale=row_scale, resid=resid, ld_resid=N, **kw)
@@ -82,7 +106,7 @@ def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale
 
 
 def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, resid=None, grouped=None,
-                 w_group_stride=0):
+                 w_group_stride=0, packed=None):
     """dx[M,K] = epi(dy[M,N] @ w[N,K])   (w used as an MN-major B operand; no transposed copy)."""
     M, N = dy.shape
     K = w.shape[-1]
@@ -91,6 +115,8 @@ def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, re
     kw = {}
     if grouped is not None:
         kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
+    if packed is not None:
+        kw.update(b_packed=packed[0], b_packed_group_stride=packed[1])
     gemm(A=dy, a_smn=N, a_sk=1, B=w, b_smn=1, b_sk=K, b_group_stride=w_group_stride, M=M, N=K, K=N, D=out, ldd=K,
          epilogue=epilogue, aux_in=aux_in, ld_aux=K, row_scale=row_scale, resid=resid, ld_resid=K, **kw)
     return out

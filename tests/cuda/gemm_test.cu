@@ -28,7 +28,7 @@ struct Case {
   std::string name;
   int M, N, K, BN = 0;
   bool a_mn = false, b_mn = false;
-  bool gather = false, ints = false, kgather = false;
+  bool gather = false, ints = false, kgather = false, packed = false;
   int sched = SCHED_DENSE, groups = 1, k_splits = 1;
   int epi = 0;
 };
@@ -108,6 +108,15 @@ static void run(const Case& c) {
   float* dcs = dev(cs); float* drs = dev(rs); float* dres = dev(resid);
   p.col_scale = dcs; p.row_scale = drs; p.resid = dres; p.ld_resid = N;
 
+  uint16_t* dpack = nullptr;
+  if (c.packed) {
+    const long long per = packed_elems(N, K);
+    const int pg = (c.sched == SCHED_GROUPED) ? G : 1;
+    CK(cudaMalloc(&dpack, (size_t)pg * per * 2));
+    int prc = pack_b(dB, c.b_mn ? 1 : K, c.b_mn ? N : 1, (long long)N * K, pg, N, K, dpack, 0);
+    if (prc != 0) { printf("CASE %-28s PACK FAILED (%s)\n", c.name.c_str(), last_error()); g_fail++; return; }
+    p.b_packed = dpack; p.b_packed_group_stride = per;
+  }
   int rc = launch(p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (rc != 0 || e != cudaSuccess) {
@@ -169,7 +178,7 @@ static void run(const Case& c) {
   if (dridx) cudaFree(dridx); if (dtg) cudaFree(dtg); cudaFree(dnmt); if (dsb) cudaFree(dsb); if (dse) cudaFree(dse);
 }
 
-static void bench(const char* name, int M, int N, int K, bool a_mn, bool b_mn, int epi, int sched = SCHED_DENSE, int splits = 1) {
+static void bench(const char* name, int M, int N, int K, bool a_mn, bool b_mn, int epi, int sched = SCHED_DENSE, int splits = 1, bool packed = false) {
   float *A, *B, *D, *bias, *aux;
   CK(cudaMalloc(&A, (size_t)M * K * 4)); CK(cudaMalloc(&B, (size_t)N * K * 4)); CK(cudaMalloc(&D, (size_t)M * N * 4));
   CK(cudaMalloc(&bias, (size_t)N * 4)); CK(cudaMalloc(&aux, (size_t)M * N * 4));
@@ -179,6 +188,8 @@ static void bench(const char* name, int M, int N, int K, bool a_mn, bool b_mn, i
   if (!a_mn) { p.a_smn = K; p.a_sk = 1; } else { p.a_smn = 1; p.a_sk = M; }
   if (!b_mn) { p.b_smn = K; p.b_sk = 1; } else { p.b_smn = 1; p.b_sk = N; }
   p.sched = sched; p.k_splits = splits; p.num_groups = 1;
+  uint16_t* dpack = nullptr;
+  if (packed) { CK(cudaMalloc(&dpack, (size_t)packed_elems(N, K) * 2)); pack_b(B, b_mn ? 1 : K, b_mn ? N : 1, 0, 1, N, K, dpack, 0); p.b_packed = dpack; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) launch(p, 0);
   cudaEventRecord(e0);
@@ -216,12 +227,26 @@ int main(int argc, char** argv) {
   { Case c; c.name = "tn_f32_wgrad_splitk"; c.M = 384; c.N = 96; c.K = 5000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 7; c.epi = EPI_ATOMIC; add(c); }
   { Case c; c.name = "tn_f32_wgrad_groups"; c.M = 96; c.N = 384; c.K = 4000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 3; c.groups = 4; c.epi = EPI_ATOMIC; add(c); }
   { Case c; c.name = "tn_f32_wgrad_kgather"; c.M = 384; c.N = 96; c.K = 3000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 5; c.groups = 3; c.epi = EPI_ATOMIC; c.kgather = true; add(c); }
+  { Case c; c.name = "nt_packed";         c.M = 1000; c.N = 384; c.K = 96;  c.packed = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
+  { Case c; c.name = "nt_packed_ktail48"; c.M = 333; c.N = 96;  c.K = 48;  c.packed = true; add(c); }
+  { Case c; c.name = "nt_packed_bigK";    c.M = 256; c.N = 768; c.K = 3072; c.packed = true; add(c); }
+  { Case c; c.name = "nn_packed (dgrad)"; c.M = 450; c.N = 384; c.K = 96;  c.b_mn = true; c.packed = true; c.epi = EPI_DGELU; add(c); }
+  { Case c; c.name = "nn_packed_bn192";   c.M = 130; c.N = 192; c.K = 768; c.b_mn = true; c.packed = true; add(c); }
+  { Case c; c.name = "grouped_packed_gather"; c.M = 1024; c.N = 384; c.K = 96; c.sched = SCHED_GROUPED; c.groups = 3; c.gather = true; c.packed = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
+  { Case c; c.name = "grouped_nn_packed"; c.M = 640; c.N = 96; c.K = 384; c.sched = SCHED_GROUPED; c.groups = 4; c.b_mn = true; c.packed = true; add(c); }
   { Case c; c.name = "grouped_nt_gelu";    c.M = 1024; c.N = 384; c.K = 96; c.sched = SCHED_GROUPED; c.groups = 3; c.gather = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
   { Case c; c.name = "grouped_nn";         c.M = 640; c.N = 96; c.K = 384; c.sched = SCHED_GROUPED; c.groups = 4; c.b_mn = true; add(c); }
   if (!only_bench) for (auto& c : cases) run(c);
   if (!quick) {
     int bi = 0;
 #define B_(...) do { if (bench_idx < 0 || bench_idx == bi) bench(__VA_ARGS__); ++bi; } while (0)
+    B_("ffn1 stage2 PACKED", 32768, 1536, 384, false, false, EPI_BIAS | EPI_GELU, SCHED_DENSE, 1, true);
+    B_("ffn2 stage2 PACKED", 32768, 384, 1536, false, false, EPI_BIAS, SCHED_DENSE, 1, true);
+    B_("ffn1 stage0 PACKED", 524288, 384, 96, false, false, EPI_BIAS | EPI_GELU, SCHED_DENSE, 1, true);
+    B_("ffn2 stage0 PACKED", 524288, 96, 384, false, false, EPI_BIAS, SCHED_DENSE, 1, true);
+    B_("ffn1 stage3 PACKED", 8192, 3072, 768, false, false, EPI_BIAS, SCHED_DENSE, 1, true);
+    B_("dgrad stage2 PACKED", 32768, 384, 1536, false, true, 0, SCHED_DENSE, 1, true);
+    B_("square 8192 PACKED", 8192, 8192, 8192, false, false, 0, SCHED_DENSE, 1, true);
     B_("ffn1 stage2 (gelu)", 32768, 1536, 384, false, false, EPI_BIAS | EPI_GELU);
     B_("ffn2 stage2", 32768, 384, 1536, false, false, EPI_BIAS);
     B_("ffn1 stage0 (gelu)", 524288, 384, 96, false, false, EPI_BIAS | EPI_GELU);
