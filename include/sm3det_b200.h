@@ -54,7 +54,8 @@ enum {
   SM3_EPI_ROWSCALE = 16, /* acc *= row_scale[m]   (drop-path / gate) */
   SM3_EPI_RESID = 32,    /* acc += resid[m,n]     (shortcut) */
   SM3_EPI_ATOMIC = 64,   /* atomicAdd into D (split-K) */
-  SM3_EPI_AUXSTORE = 128 /* aux_out[m,n] = acc after bias (no activation) */
+  SM3_EPI_AUXSTORE = 128,/* aux_out[m,n] = acc after bias (no activation) */
+  SM3_EPI_COLSUM = 256   /* colsum[group][n] += column sums of the final values (bias gradient fused in dgrad) */
 };
 typedef struct sm3_gemm_args {
   const float* A; int64_t a_stride_mn, a_stride_k;
@@ -77,6 +78,7 @@ typedef struct sm3_gemm_args {
   float* aux_out; const float* aux_in; int64_t ld_aux;
   const float* col_scale; const float* row_scale;
   const float* resid; int64_t ld_resid;
+  float* colsum; int64_t colsum_group_stride;
 } sm3_gemm_args;
 int sm3_gemm(const sm3_gemm_args* args, void* stream);
 /* Weights are constant across the tokens of a step: split them into bf16 hi/lo ONCE per optimizer step, already

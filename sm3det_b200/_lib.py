@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ('aux_out', c_f32p), ('aux_in', c_f32p), ('ld_aux', C.c_int64),
         ('col_scale', c_f32p), ('row_scale', c_f32p),
         ('resid', c_f32p), ('ld_resid', C.c_int64),
+        ('colsum', c_f32p), ('colsum_group_stride', C.c_int64),
     ]
 
 

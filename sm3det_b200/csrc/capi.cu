@@ -37,6 +37,7 @@ int sm3_gemm(const sm3_gemm_args* a, void* stream) {
   p.aux_out = a->aux_out; p.aux_in = a->aux_in; p.ld_aux = a->ld_aux;
   p.col_scale = a->col_scale; p.row_scale = a->row_scale;
   p.resid = a->resid; p.ld_resid = a->ld_resid;
+  p.colsum = a->colsum; p.colsum_group_stride = a->colsum_group_stride;
   return gemm::launch(p, S(stream));
 }
 

@@ -96,6 +96,7 @@ int launch(Params p, cudaStream_t stream) {
   if (p.epi & EPI_BIAS) SM3_REQUIRE(p.bias && aligned16(p.bias) && p.bias_group_stride % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: bias");
   if (p.epi & EPI_COLSCALE) SM3_REQUIRE(p.col_scale && aligned16(p.col_scale), SM3_ERR_INVALID_ARG, "gemm: col_scale");
   if (p.epi & EPI_ROWSCALE) SM3_REQUIRE(p.row_scale, SM3_ERR_INVALID_ARG, "gemm: row_scale");
+  if (p.epi & EPI_COLSUM) SM3_REQUIRE(p.colsum && aligned16(p.colsum) && p.colsum_group_stride % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: colsum");
   if (p.epi & EPI_RESID) SM3_REQUIRE(p.resid && aligned16(p.resid) && p.ld_resid % 4 == 0, SM3_ERR_INVALID_ARG, "gemm: resid");
 
   p.n_tiles = p.N / p.BN;

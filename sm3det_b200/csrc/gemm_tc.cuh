@@ -35,7 +35,9 @@ constexpr uint32_t OFF_B_HI = 16384;
 constexpr uint32_t OFF_B_LO = 32768;
 constexpr uint32_t STAGE_BYTES = 49152;
 constexpr uint32_t BAR_BYTES = 128;
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+constexpr uint32_t EPI_STAGE_ROW_FLOATS = 36;                       // 32 columns + 4 pad: conflict-free 16-byte accesses
+constexpr uint32_t EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW_FLOATS * 4;  // per epilogue warp
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024;  // +1024 alignment slack
 constexpr uint32_t TMEM_COLS = 512;  // two 256-column fp32 accumulators
 
 enum Sched : int { SCHED_DENSE = 0, SCHED_GROUPED = 1, SCHED_SPLITK = 2 };
@@ -49,6 +51,7 @@ enum Epi : int {
   EPI_RESID = 32,     // acc += resid[m,n]
   EPI_ATOMIC = 64,    // atomicAdd(D, acc) instead of store
   EPI_AUXSTORE = 128, // aux_out[m,n] = acc (after bias), e.g. the pre-layer-scale FFN output
+  EPI_COLSUM = 256,   // colsum[group][n] += sum over the tile's rows of the final value (bias gradients)
 };
 
 struct Params {
@@ -75,6 +78,7 @@ struct Params {
   float* aux_out; const float* aux_in; long long ld_aux;
   const float* col_scale; const float* row_scale;
   const float* resid; long long ld_resid;
+  float* colsum; long long colsum_group_stride;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -276,18 +280,20 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 
   if (warp < NUM_EPI_WARPS) {
     // ============================== EPILOGUE ==============================================
+    // TMEM -> registers (lane = row) -> per-warp smem transpose -> (lane = 4 columns) so that every global
+    // access of the epilogue (stores, residual / saved-activation loads, atomics) is a coalesced 128-byte row.
     int acc = 0; uint32_t acc_phase = 0;
     const int nchunks = p.BN / 32;
+    const uint32_t stage_base = bar_base + BAR_BYTES + (uint32_t)warp * EPI_STAGE_BYTES;
+    const int rl = lane >> 3, c4 = (lane & 7) * 4;      // this lane's row-in-group-of-4 and first column of 4
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const Tile tl = decode_tile(p, t);
       if (tl.nkb() == 0) continue;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = tl.m0 + warp * 32 + lane;
-      const bool row_ok = row < p.M;
-      float* drow = p.D + (long long)tl.group * p.d_group_stride + (long long)row * p.ldd + tl.n0;
-      const float* bias = p.bias ? p.bias + (long long)tl.group * p.bias_group_stride + tl.n0 : nullptr;
-      const float rscale = ((p.epi & EPI_ROWSCALE) && row_ok) ? __ldg(p.row_scale + row) : 1.0f;
+      const int row0 = tl.m0 + warp * 32;
+      float* dbase = p.D + (long long)tl.group * p.d_group_stride;
+      const float* bias = p.bias ? p.bias + (long long)tl.group * p.bias_group_stride : nullptr;
       for (int c = 0; c < nchunks; ++c) {
         float v[32];
         tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c * 32), v);
@@ -296,66 +302,59 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (!row_ok) continue;
-        const int col0 = c * 32;
-        if (p.epi & EPI_BIAS) {
+        __syncwarp();                                     // previous chunk's reads of the stage are done
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = ldg_f4(bias + col0 + i);
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(stage_base + (uint32_t)(lane * EPI_STAGE_ROW_FLOATS + 4 * j) * 4u),
+                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+        __syncwarp();
+        const int n = tl.n0 + c * 32 + c4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), sv = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.epi & EPI_BIAS) bv = ldg_f4(bias + n);
+        if (p.epi & EPI_COLSCALE) sv = ldg_f4(p.col_scale + n);
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rl;
+          const int row = row0 + r;
+          if (row >= p.M) continue;
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                       : "r"(stage_base + (uint32_t)(r * EPI_STAGE_ROW_FLOATS + c4) * 4u) : "memory");
+          x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+          if ((p.epi & (EPI_AUXSTORE | EPI_GELU)) && p.aux_out)
+            *reinterpret_cast<float4*>(p.aux_out + (long long)row * p.ld_aux + n) = x;
+          if (p.epi & EPI_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+          if (p.epi & EPI_DGELU) {
+            const float4 h = ldg_f4(p.aux_in + (long long)row * p.ld_aux + n);
+            x.x *= gelu_erf_grad(h.x); x.y *= gelu_erf_grad(h.y); x.z *= gelu_erf_grad(h.z); x.w *= gelu_erf_grad(h.w);
+          }
+          x.x *= sv.x; x.y *= sv.y; x.z *= sv.z; x.w *= sv.w;
+          if (p.epi & EPI_ROWSCALE) { const float rs = __ldg(p.row_scale + row); x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs; }
+          if (p.epi & EPI_RESID) {
+            const float4 rr = ldg_f4(p.resid + (long long)row * p.ld_resid + n);
+            x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+          }
+          cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
+          float* dst = dbase + (long long)row * p.ldd + n;
+          if (p.epi & EPI_ATOMIC) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+          } else {
+            *reinterpret_cast<float4*>(dst) = x;
           }
         }
-        if ((p.epi & EPI_AUXSTORE) && p.aux_out) {
-          float* arow = p.aux_out + (long long)row * p.ld_aux + tl.n0 + col0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(arow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-        if (p.epi & EPI_GELU) {
-          if (p.aux_out) {
-            float* arow = p.aux_out + (long long)row * p.ld_aux + tl.n0 + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(arow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if (p.epi & EPI_COLSUM) {
+          // lanes with the same (lane & 7) hold partial sums of the same 4 columns
+          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8);  cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8);  cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+          if (lane < 8) {
+            float* cd = p.colsum + (long long)tl.group * p.colsum_group_stride + n;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cd), "f"(cs.x), "f"(cs.y), "f"(cs.z), "f"(cs.w) : "memory");
           }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        }
-        if (p.epi & EPI_DGELU) {
-          const float* arow = p.aux_in + (long long)row * p.ld_aux + tl.n0 + col0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 h = ldg_f4(arow + i);
-            v[i] *= gelu_erf_grad(h.x); v[i + 1] *= gelu_erf_grad(h.y);
-            v[i + 2] *= gelu_erf_grad(h.z); v[i + 3] *= gelu_erf_grad(h.w);
-          }
-        }
-        if (p.epi & EPI_COLSCALE) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 s = ldg_f4(p.col_scale + tl.n0 + col0 + i);
-            v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
-          }
-        }
-        if (p.epi & EPI_ROWSCALE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= rscale;
-        }
-        if (p.epi & EPI_RESID) {
-          const float* rrow = p.resid + (long long)row * p.ld_resid + tl.n0 + col0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 r = ldg_f4(rrow + i);
-            v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
-          }
-        }
-        if (p.epi & EPI_ATOMIC) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(drow + col0 + i, v[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(drow + col0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;

@@ -169,15 +169,14 @@ class DenseBlockFn(Function):
         ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
         db2 = csum * gamma
         w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
+        db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
         dh = ops.linear_dgrad(dz, w2g, epilogue=EPI_DGELU | (EPI_ROWSCALE if rs is not None else 0), aux_in=h,
-                              row_scale=rs, packed=ops.pack_weight(w2g, transposed=True))
+                              row_scale=rs, packed=ops.pack_weight(w2g, transposed=True), colsum=db1)
         dzs = dz if rs is None else ops.scale_rows(dz, row_scale=rs)
         dw2 = torch.zeros_like(w2)
         ops.linear_wgrad(dzs, a, dw2, row_scale=gamma)
         dw1 = torch.zeros_like(w1)
         ops.linear_wgrad(dh, v, dw1)
-        db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
-        ops.colsum(dh, db1, rows=T, Cc=4 * C)
         dv = ops.linear_dgrad(dh, w1, packed=ctx.packs.get('w1_t'))
         dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
         return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
@@ -256,16 +255,15 @@ class MoEBlockFn(Function):
         dgate = ops.moe_combine_bwd(dz, o, slot_of, top_idx, top_gate, gamma, rs, d_o, dgamma, T=T, Cc=C, k=k)
         # experts (grouped over the padded expert segments)
         dh = torch.zeros((R, 4 * C), device=dev, dtype=torch.float32)
+        db1s = torch.zeros((E, 4 * C), device=dev, dtype=torch.float32)
         ops.linear_dgrad(d_o, w2, epilogue=EPI_DGELU, aux_in=h, out=dh, grouped=grouped, w_group_stride=4 * C * C,
-                         packed=ctx.packs.get('w2_t'))
+                         packed=ctx.packs.get('w2_t'), colsum=db1s, colsum_group_stride=4 * C)
         dw2s = torch.zeros((E, C, 4 * C), device=dev, dtype=torch.float32)
         ops.linear_wgrad(d_o, a, dw2s, rows=R, segs=segs, num_groups=E)
         db2s = torch.zeros((E, C), device=dev, dtype=torch.float32)
         ops.colsum(d_o, db2s, rows=R, Cc=C, segs=segs, groups=E)
         dw1s = torch.zeros((E, 4 * C, C), device=dev, dtype=torch.float32)
         ops.linear_wgrad(dh, v, dw1s, rows=R, x_row_index=pair_token, segs=segs, num_groups=E)
-        db1s = torch.zeros((E, 4 * C), device=dev, dtype=torch.float32)
-        ops.colsum(dh, db1s, rows=R, Cc=4 * C, segs=segs, groups=E)
         dxp = torch.zeros((R, C), device=dev, dtype=torch.float32)
         ops.linear_dgrad(dh, w1, out=dxp, grouped=grouped, w_group_stride=4 * C * C, packed=ctx.packs.get('w1_t'))
         # router

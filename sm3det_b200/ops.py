@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 SCHED_DENSE, SCHED_GROUPED, SCHED_SPLITK = 0, 1, 2
-EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_COLSCALE, EPI_ROWSCALE, EPI_RESID, EPI_ATOMIC, EPI_AUXSTORE = 1, 2, 4, 8, 16, 32, 64, 128
+EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_COLSCALE, EPI_ROWSCALE, EPI_RESID, EPI_ATOMIC, EPI_AUXSTORE, EPI_COLSUM = 1, 2, 4, 8, 16, 32, 64, 128, 256
 LN_NHWC, LN_PATCH2, LN_NCHW = 0, 1, 2
 
 
@@ -44,7 +44,7 @@ def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a
          sched=SCHED_DENSE, k_splits=1, num_groups=1, tile_group=None, num_m_tiles=None, seg_begin=None,
          seg_end=None, d_group_stride=0, bias=None, bias_group_stride=0, epilogue=0, aux_out=None, aux_in=None,
          ld_aux=0, col_scale=None, row_scale=None, resid=None, ld_resid=0, tile_n=0, b_packed=None,
-         b_packed_group_stride=0):
+         b_packed_group_stride=0, colsum=None, colsum_group_stride=0):
     lib = _lib.load()
     a = _lib.GemmArgs()
     a.A = _p(A); a.a_stride_mn = a_smn; a.a_stride_k = a_sk
@@ -61,6 +61,7 @@ def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a
     a.aux_out = _p(aux_out); a.aux_in = _p(aux_in); a.ld_aux = ld_aux
     a.col_scale = _p(col_scale); a.row_scale = _p(row_scale)
     a.resid = _p(resid); a.ld_resid = ld_resid
+    a.colsum = _p(colsum); a.colsum_group_stride = colsum_group_stride
     _lib.check(lib.sm3_gemm(C.byref(a), _stream()), 'sm3_gemm')
     return D
 
@@ -106,7 +107,7 @@ def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale
 
 
 def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, resid=None, grouped=None,
-                 w_group_stride=0, packed=None):
+                 w_group_stride=0, packed=None, colsum=None, colsum_group_stride=0):
     """dx[M,K] = epi(dy[M,N] @ w[N,K])   (w used as an MN-major B operand; no transposed copy)."""
     M, N = dy.shape
     K = w.shape[-1]
@@ -118,7 +119,8 @@ def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, re
     if packed is not None:
         kw.update(b_packed=packed[0], b_packed_group_stride=packed[1])
     gemm(A=dy, a_smn=N, a_sk=1, B=w, b_smn=1, b_sk=K, b_group_stride=w_group_stride, M=M, N=K, K=N, D=out, ldd=K,
-         epilogue=epilogue, aux_in=aux_in, ld_aux=K, row_scale=row_scale, resid=resid, ld_resid=K, **kw)
+         epilogue=epilogue | (EPI_COLSUM if colsum is not None else 0), aux_in=aux_in, ld_aux=K, row_scale=row_scale,
+         resid=resid, ld_resid=K, colsum=colsum, colsum_group_stride=colsum_group_stride, **kw)
     return out
 
 

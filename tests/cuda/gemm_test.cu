@@ -105,6 +105,8 @@ static void run(const Case& c) {
   p.epi = c.epi;
   float* dauxo = dev(AUXO); float* daux = dev(aux);
   p.aux_out = (c.epi & EPI_GELU) ? dauxo : nullptr; p.aux_in = daux; p.ld_aux = N;
+  std::vector<float> colsum_h((size_t)G * N, 0.f);
+  float* dcolsum = dev(colsum_h); p.colsum = dcolsum; p.colsum_group_stride = (c.sched == SCHED_GROUPED) ? N : 0;
   float* dcs = dev(cs); float* drs = dev(rs); float* dres = dev(resid);
   p.col_scale = dcs; p.row_scale = drs; p.resid = dres; p.ld_resid = N;
 
@@ -126,6 +128,8 @@ static void run(const Case& c) {
   CK(cudaMemcpy(D.data(), dD, D.size() * sizeof(float), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(AUXO.data(), dauxo, AUXO.size() * sizeof(float), cudaMemcpyDeviceToHost));
 
+  CK(cudaMemcpy(colsum_h.data(), dcolsum, colsum_h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<double> colsum_ref((size_t)G * N, 0.0);
   // reference
   double max_err = 0, max_ref = 0, max_aux_err = 0; long long nbad = 0; int bad_m = -1, bad_n = -1;
   const double max_ref_bound = c.ints ? 1e-9 : (3.0 * sqrt((double)K) + 10.0);   // ~ scale of |sum_k a*b| for N(0,1) data
@@ -157,6 +161,7 @@ static void run(const Case& c) {
       if (c.epi & EPI_COLSCALE) acc *= cs[n];
       if (c.epi & EPI_ROWSCALE) acc *= rs[m];
       if (c.epi & EPI_RESID) acc += resid[(size_t)m * N + n];
+      if (c.epi & EPI_COLSUM) colsum_ref[(size_t)((c.sched == SCHED_GROUPED) ? g : 0) * N + n] += acc;
       const double got = D[(size_t)go * M * N + (size_t)m * N + n];
       const double err = fabs(got - acc);
       if (err > max_err) { max_err = err; }
@@ -165,6 +170,9 @@ static void run(const Case& c) {
       if (c.epi & EPI_GELU) max_aux_err = std::max(max_aux_err, fabs((double)AUXO[(size_t)m * N + n] - pre));
     }
   }
+  double cs_err = 0, cs_ref = 0;
+  if (c.epi & EPI_COLSUM) for (size_t i = 0; i < colsum_ref.size(); ++i) { cs_err = std::max(cs_err, fabs(colsum_ref[i] - colsum_h[i])); cs_ref = std::max(cs_ref, fabs(colsum_ref[i])); }
+  if (cs_err > 1e-4 * (cs_ref + 1.0)) { nbad++; printf("   colsum mismatch: err %.3e ref %.3e\n", cs_err, cs_ref); }
   const double rel = max_err / (max_ref + 1e-30);
   const bool ok = (c.ints ? max_err == 0.0 : rel < 4e-5) && nbad == 0 && max_aux_err < 1e-3;
   printf("CASE %-28s M=%d N=%d K=%d BN=%d a_mn=%d b_mn=%d : max_abs_err=%.3e max_ref=%.3e rel=%.3e aux_err=%.2e bad=%lld first_bad=(%d,%d) %s\n",
@@ -227,6 +235,8 @@ int main(int argc, char** argv) {
   { Case c; c.name = "tn_f32_wgrad_splitk"; c.M = 384; c.N = 96; c.K = 5000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 7; c.epi = EPI_ATOMIC; add(c); }
   { Case c; c.name = "tn_f32_wgrad_groups"; c.M = 96; c.N = 384; c.K = 4000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 3; c.groups = 4; c.epi = EPI_ATOMIC; add(c); }
   { Case c; c.name = "tn_f32_wgrad_kgather"; c.M = 384; c.N = 96; c.K = 3000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 5; c.groups = 3; c.epi = EPI_ATOMIC; c.kgather = true; add(c); }
+  { Case c; c.name = "nn_dgelu_colsum";   c.M = 450; c.N = 384; c.K = 96;  c.b_mn = true; c.epi = EPI_DGELU | EPI_COLSUM; add(c); }
+  { Case c; c.name = "grouped_nn_packed_colsum"; c.M = 640; c.N = 96; c.K = 384; c.sched = SCHED_GROUPED; c.groups = 4; c.b_mn = true; c.packed = true; c.epi = EPI_COLSUM; add(c); }
   { Case c; c.name = "nt_packed";         c.M = 1000; c.N = 384; c.K = 96;  c.packed = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
   { Case c; c.name = "nt_packed_ktail48"; c.M = 333; c.N = 96;  c.K = 48;  c.packed = true; add(c); }
   { Case c; c.name = "nt_packed_bigK";    c.M = 256; c.N = 768; c.K = 3072; c.packed = true; add(c); }
