@@ -64,6 +64,7 @@ typedef struct sm3_gemm_args {
   const int32_t* b_k_index;        /* optional gather of B along the reduction index (MN-major B) */
   const uint16_t* b_packed;        /* optional pre-split weight image from sm3_gemm_pack_b (then B may be NULL) */
   int64_t b_packed_group_stride;   /* bf16 elements between the packed images of consecutive groups */
+  const uint16_t* a_packed;        /* optional pre-split activation image from sm3_gemm_pack_act (needs b_packed) */
   int32_t M, N, K;
   int32_t tile_n;                  /* 0 = auto */
   int32_t sched;
@@ -88,6 +89,14 @@ int sm3_gemm(const sm3_gemm_args* args, void* stream);
 int64_t sm3_gemm_packed_elems(int32_t N, int32_t K);
 int sm3_gemm_pack_b(const float* B, int64_t stride_mn, int64_t stride_k, int64_t group_stride, int32_t groups,
                     int32_t N, int32_t K, uint16_t* out, void* stream);
+/* Activation operands.  mn_major = 0: X[rows, cols=K] row-major (optional row gather = the MoE dispatch, -1 =
+ * zero row) -> K-major tiles of `tile` rows (128 for A).  mn_major = 1: X[rows, cols] row-major whose ROW index is
+ * the reduction index (wgrad operands; optional row gather) -> MN-major tiles of `tile` columns (128 for A, the
+ * GEMM's tile width for B).  With both operands packed the GEMM main loop is two cp.async.bulk per k-block. */
+int64_t sm3_gemm_packed_act_elems(int64_t rows, int32_t cols, int32_t mn_major, int32_t tile);
+int sm3_gemm_pack_act(const float* X, int64_t ld, const int32_t* row_index, int64_t rows, int32_t cols,
+                      int32_t mn_major, int32_t tile, uint16_t* out, void* stream);
+int32_t sm3_gemm_tile_n(int32_t N);   /* tile width the GEMM uses for an N-column output (0 if unsupported) */
 
 /* ---- LayerNorm over channels (F.layer_norm, eps inside rsqrt, biased variance) ---------------
  * Replaces LayerNorm2d.forward (convnext_moe.py:34-47) at :351 (block norm), :549-551 (downsample

@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
     _fields_ = [
         ('A', c_f32p), ('a_stride_mn', C.c_int64), ('a_stride_k', C.c_int64),
         ('B', c_f32p), ('b_stride_mn', C.c_int64), ('b_stride_k', C.c_int64), ('b_group_stride', C.c_int64),
-        ('a_row_index', c_i32p), ('b_k_index', c_i32p), ('b_packed', C.c_void_p), ('b_packed_group_stride', C.c_int64),
+        ('a_row_index', c_i32p), ('b_k_index', c_i32p), ('b_packed', C.c_void_p), ('b_packed_group_stride', C.c_int64), ('a_packed', C.c_void_p),
         ('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32),
         ('tile_n', C.c_int32), ('sched', C.c_int32), ('k_splits', C.c_int32), ('num_groups', C.c_int32),
         ('tile_group', c_i32p), ('num_m_tiles', c_i32p), ('seg_begin', c_i32p), ('seg_end', c_i32p),
@@ -65,6 +65,9 @@ SIGNATURES = {
     'sm3_gemm': [C.POINTER(GemmArgs), _P],
     'sm3_gemm_packed_elems': [_I32, _I32],
     'sm3_gemm_pack_b': [_P, _I64, _I64, _I64, _I32, _I32, _I32, _P, _P],
+    'sm3_gemm_packed_act_elems': [_I64, _I32, _I32, _I32],
+    'sm3_gemm_pack_act': [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P],
+    'sm3_gemm_tile_n': [_I32],
     'sm3_layernorm_fwd': [_P, _P, _P, _P, _P, _I64, _I32, _F32, _I32, _I32, _I32, _P],
     'sm3_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P],
     'sm3_stem_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _P],
@@ -83,7 +86,7 @@ SIGNATURES = {
     'sm3_scale_rows': [_P, _P, _P, _P, _I64, _I32, _P],
     'sm3_moe_router_bwd': [_P, _P],
 }
-_RESTYPES = {'sm3_last_error': C.c_char_p, 'sm3_gemm_packed_elems': C.c_int64}
+_RESTYPES = {'sm3_last_error': C.c_char_p, 'sm3_gemm_packed_elems': C.c_int64, 'sm3_gemm_packed_act_elems': C.c_int64}
 
 
 class RouterBwdArgs(C.Structure):

@@ -26,7 +26,7 @@ int sm3_gemm(const sm3_gemm_args* a, void* stream) {
   p.A = a->A; p.a_smn = a->a_stride_mn; p.a_sk = a->a_stride_k;
   p.B = a->B; p.b_smn = a->b_stride_mn; p.b_sk = a->b_stride_k; p.b_group_stride = a->b_group_stride;
   p.a_row_index = a->a_row_index; p.b_k_index = a->b_k_index;
-  p.b_packed = a->b_packed; p.b_packed_group_stride = a->b_packed_group_stride;
+  p.b_packed = a->b_packed; p.b_packed_group_stride = a->b_packed_group_stride; p.a_packed = a->a_packed;
   p.M = a->M; p.N = a->N; p.K = a->K; p.BN = a->tile_n;
   p.sched = a->sched; p.k_splits = a->k_splits; p.num_groups = a->num_groups;
   p.tile_group = a->tile_group; p.num_m_tiles_dev = a->num_m_tiles;
@@ -46,6 +46,15 @@ int sm3_gemm_pack_b(const float* B, int64_t s_mn, int64_t s_k, int64_t group_str
                     uint16_t* out, void* stream) {
   return gemm::pack_b(B, s_mn, s_k, group_stride, groups, N, K, out, S(stream));
 }
+
+int64_t sm3_gemm_packed_act_elems(int64_t rows, int32_t cols, int32_t mn_major, int32_t tile) {
+  return gemm::packed_act_elems(rows, cols, mn_major, tile);
+}
+int sm3_gemm_pack_act(const float* X, int64_t ld, const int32_t* row_index, int64_t rows, int32_t cols, int32_t mn_major,
+                      int32_t tile, uint16_t* out, void* stream) {
+  return gemm::pack_act(X, ld, row_index, rows, cols, mn_major, tile, out, S(stream));
+}
+int32_t sm3_gemm_tile_n(int32_t N) { return gemm::pick_bn(N); }
 
 int sm3_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int64_t T, int32_t C,
                       float eps, int32_t out_mode, int32_t H, int32_t W, void* stream) {

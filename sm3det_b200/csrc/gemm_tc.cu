@@ -70,14 +70,122 @@ int pack_b(const float* B, long long s_mn, long long s_k, long long group_stride
   return check_launch("pack_b_kernel");
 }
 
+long long packed_act_elems(long long rows, int cols, int mn_major, int tile) {
+  if (!mn_major) {     // [rows, K=cols] -> ceil(rows/tile) row tiles x ceil(K/32) k-blocks x 2 planes of tile x 32
+    const long long rt = (rows + tile - 1) / tile, kb = (cols + BK - 1) / BK;
+    return rt * kb * 2 * (long long)tile * BK;
+  }
+  const long long ct = (cols + tile - 1) / tile, kb = (rows + BK - 1) / BK;
+  return ct * kb * 2 * (long long)(plane_bytes(tile, true) / 2);
+}
+
+// K-major activation pack: one thread per 16-byte chunk (8 k of one row); rows beyond `rows` / gathered -1 -> zeros
+__global__ void __launch_bounds__(256) pack_act_k_kernel(const float* __restrict__ X, long long ld, const int* __restrict__ row_index,
+                                                        long long rows, int K, int tile, uint16_t* __restrict__ out,
+                                                        long long chunks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chunks) return;
+  const int kblocks = (K + BK - 1) / BK;
+  // consecutive threads -> consecutive chunks of one row (coalesced 32 B each), then rows
+  const int cpr = kblocks * 4;
+  const long long row = i / cpr;
+  const int cc = (int)(i % cpr), kb = cc >> 2, c = cc & 3;
+  long long src_row = row < rows ? row : -1;
+  if (src_row >= 0 && row_index) src_row = __ldg(row_index + row);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (src_row >= 0) {
+    const int k = kb * BK + c * 8;
+    const float* src = X + src_row * ld + k;
+    if (k + 8 <= K) { const float4 a = ldg_f4(src), b = ldg_f4(src + 4); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+    else { for (int e = 0; e < 8; ++e) if (k + e < K) v[e] = __ldg(src + e); }
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) {
+    const uint32_t u0 = __float_as_uint(v[e]), u1 = __float_as_uint(v[e + 1]);
+    hi[e / 2] = __byte_perm(u0, u1, 0x7632);
+    const uint32_t r0 = __float_as_uint(v[e] - __uint_as_float(u0 & 0xFFFF0000u)) + 0x8000u;
+    const uint32_t r1 = __float_as_uint(v[e + 1] - __uint_as_float(u1 & 0xFFFF0000u)) + 0x8000u;
+    lo[e / 2] = __byte_perm(r0, r1, 0x7632);
+  }
+  const long long rt = row / tile; const int rr = (int)(row % tile);
+  uint8_t* img = reinterpret_cast<uint8_t*>(out) + (rt * kblocks + kb) * ((long long)tile * 128);
+  const uint32_t o = kmajor_sw64_offset((uint32_t)rr, (uint32_t)c);
+  *reinterpret_cast<uint4*>(img + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(img + (long long)tile * 64 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// MN-major activation pack: chunk = 8 consecutive columns of one (reduction) row
+__global__ void __launch_bounds__(256) pack_act_mn_kernel(const float* __restrict__ X, long long ld, const int* __restrict__ row_index,
+                                                         long long rows, int W, int tile, uint16_t* __restrict__ out,
+                                                         long long chunks, long long rows_pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chunks) return;
+  const int ct = (W + tile - 1) / tile;
+  const int cpr = ct * (tile / 8);                 // chunks per (padded) row, including tile padding columns
+  const long long r = i / cpr;
+  const int cc = (int)(i % cpr);
+  const int mt = cc / (tile / 8), mc = cc % (tile / 8);
+  const int col = mt * tile + mc * 8;
+  long long src_row = r < rows ? r : -1;
+  if (src_row >= 0 && row_index) src_row = __ldg(row_index + r);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (src_row >= 0 && col + 8 <= W) { const float* src = X + src_row * ld + col; a = ldg_f4(src); b = ldg_f4(src + 4); }
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) {
+    const uint32_t u0 = __float_as_uint(v[e]), u1 = __float_as_uint(v[e + 1]);
+    hi[e / 2] = __byte_perm(u0, u1, 0x7632);
+    const uint32_t r0 = __float_as_uint(v[e] - __uint_as_float(u0 & 0xFFFF0000u)) + 0x8000u;
+    const uint32_t r1 = __float_as_uint(v[e + 1] - __uint_as_float(u1 & 0xFFFF0000u)) + 0x8000u;
+    lo[e / 2] = __byte_perm(r0, r1, 0x7632);
+  }
+  const long long kblocks = rows_pad / BK;
+  const long long kb = r / BK; const uint32_t k = (uint32_t)(r % BK);
+  const uint32_t pb = plane_bytes(tile, true);
+  uint8_t* img = reinterpret_cast<uint8_t*>(out) + ((long long)mt * kblocks + kb) * (2LL * pb);
+  const uint32_t o = mnmajor_sw128_offset(k, (uint32_t)mc);
+  *reinterpret_cast<uint4*>(img + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(img + pb + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+int pack_act(const float* X, long long ld, const int* row_index, long long rows, int cols, int mn_major, int tile,
+             uint16_t* out, cudaStream_t stream) {
+  SM3_REQUIRE(X && out && rows > 0 && cols > 0, SM3_ERR_INVALID_ARG, "gemm pack_act: bad argument");
+  SM3_REQUIRE(tile >= 32 && tile <= 256 && tile % 32 == 0, SM3_ERR_INVALID_ARG, "gemm pack_act: tile=%d", tile);
+  SM3_REQUIRE(aligned16(X) && aligned16(out) && ld % 4 == 0 && cols % 4 == 0, SM3_ERR_INVALID_ARG, "gemm pack_act: alignment");
+  if (!mn_major) {
+    const long long rt = (rows + tile - 1) / tile, kb = (cols + BK - 1) / BK;
+    const long long chunks = rt * tile * kb * 4;
+    pack_act_k_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(X, ld, row_index, rows, cols, tile, out, chunks);
+  } else {
+    SM3_REQUIRE(cols % 8 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm pack_act: MN-major needs cols%%8==0");
+    const long long rows_pad = (rows + BK - 1) / BK * BK;
+    const long long ct = (cols + tile - 1) / tile;
+    const long long chunks = rows_pad * ct * (tile / 8);
+    // plane padding beyond tile/64 groups (tile = 96 or 160...) is never read by the MMA (N = tile columns)
+    pack_act_mn_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(X, ld, row_index, rows, cols, tile, out, chunks, rows_pad);
+  }
+  return check_launch("pack_act");
+}
+
 int launch(Params p, cudaStream_t stream) {
   if (p.b_packed && !p.B) p.B = reinterpret_cast<const float*>(p.b_packed);   // B itself is not read in packed mode
+  if (p.a_packed && !p.A) p.A = reinterpret_cast<const float*>(p.a_packed);
   SM3_REQUIRE(p.A && p.B && p.D, SM3_ERR_INVALID_ARG, "gemm: null operand");
   SM3_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0, SM3_ERR_INVALID_ARG, "gemm: bad shape %d %d %d", p.M, p.N, p.K);
   SM3_REQUIRE((p.a_smn == 1) != (p.a_sk == 1) || (p.a_smn == 1 && p.M == 1), SM3_ERR_INVALID_ARG,
               "gemm: A needs exactly one unit stride");
   const bool packed = p.b_packed != nullptr;
-  if (packed) { p.b_smn = p.K; p.b_sk = 1; }     // the packed image is always K-major
+  const bool apacked = p.a_packed != nullptr;
+  if (packed && !apacked) { p.b_smn = p.K; p.b_sk = 1; }     // weights-only packing: the image is always K-major
+  if (apacked) {                                             // fully packed: B's image has A's majorness
+    const bool amn = (p.a_smn == 1 && p.a_sk != 1);
+    if (amn) { p.b_smn = 1; p.b_sk = p.N; } else { p.b_smn = p.K; p.b_sk = 1; }
+  }
   SM3_REQUIRE((p.b_smn == 1) != (p.b_sk == 1), SM3_ERR_INVALID_ARG, "gemm: B needs exactly one unit stride");
   const bool a_mn = (p.a_smn == 1 && p.a_sk != 1), b_mn = (p.b_smn == 1 && p.b_sk != 1);
   if (p.BN == 0) p.BN = pick_bn(p.N);
@@ -85,7 +193,7 @@ int launch(Params p, cudaStream_t stream) {
               "gemm: N=%d has no tile width (multiple of 32 <= 256 dividing N)", p.N);
   SM3_REQUIRE(aligned16(p.A) && aligned16(p.B) && aligned16(p.D), SM3_ERR_INVALID_ARG, "gemm: pointers must be 16B aligned");
   if (!a_mn) SM3_REQUIRE(p.a_smn % 4 == 0 && p.K % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: K-major A needs K%%4==0, lda%%4==0");
-  else       SM3_REQUIRE(p.a_sk % 4 == 0 && p.M % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major A needs M%%4==0, lda%%4==0");
+  else       SM3_REQUIRE(p.a_sk % 4 == 0 && p.M % 8 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major A needs M%%8==0, lda%%4==0");
   if (!b_mn) SM3_REQUIRE(p.b_smn % 4 == 0 && p.K % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: K-major B needs K%%4==0, ldb%%4==0");
   else       SM3_REQUIRE(p.b_sk % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major B needs ldb%%4==0");
   SM3_REQUIRE(!(p.a_row_index && a_mn), SM3_ERR_INVALID_ARG, "gemm: row gather needs K-major A");
@@ -117,28 +225,36 @@ int launch(Params p, cudaStream_t stream) {
   }
   // 32-bit element offsets inside the kernel: every operand must span < 2^32 floats (16 GiB)
   {
-    const long long a_ext = a_mn ? (long long)p.K * p.a_sk : (long long)(p.a_row_index ? (1LL << 31) / (p.a_smn ? p.a_smn : 1) : p.M) * p.a_smn;
+    const long long a_ext = apacked ? 0 : a_mn ? (long long)p.K * p.a_sk : (long long)(p.a_row_index ? (1LL << 31) / (p.a_smn ? p.a_smn : 1) : p.M) * p.a_smn;
     const long long b_ext = packed ? 0 : b_mn ? (long long)(p.b_k_index ? 1 : p.K) * p.b_sk + p.N : (long long)p.N * p.b_smn;
     SM3_REQUIRE(a_ext < (1LL << 32) && b_ext < (1LL << 32), SM3_ERR_UNSUPPORTED_SHAPE, "gemm: operand larger than 2^32 elements");
   }
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   if (grid < 1) grid = 1;
-#define SM3_GEMM_LAUNCH(AMN, BMN, BPK)                                                                                   \
+#define SM3_GEMM_LAUNCH(AMN, BMN, BPK, APK)                                                                                \
   do {                                                                                                                   \
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<AMN, BMN, BPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES); \
-    gemm_bf16x3_kernel<AMN, BMN, BPK><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);                                     \
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<AMN, BMN, BPK, APK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES); \
+    gemm_bf16x3_kernel<AMN, BMN, BPK, APK><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);                                     \
   } while (0)
-  if (packed) {
+  if (apacked) {
+    SM3_REQUIRE(packed && a_mn == b_mn && p.BN == pick_bn(p.N) && !p.a_row_index && !p.b_k_index, SM3_ERR_INVALID_ARG,
+                "gemm: packed A needs packed B of the same majorness (gathers are applied by the pack kernels)");
+    SM3_REQUIRE(aligned16(p.a_packed) && aligned16(p.b_packed) && (p.b_packed_group_stride % 8) == 0, SM3_ERR_INVALID_ARG,
+                "gemm: packed operands must be 16B aligned");
+    if (a_mn) SM3_GEMM_LAUNCH(true, true, true, true);
+    else SM3_GEMM_LAUNCH(false, false, true, true);
+  }
+  else if (packed) {
     SM3_REQUIRE(!a_mn && p.sched != SCHED_SPLITK && p.BN == pick_bn(p.N), SM3_ERR_INVALID_ARG,
                 "gemm: packed B needs K-major A, a dense/grouped schedule and the default tile width");
     SM3_REQUIRE((reinterpret_cast<uintptr_t>(p.b_packed) & 15u) == 0 && (p.b_packed_group_stride % 8) == 0,
                 SM3_ERR_INVALID_ARG, "gemm: packed B must be 16B aligned");
-    SM3_GEMM_LAUNCH(false, false, true);
+    SM3_GEMM_LAUNCH(false, false, true, false);
   }
-  else if (!a_mn && !b_mn) SM3_GEMM_LAUNCH(false, false, false);
-  else if (!a_mn && b_mn) SM3_GEMM_LAUNCH(false, true, false);
-  else if (a_mn && b_mn) SM3_GEMM_LAUNCH(true, true, false);
+  else if (!a_mn && !b_mn) SM3_GEMM_LAUNCH(false, false, false, false);
+  else if (!a_mn && b_mn) SM3_GEMM_LAUNCH(false, true, false, false);
+  else if (a_mn && b_mn) SM3_GEMM_LAUNCH(true, true, false, false);
   else SM3_REQUIRE(false, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major A with K-major B is not instantiated");
 #undef SM3_GEMM_LAUNCH
   return check_launch("gemm_bf16x3_kernel");

@@ -37,7 +37,8 @@ constexpr uint32_t STAGE_BYTES = 49152;
 constexpr uint32_t BAR_BYTES = 128;
 constexpr uint32_t EPI_STAGE_ROW_FLOATS = 36;                       // 32 columns + 4 pad: conflict-free 16-byte accesses
 constexpr uint32_t EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW_FLOATS * 4;  // per epilogue warp
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024;  // +1024 alignment slack
+constexpr int COLSUM_SMEM_COLS = 3072;                              // EPI_COLSUM accumulates per CTA in smem when N fits
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + COLSUM_SMEM_COLS * 4 + 1024;  // +1024 alignment slack
 constexpr uint32_t TMEM_COLS = 512;  // two 256-column fp32 accumulators
 
 enum Sched : int { SCHED_DENSE = 0, SCHED_GROUPED = 1, SCHED_SPLITK = 2 };
@@ -62,6 +63,7 @@ struct Params {
   const int* b_k_index;     // optional gather of B along the reduction index (MN-major B only); -1 -> zero
   // pre-split weights (see pack_b): tile-ordered bf16 hi/lo images brought in with one cp.async.bulk per k-block
   const uint16_t* b_packed; long long b_packed_group_stride;   // stride in bf16 elements
+  const uint16_t* a_packed;   // pre-split activation image (pack_a); with b_packed the whole main loop is bulk copies
   int M, N, K, BN;
   // schedule
   int sched;
@@ -79,6 +81,7 @@ struct Params {
   const float* col_scale; const float* row_scale;
   const float* resid; long long ld_resid;
   float* colsum; long long colsum_group_stride;
+  int debug;   // perf experiments only: bit0 skip A loads+stores, bit1 skip the packed-B bulk copy, bit2 skip MMAs
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -95,6 +98,10 @@ __host__ __device__ inline uint32_t mnmajor_sw128_offset(uint32_t k, uint32_t mn
 constexpr uint32_t MN_LBO_BYTES = 4096;  // stride between 64-element mn groups
 constexpr uint32_t MN_SBO_BYTES = 1024;  // stride between 8-row k groups
 constexpr uint32_t K_SBO_BYTES = 512;    // stride between 8-row groups (K-major SW64)
+// bytes of one bf16 plane of a [width x 32] k-block tile in the two canonical layouts
+__host__ __device__ inline uint32_t plane_bytes(int width, bool mn_major) {
+  return mn_major ? (uint32_t)((width + 63) / 64) * 4096u : (uint32_t)width * 64u;
+}
 
 __host__ __device__ inline uint64_t make_smem_desc(uint32_t smem_addr, bool mn_major) {
   uint64_t d = 0;
@@ -247,7 +254,7 @@ __device__ __forceinline__ void split4(const float4& x, uint32_t& h01, uint32_t&
 // 2 k-rows x 128 mn (MN-major); unit u of a k-block belongs to producer warp u % 7.  All per-tile
 // address arithmetic is hoisted: a thread keeps one 32-bit element offset per (unit, half) and
 // advances it by a constant per k-block.
-template <bool A_MN, bool B_MN, bool B_PACKED>
+template <bool A_MN, bool B_MN, bool B_PACKED, bool A_PACKED>
 __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -261,7 +268,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), NUM_PROD_WARPS + (B_PACKED ? 1 : 0)); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), A_PACKED ? 1 : NUM_PROD_WARPS + (B_PACKED ? 1 : 0)); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -286,9 +293,31 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     const int nchunks = p.BN / 32;
     const uint32_t stage_base = bar_base + BAR_BYTES + (uint32_t)warp * EPI_STAGE_BYTES;
     const int rl = lane >> 3, c4 = (lane & 7) * 4;      // this lane's row-in-group-of-4 and first column of 4
+    // EPI_COLSUM: column sums are accumulated per CTA in shared memory across all its tiles of one group and
+    // flushed with one global atomic per column (instead of one per column per tile).
+    const uint32_t cs_base = bar_base + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+    const bool cs_smem = (p.epi & EPI_COLSUM) && p.N <= COLSUM_SMEM_COLS;
+    int cs_group = -1;
+    auto epi_bar = []() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    auto cs_flush = [&](int group) {
+      epi_bar();
+      if (group >= 0) {
+        float* cd = p.colsum + (long long)group * p.colsum_group_stride;
+        for (int n = threadIdx.x; n < p.N; n += NUM_EPI_WARPS * 32) {
+          float sv;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(cs_base + 4u * n) : "memory");
+          if (sv != 0.f) atomicAdd(cd + n, sv);
+        }
+      }
+      for (int n = threadIdx.x; n < p.N; n += NUM_EPI_WARPS * 32)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cs_base + 4u * n), "f"(0.f) : "memory");
+      epi_bar();
+    };
+    if (cs_smem) cs_flush(-1);
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const Tile tl = decode_tile(p, t);
       if (tl.nkb() == 0) continue;
+      if (cs_smem && tl.group != cs_group) { if (cs_group >= 0) cs_flush(cs_group); cs_group = tl.group; }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row0 = tl.m0 + warp * 32;
@@ -352,13 +381,22 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
           cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
           if (lane < 8) {
-            float* cd = p.colsum + (long long)tl.group * p.colsum_group_stride + n;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cd), "f"(cs.x), "f"(cs.y), "f"(cs.z), "f"(cs.w) : "memory");
+            if (cs_smem) {
+              const uint32_t sa = cs_base + 4u * (uint32_t)n;
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa), "f"(cs.x) : "memory");
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 4u), "f"(cs.y) : "memory");
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 8u), "f"(cs.z) : "memory");
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa + 12u), "f"(cs.w) : "memory");
+            } else {
+              float* cd = p.colsum + (long long)tl.group * p.colsum_group_stride + n;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cd), "f"(cs.x), "f"(cs.y), "f"(cs.z), "f"(cs.w) : "memory");
+            }
           }
         }
       }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
+    if (cs_smem && cs_group >= 0) cs_flush(cs_group);
   } else if (warp == MMA_WARP) {
     // ============================== MMA ISSUER ============================================
     if (lane == 0) {
@@ -381,12 +419,14 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           for (int j = 0; j < BK / 16; ++j) {
             const uint64_t ahi = make_smem_desc(sb + OFF_A_HI + j * a_kstep, A_MN);
             const uint64_t alo = make_smem_desc(sb + OFF_A_LO + j * a_kstep, A_MN);
-            const uint32_t b_lo_off = B_PACKED ? OFF_B_HI + (uint32_t)p.BN * 64u : OFF_B_LO;   // packed: lo follows hi
+            const uint32_t b_lo_off = B_PACKED ? OFF_B_HI + plane_bytes(p.BN, B_MN) : OFF_B_LO;   // packed: lo follows hi
             const uint64_t bhi = make_smem_desc(sb + OFF_B_HI + j * b_kstep, B_MN);
             const uint64_t blo = make_smem_desc(sb + b_lo_off + j * b_kstep, B_MN);
-            tc_mma(tmem_d, alo, bhi, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-            tc_mma(tmem_d, ahi, blo, idesc, 1u);
-            tc_mma(tmem_d, ahi, bhi, idesc, 1u);
+            if (!(p.debug & 4)) {
+              tc_mma(tmem_d, alo, bhi, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+              tc_mma(tmem_d, ahi, blo, idesc, 1u);
+              tc_mma(tmem_d, ahi, bhi, idesc, 1u);
+            }
           }
           tc_commit(empty_bar(stage));
           if (kb == nkb - 1) tc_commit(tfull_bar(acc));
@@ -397,28 +437,58 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     }
   } else {
     // ============================== PRODUCERS =============================================
+    if (A_PACKED) {
+      // Both operands are pre-split tile images: one thread streams them in with two cp.async.bulk per k-block.
+      if (warp == FIRST_PROD_WARP && lane == 0) {
+        const uint32_t a_bytes = 2u * plane_bytes(BM, A_MN), b_bytes = 2u * plane_bytes(p.BN, B_MN);
+        const long long kblocks = (p.K + BK - 1) / BK;
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+          const Tile tl = decode_tile(p, t);
+          const int nkb = tl.nkb();
+          if (nkb == 0) continue;
+          const long long kb0 = tl.k_begin / BK;
+          const uint8_t* srcA = reinterpret_cast<const uint8_t*>(p.a_packed) + ((long long)(tl.m0 / BM) * kblocks + kb0) * a_bytes;
+          const uint8_t* srcB = reinterpret_cast<const uint8_t*>(p.b_packed + (long long)tl.group * p.b_packed_group_stride) +
+                                ((long long)(tl.n0 / p.BN) * kblocks + kb0) * b_bytes;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sb = smem_base + stage * STAGE_BYTES;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)), "r"(a_bytes + b_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sb + OFF_A_HI), "l"(srcA + (long long)kb * a_bytes), "r"(a_bytes), "r"(full_bar(stage)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sb + OFF_B_HI), "l"(srcB + (long long)kb * b_bytes), "r"(b_bytes), "r"(full_bar(stage)) : "memory");
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else {
+    // A k-block of an operand is cut into "units" a warp handles with two LDG.128 + two STS.128 per lane:
+    //   K-major : 8 rows x 32 k  -- lane = (row l>>2, 16-byte chunk l&3 = 8 consecutive k)
+    //   MN-major: 2 k-rows x 128 mn -- lane = (k-row l>>4, chunk l&15 = 8 consecutive mn)
+    // Every lane owns a whole 8-element chunk, so hi/lo go out as one 16-byte store each with no shuffles;
+    // a quarter-warp writes 128 contiguous (swizzled) bytes -> bank-conflict free.
     const int wq = warp - FIRST_PROD_WARP;
-    const int sub = lane >> 3, f4 = lane & 7;
-    const bool odd = lane & 1;
     constexpr int units_a = 16;
     const int segs_b = (p.BN + 127) / 128;
     const int units_b = B_PACKED ? 0 : (B_MN ? 16 * segs_b : p.BN / 8);
     const int units = units_a + units_b;
     // lane-constant parts of the shared-memory store offsets
-    const uint32_t st_k = (uint32_t)((2 * sub + (odd ? 1 : 0)) * 64 + ((((uint32_t)f4 >> 1) ^ (uint32_t)sub) << 4));
-    const uint32_t cc = (uint32_t)(lane >> 1) & 7u, g_lane = (uint32_t)lane >> 4;
+    const uint32_t st_k = (uint32_t)((lane >> 2) * 64 + ((((uint32_t)lane & 3u) ^ (((uint32_t)lane >> 3) & 3u)) << 4));
+    const uint32_t kr_lane = (uint32_t)lane >> 4, j_lane = (uint32_t)lane & 15u;
 
     // per-tile state
     constexpr int MU = B_PACKED ? 3 : MAX_UNITS;   // units per producer warp per k-block
-    uint32_t off[MU][2];            // element offsets from the operand base (A) / group base (B)
-    uint32_t vmask = 0;             // bit (2i+h): row / mn range valid
+    uint32_t off[MU];               // element offset of this lane's chunk from the operand base (A) / group base (B)
+    uint32_t vmask = 0;             // bit i: row / mn range valid
     const float* baseB = p.B;
     const uint16_t* packB = nullptr;   // packed B image of the current tile's first k-block
     int t_cur = blockIdx.x - gridDim.x, kb_cur = 0, nkb_cur = 0, k_begin = 0, k_end = 0;
     const uint32_t adv_a = A_MN ? (uint32_t)(BK * p.a_sk) : (uint32_t)BK;
     const uint32_t adv_b = B_MN ? (uint32_t)(BK * p.b_sk) : (uint32_t)BK;
-
     const bool b_gather = B_MN && (p.b_k_index != nullptr);   // B rows come through an index (expert wgrad)
+
     auto setup_tile = [&](const Tile& tl) {
       k_begin = tl.k_begin; k_end = tl.k_end;
       baseB = p.B + (long long)tl.group * p.b_group_stride;
@@ -431,39 +501,31 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 #pragma unroll
       for (int i = 0; i < MU; ++i) {
         const int u = wq + NUM_PROD_WARPS * i;
-        off[i][0] = 0; off[i][1] = 0;
+        off[i] = 0;
         if (u >= units) continue;
         const bool is_a = u < units_a;
         const int ul = is_a ? u : u - units_a;
+        const int mn0 = is_a ? tl.m0 : tl.n0;
+        const int mn_lim = is_a ? p.M : p.N;
         if (is_a ? !A_MN : !B_MN) {
-          const int mn0 = is_a ? tl.m0 : tl.n0;
-          const int mn_lim = is_a ? p.M : p.N;
           const long long s_mn = is_a ? p.a_smn : p.b_smn;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int row = mn0 + 8 * ul + 2 * sub + h;
-            if (row >= mn_lim) continue;
-            long long ridx = row;
-            if (is_a && p.a_row_index) { ridx = __ldg(p.a_row_index + row); if (ridx < 0) continue; }
-            off[i][h] = (uint32_t)(ridx * s_mn + tl.k_begin + 4 * f4);
-            vmask |= 1u << (2 * i + h);
-          }
+          const int row = mn0 + 8 * ul + (lane >> 2);
+          if (row >= mn_lim) continue;
+          long long ridx = row;
+          if (is_a && p.a_row_index) { ridx = __ldg(p.a_row_index + row); if (ridx < 0) continue; }
+          off[i] = (uint32_t)(ridx * s_mn + tl.k_begin + 8 * (lane & 3));
+          vmask |= 1u << i;
         } else {
           const int segs = is_a ? 1 : segs_b;
           const int pi = (segs == 2) ? (ul >> 1) : ul, seg = (segs == 2) ? (ul & 1) : 0;
-          const int mnl = seg * 128 + 4 * lane;
-          const int mn0 = is_a ? tl.m0 : tl.n0;
+          const int mnl = seg * 128 + 8 * (int)j_lane;
           const int tile_w = is_a ? BM : p.BN;
-          const int mn_lim = is_a ? p.M : p.N;
-          if (mnl + 4 > tile_w || mn0 + mnl + 4 > mn_lim) continue;
+          if (mnl + 8 > tile_w || mn0 + mnl + 8 > mn_lim) continue;     // tile widths / extents are multiples of 8
           const long long s_k = is_a ? p.a_sk : p.b_sk;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int koff = (pi >> 2) * 8 + (pi & 3) + 4 * h;
-            off[i][h] = (!is_a && b_gather) ? (uint32_t)(mn0 + mnl)
-                                            : (uint32_t)((long long)(tl.k_begin + koff) * s_k + mn0 + mnl);
-            vmask |= 1u << (2 * i + h);
-          }
+          const int koff = 2 * pi + (int)kr_lane;
+          off[i] = (!is_a && b_gather) ? (uint32_t)(mn0 + mnl)
+                                       : (uint32_t)((long long)(tl.k_begin + koff) * s_k + mn0 + mnl);
+          vmask |= 1u << i;
         }
       }
     };
@@ -481,7 +543,8 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     // issue the global loads of the current k-block, then step the offsets to the next one
     auto load_kb = [&](float4 (&r)[MU][2]) {
       const int k0 = k_begin + kb_cur * BK;
-      const bool kin = (k0 + 4 * f4 + 4 <= k_end);          // K-major operands: this lane's 4 k values
+      const int kl = k0 + 8 * (lane & 3);                     // K-major operands: this lane's 8 k values
+      const bool kin0 = (kl + 4 <= k_end), kin1 = (kl + 8 <= k_end);
 #pragma unroll
       for (int i = 0; i < MU; ++i) {
         r[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -490,31 +553,28 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
         if (u >= units) continue;
         const bool is_a = u < units_a;
         const float* base = is_a ? p.A : baseB;
+        const bool ok = (vmask >> i) & 1u;
         if (is_a ? !A_MN : !B_MN) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (((vmask >> (2 * i + h)) & 1u) && kin) r[i][h] = ldg_f4(base + off[i][h]);
+          if (ok && kin0) r[i][0] = ldg_f4(base + off[i]);
+          if (ok && kin1) r[i][1] = ldg_f4(base + off[i] + 4);
         } else {
           const int ul = is_a ? u : u - units_a;
           const int pi = (!is_a && segs_b == 2) ? (ul >> 1) : ul;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int k = k0 + (pi >> 2) * 8 + (pi & 3) + 4 * h;
-            if (!((vmask >> (2 * i + h)) & 1u) || k >= k_end) continue;
+          const int k = k0 + 2 * pi + (int)kr_lane;
+          if (ok && k < k_end) {
+            const float* src = base + off[i];
             if (!is_a && b_gather) {
               const int kk = __ldg(p.b_k_index + k);
-              if (kk >= 0) r[i][h] = ldg_f4(base + (long long)kk * p.b_sk + off[i][h]);
-            } else {
-              r[i][h] = ldg_f4(base + off[i][h]);
+              src = (kk >= 0) ? base + (long long)kk * p.b_sk + off[i] : nullptr;
             }
+            if (src) { r[i][0] = ldg_f4(src); r[i][1] = ldg_f4(src + 4); }
           }
         }
-        const uint32_t adv = is_a ? adv_a : ((!is_a && b_gather) ? 0u : adv_b);
-        off[i][0] += adv; off[i][1] += adv;
+        off[i] += is_a ? adv_a : ((!is_a && b_gather) ? 0u : adv_b);
       }
     };
 
-    // split + pair exchange + store one k-block into its smem stage
+    // split + store one k-block into its smem stage
     auto store_kb = [&](const float4 (&r)[MU][2], uint32_t sb) {
 #pragma unroll
       for (int i = 0; i < MU; ++i) {
@@ -522,19 +582,9 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
         if (u >= units) continue;
         const bool is_a = u < units_a;
         const int ul = is_a ? u : u - units_a;
-        uint32_t hA0, hA1, lA0, lA1, hB0, hB1, lB0, lB1;
-        split4(r[i][0], hA0, hA1, lA0, lA1);
-        split4(r[i][1], hB0, hB1, lB0, lB1);
-        // even lane keeps half 0 (needs the odd lane's half-0 part); odd lane keeps half 1
-        const uint32_t s0 = odd ? hA0 : hB0, s1 = odd ? hA1 : hB1;
-        const uint32_t s2 = odd ? lA0 : lB0, s3 = odd ? lA1 : lB1;
-        const uint32_t q0 = __shfl_xor_sync(0xffffffffu, s0, 1);
-        const uint32_t q1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-        const uint32_t q2 = __shfl_xor_sync(0xffffffffu, s2, 1);
-        const uint32_t q3 = __shfl_xor_sync(0xffffffffu, s3, 1);
         uint4 hi, lo;
-        if (!odd) { hi = make_uint4(hA0, hA1, q0, q1); lo = make_uint4(lA0, lA1, q2, q3); }
-        else      { hi = make_uint4(q0, q1, hB0, hB1); lo = make_uint4(q2, q3, lB0, lB1); }
+        split4(r[i][0], hi.x, hi.y, lo.x, lo.y);
+        split4(r[i][1], hi.z, hi.w, lo.z, lo.w);
         uint32_t o;
         if (is_a ? !A_MN : !B_MN) {
           o = (uint32_t)ul * 512u + st_k;
@@ -542,8 +592,9 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           const int segs = is_a ? 1 : segs_b;
           const uint32_t pi = (segs == 2) ? (uint32_t)(ul >> 1) : (uint32_t)ul;
           const uint32_t seg = (segs == 2) ? (uint32_t)(ul & 1) : 0u;
-          const uint32_t k7 = (pi & 3u) + (odd ? 4u : 0u);
-          o = (seg * 2u + g_lane) * 4096u + (pi >> 2) * 1024u + k7 * 128u + ((cc ^ k7) << 4);
+          const uint32_t k = 2u * pi + kr_lane;             // k-row inside the k-block
+          const uint32_t mc = seg * 16u + j_lane;           // 8-element mn chunk inside the tile
+          o = ((mc >> 3) * 4u + (k >> 3)) * 1024u + (k & 7u) * 128u + (((mc & 7u) ^ (k & 7u)) << 4);
         }
         const uint32_t dst_hi = sb + (is_a ? OFF_A_HI : OFF_B_HI) + o;
         const uint32_t dst_lo = sb + (is_a ? OFF_A_LO : OFF_B_LO) + o;
@@ -558,7 +609,9 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     const uint16_t* pub_src = nullptr; int pub_kb = 0;   // packed-B source of the k-block the next publish() stores
     auto publish = [&](const float4 (&r)[MU][2]) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
-      if (B_PACKED && wq == 0 && lane == 0) {
+      if (B_PACKED && wq == 0 && lane == 0 && (p.debug & 2)) {
+        mbar_arrive(full_bar(stage));
+      } else if (B_PACKED && wq == 0 && lane == 0) {
         // one thread: arm the stage barrier with the byte count and start the bulk copy of B's hi|lo image
         const uint32_t bytes = (uint32_t)p.BN * 128u;
         const uint16_t* src = pub_src + (long long)pub_kb * (2LL * p.BN * BK);
@@ -566,29 +619,47 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_base + stage * STAGE_BYTES + OFF_B_HI), "l"(src), "r"(bytes), "r"(full_bar(stage)) : "memory");
       }
-      store_kb(r, smem_base + stage * STAGE_BYTES);
+      if (p.debug & 8) {            // loads only: consume the registers without the split / stores
+#pragma unroll
+        for (int i = 0; i < MU; ++i) asm volatile("" ::"f"(r[i][0].x), "f"(r[i][1].w));
+      } else if (!(p.debug & 1)) store_kb(r, smem_base + stage * STAGE_BYTES);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     };
 
-    float4 r0[MU][2], r1[MU][2];
-    // publish() runs one k-block behind load_kb(): remember which packed image each register set belongs to
-    const uint16_t* src0 = nullptr; const uint16_t* src1 = nullptr; int kb0 = 0, kb1 = 0;
-    if (advance()) {
-      src0 = packB; kb0 = kb_cur; load_kb(r0);
-      while (true) {
-        const bool more1 = advance();
-        if (more1) { src1 = packB; kb1 = kb_cur; load_kb(r1); }
-        pub_src = src0; pub_kb = kb0; publish(r0);
-        if (!more1) break;
-        const bool more2 = advance();
-        if (more2) { src0 = packB; kb0 = kb_cur; load_kb(r0); }
-        pub_src = src1; pub_kb = kb1; publish(r1);
-        if (!more2) break;
+    // PF k-blocks of global loads are kept in flight per thread (register ring, statically indexed): one
+    // k-block (16 KB of A per SM) in flight is latency-bound at ~14 GB/s/SM -- measured 3x slower than the MMAs.
+    constexpr int PF = B_PACKED ? 4 : 2;
+    float4 r[PF][MU][2];
+    if (p.debug & 16) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d)
+#pragma unroll
+        for (int i = 0; i < MU; ++i) { r[d][i][0] = make_float4(1.f, 2.f, 3.f, 4.f); r[d][i][1] = r[d][i][0]; }
+    }
+    const uint16_t* q_src[PF]; int q_kb[PF]; bool q_ok[PF];
+    const bool dbg_noload = p.debug & (1 | 16);   // bit4: stores of zeros without loads
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+      q_ok[d] = advance();
+      q_src[d] = packB; q_kb[d] = kb_cur;
+      if (q_ok[d] && !dbg_noload) load_kb(r[d]);
+    }
+    bool done = !q_ok[0];
+    while (!done) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        if (!q_ok[d]) { done = true; break; }
+        pub_src = q_src[d]; pub_kb = q_kb[d];
+        publish(r[d]);
+        q_ok[d] = advance();
+        q_src[d] = packB; q_kb[d] = kb_cur;
+        if (q_ok[d] && !dbg_noload) load_kb(r[d]);
       }
     }
+    }  // !A_PACKED
   }
 
   tc_fence_before();
@@ -607,6 +678,12 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 long long packed_elems(int N, int K);
 int pack_b(const float* B, long long s_mn, long long s_k, long long group_stride, int groups, int N, int K,
            uint16_t* out, cudaStream_t stream);
+// Pre-split an ACTIVATION operand.  mn_major = 0: X[rows, K] row-major (optional row gather, -1 = zero row) ->
+// K-major tiles of `tile` rows (128 for the A operand).  mn_major = 1: X[R, W] row-major where the ROW index is the
+// reduction index (wgrad operands; optional row gather) -> MN-major tiles of `tile` columns (128 for A, BN for B).
+long long packed_act_elems(long long rows, int cols, int mn_major, int tile);
+int pack_act(const float* X, long long ld, const int* row_index, long long rows, int cols, int mn_major, int tile,
+             uint16_t* out, cudaStream_t stream);
 // Host-side launcher (gemm_tc.cu): validates shapes, fills derived fields, launches on `stream`.
 int launch(Params p, cudaStream_t stream);
 // Picks the largest supported tile width that divides N (multiple of 32, <= 256); 0 if none.

@@ -36,6 +36,13 @@ def _pi(t):
     return _p(t, torch.int32)
 
 
+def _pick_bn(n: int) -> int:
+    for bn in (256, 224, 192, 160, 128, 96, 64, 32):
+        if n % bn == 0:
+            return bn
+    raise ValueError(f'N={n} has no GEMM tile width (multiple of 32)')
+
+
 def num_sms() -> int:
     return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 
@@ -44,11 +51,12 @@ def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a
          sched=SCHED_DENSE, k_splits=1, num_groups=1, tile_group=None, num_m_tiles=None, seg_begin=None,
          seg_end=None, d_group_stride=0, bias=None, bias_group_stride=0, epilogue=0, aux_out=None, aux_in=None,
          ld_aux=0, col_scale=None, row_scale=None, resid=None, ld_resid=0, tile_n=0, b_packed=None,
-         b_packed_group_stride=0, colsum=None, colsum_group_stride=0):
+         b_packed_group_stride=0, colsum=None, colsum_group_stride=0, a_packed=None):
     lib = _lib.load()
     a = _lib.GemmArgs()
     a.A = _p(A); a.a_stride_mn = a_smn; a.a_stride_k = a_sk
     a.b_packed = None if b_packed is None else _p(b_packed, torch.int16); a.b_packed_group_stride = b_packed_group_stride
+    a.a_packed = None if a_packed is None else _p(a_packed, torch.int16)
     a.B = _p(B); a.b_stride_mn = b_smn; a.b_stride_k = b_sk; a.b_group_stride = b_group_stride
     a.a_row_index = _pi(a_row_index); a.b_k_index = _pi(b_k_index)
     a.M, a.N, a.K = M, N, K
@@ -86,6 +94,29 @@ def pack_weight(w, *, transposed: bool, groups: int = 1, out=None):
     return out, per
 
 
+def pack_act(x, *, rows, cols, mn_major, tile=128, row_index=None, ld=None):
+    """Pre-split an activation operand (sm3_gemm_pack_act).  mn_major=False: x[rows, cols=K] -> K-major A tiles
+    (row_index = MoE dispatch gather).  mn_major=True: x[rows = reduction index, cols] -> MN-major tiles of `tile` cols."""
+    lib = _lib.load()
+    n = lib.sm3_gemm_packed_act_elems(rows, cols, 1 if mn_major else 0, tile)
+    out = torch.empty((n,), device=x.device, dtype=torch.int16)
+    _lib.check(lib.sm3_gemm_pack_act(_p(x), cols if ld is None else ld, _pi(row_index), rows, cols, 1 if mn_major else 0, tile,
+                                     out.data_ptr(), _stream()), 'sm3_gemm_pack_act')
+    return out
+
+
+# When is an extra pack pass (8 B/element of HBM traffic) cheaper than splitting the operand inside the GEMM?  The
+# in-kernel split is repeated for every tile column that re-reads the operand and is latency/issue bound
+# (profiles/r01_gemm_isolation.txt); the packed main loop runs at the tensor-pipe rate.  Thresholds from measurements.
+import os as _os
+PACK_A_MIN_K = int(_os.environ.get('SM3_PACK_A_MIN_K', '192'))
+PACK_W_MIN_TILES = int(_os.environ.get('SM3_PACK_W_MIN_TILES', '2'))
+
+
+def _pack_a_pays(N, K):
+    return K >= PACK_A_MIN_K and (N // _pick_bn(N)) >= 2 or K >= 4 * PACK_A_MIN_K
+
+
 def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale=None, row_scale=None, resid=None,
                row_index=None, rows=None, grouped=None, w_group_stride=0, bias_group_stride=0, packed=None):
     """out[M,N] = epi(x[M,K] @ w[N,K]^T).  grouped = (tile_group, num_m_tiles) for expert segments."""
@@ -100,6 +131,9 @@ def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale
         kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
     if packed is not None:
         kw.update(b_packed=packed[0], b_packed_group_stride=packed[1])
+        if _pack_a_pays(N, K):
+            kw.update(a_packed=pack_act(x, rows=M, cols=K, mn_major=False, row_index=row_index))
+            row_index = None
     gemm(A=x, a_smn=K, a_sk=1, B=w, b_smn=K, b_sk=1, b_group_stride=w_group_stride, M=M, N=N, K=K, D=out, ldd=N,
          a_row_index=row_index, bias=bias, bias_group_stride=bias_group_stride, epilogue=epi, aux_out=aux_out,
          ld_aux=N, col_scale=col_scale, row_scale=row_scale, resid=resid, ld_resid=N, **kw)
@@ -118,6 +152,8 @@ def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, re
         kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
     if packed is not None:
         kw.update(b_packed=packed[0], b_packed_group_stride=packed[1])
+        if _pack_a_pays(K, N):
+            kw.update(a_packed=pack_act(dy, rows=M, cols=N, mn_major=False))
     gemm(A=dy, a_smn=N, a_sk=1, B=w, b_smn=1, b_sk=K, b_group_stride=w_group_stride, M=M, N=K, K=N, D=out, ldd=K,
          epilogue=epilogue | (EPI_COLSUM if colsum is not None else 0), aux_in=aux_in, ld_aux=K, row_scale=row_scale,
          resid=resid, ld_resid=K, colsum=colsum, colsum_group_stride=colsum_group_stride, **kw)
@@ -133,13 +169,19 @@ def linear_wgrad(dy, x, dw, *, rows=None, x_row_index=None, row_scale=None, segs
     R = rows if rows is not None else dy.shape[0]
     N = dy.shape[1]
     K = x.shape[1]
-    tiles = ((N + 127) // 128) * max(1, K // 256 if K % 256 == 0 else 1) * num_groups
-    splits = max(1, min(64, (2 * num_sms()) // max(1, tiles)))
-    if R < 4096:
-        splits = max(1, min(splits, R // 512 + 1))
+    tiles = ((N + 127) // 128) * (K // _pick_bn(K)) * num_groups
+    # ~3 work items per SM (the per-expert segments are unequal), but at least 1024 reduction rows per split
+    splits = -(-3 * num_sms() // max(1, tiles))
+    splits = max(1, min(64, splits, max(1, (R // num_groups) // 1024)))
     epi = EPI_ATOMIC | (EPI_ROWSCALE if row_scale is not None else 0)
+    kw = {}
+    if ((N + 127) // 128) * (K // _pick_bn(K)) >= PACK_W_MIN_TILES:
+        # both operands are re-read by several output tiles: split them once (MN-major images), gather included
+        kw = dict(a_packed=pack_act(dy, rows=R, cols=N, mn_major=True, tile=128),
+                  b_packed=pack_act(x, rows=R, cols=K, mn_major=True, tile=_pick_bn(K), row_index=x_row_index))
+        x_row_index = None
     gemm(A=dy, a_smn=1, a_sk=N, B=x, b_smn=1, b_sk=K, M=N, N=K, K=R, D=dw, ldd=K, d_group_stride=N * K,
-         b_k_index=x_row_index, sched=SCHED_SPLITK, k_splits=splits, num_groups=num_groups,
+         b_k_index=x_row_index, **kw, sched=SCHED_SPLITK, k_splits=splits, num_groups=num_groups,
          seg_begin=None if segs is None else segs[0], seg_end=None if segs is None else segs[1],
          epilogue=epi, row_scale=row_scale)
     return dw

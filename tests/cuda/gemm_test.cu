@@ -23,12 +23,13 @@ static double gelu(double x) { return 0.5 * x * (1.0 + erf(x / sqrt(2.0))); }
 static double dgelu(double x) { return 0.5 * (1.0 + erf(x / sqrt(2.0))) + x * exp(-0.5 * x * x) / sqrt(2.0 * M_PI); }
 
 static int g_fail = 0;
+static int g_debug = 0;
 
 struct Case {
   std::string name;
   int M, N, K, BN = 0;
   bool a_mn = false, b_mn = false;
-  bool gather = false, ints = false, kgather = false, packed = false;
+  bool gather = false, ints = false, kgather = false, packed = false, apacked = false;
   int sched = SCHED_DENSE, groups = 1, k_splits = 1;
   int epi = 0;
 };
@@ -119,6 +120,22 @@ static void run(const Case& c) {
     if (prc != 0) { printf("CASE %-28s PACK FAILED (%s)\n", c.name.c_str(), last_error()); g_fail++; return; }
     p.b_packed = dpack; p.b_packed_group_stride = per;
   }
+  uint16_t* dpa = nullptr; uint16_t* dpb2 = nullptr;
+  if (c.apacked) {
+    // A: activation pack (K-major with optional row gather, or MN-major for the wgrad form)
+    const long long ea = c.a_mn ? packed_act_elems(K, M, 1, 128) : packed_act_elems(M, K, 0, 128);
+    CK(cudaMalloc(&dpa, (size_t)ea * 2));
+    int prc = c.a_mn ? pack_act(dA, M, nullptr, K, M, 1, 128, dpa, 0) : pack_act(dA, K, dridx, M, K, 0, 128, dpa, 0);
+    if (prc != 0) { printf("CASE %-28s PACK_A FAILED (%s)\n", c.name.c_str(), last_error()); g_fail++; return; }
+    p.a_packed = dpa; p.a_row_index = nullptr;
+    if (c.a_mn) {   // wgrad: B is an activation too, MN-major tiles of the GEMM tile width, optional k gather
+      const int bn = pick_bn(N);
+      CK(cudaMalloc(&dpb2, (size_t)packed_act_elems(K, N, 1, bn) * 2));
+      prc = pack_act(dB, N, dkidx, K, N, 1, bn, dpb2, 0);
+      if (prc != 0) { printf("CASE %-28s PACK_B FAILED (%s)\n", c.name.c_str(), last_error()); g_fail++; return; }
+      p.b_packed = dpb2; p.b_packed_group_stride = 0; p.b_k_index = nullptr;
+    }
+  }
   int rc = launch(p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (rc != 0 || e != cudaSuccess) {
@@ -186,7 +203,7 @@ static void run(const Case& c) {
   if (dridx) cudaFree(dridx); if (dtg) cudaFree(dtg); cudaFree(dnmt); if (dsb) cudaFree(dsb); if (dse) cudaFree(dse);
 }
 
-static void bench(const char* name, int M, int N, int K, bool a_mn, bool b_mn, int epi, int sched = SCHED_DENSE, int splits = 1, bool packed = false) {
+static void bench(const char* name, int M, int N, int K, bool a_mn, bool b_mn, int epi, int sched = SCHED_DENSE, int splits = 1, bool packed = false, bool apacked = false) {
   float *A, *B, *D, *bias, *aux;
   CK(cudaMalloc(&A, (size_t)M * K * 4)); CK(cudaMalloc(&B, (size_t)N * K * 4)); CK(cudaMalloc(&D, (size_t)M * N * 4));
   CK(cudaMalloc(&bias, (size_t)N * 4)); CK(cudaMalloc(&aux, (size_t)M * N * 4));
@@ -195,9 +212,27 @@ static void bench(const char* name, int M, int N, int K, bool a_mn, bool b_mn, i
   p.A = A; p.B = B; p.D = D; p.ldd = N; p.M = M; p.N = N; p.K = K; p.bias = bias; p.epi = epi; p.aux_out = (epi & EPI_GELU) ? aux : nullptr; p.ld_aux = N;
   if (!a_mn) { p.a_smn = K; p.a_sk = 1; } else { p.a_smn = 1; p.a_sk = M; }
   if (!b_mn) { p.b_smn = K; p.b_sk = 1; } else { p.b_smn = 1; p.b_sk = N; }
-  p.sched = sched; p.k_splits = splits; p.num_groups = 1;
+  p.sched = sched; p.k_splits = splits; p.num_groups = 1; p.debug = g_debug;
   uint16_t* dpack = nullptr;
   if (packed) { CK(cudaMalloc(&dpack, (size_t)packed_elems(N, K) * 2)); pack_b(B, b_mn ? 1 : K, b_mn ? N : 1, 0, 1, N, K, dpack, 0); p.b_packed = dpack; }
+  uint16_t* dpa = nullptr; uint16_t* dpb2 = nullptr;
+  if (apacked) {
+    if (a_mn) {
+      const int bn = pick_bn(N);
+      CK(cudaMalloc(&dpa, (size_t)packed_act_elems(K, M, 1, 128) * 2)); pack_act(A, M, nullptr, K, M, 1, 128, dpa, 0);
+      CK(cudaMalloc(&dpb2, (size_t)packed_act_elems(K, N, 1, bn) * 2)); pack_act(B, N, nullptr, K, N, 1, bn, dpb2, 0);
+      p.b_packed = dpb2;
+    } else {
+      CK(cudaMalloc(&dpa, (size_t)packed_act_elems(M, K, 0, 128) * 2)); pack_act(A, K, nullptr, M, K, 0, 128, dpa, 0);
+    }
+    p.a_packed = dpa;
+    cudaEvent_t q0, q1; cudaEventCreate(&q0); cudaEventCreate(&q1);
+    cudaEventRecord(q0);
+    for (int i = 0; i < 5; ++i) { if (a_mn) pack_act(A, M, nullptr, K, M, 1, 128, dpa, 0); else pack_act(A, K, nullptr, M, K, 0, 128, dpa, 0); }
+    cudaEventRecord(q1); cudaEventSynchronize(q1);
+    float pms; cudaEventElapsedTime(&pms, q0, q1);
+    printf("      pack A: %.3f ms per call (%.0f GB/s)\n", pms / 5, 8.0 * M * K / (pms / 5) * 1e-6);
+  }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) launch(p, 0);
   cudaEventRecord(e0);
@@ -215,6 +250,8 @@ int main(int argc, char** argv) {
   const bool quick = argc > 1 && std::string(argv[1]) == "quick";
   const bool only_bench = argc > 1 && std::string(argv[1]) == "bench";
   const int bench_idx = argc > 2 ? atoi(argv[2]) : -1;
+  g_debug = argc > 3 ? atoi(argv[3]) : 0;
+  if (g_debug) printf("DEBUG FLAGS %d (results invalid)\n", g_debug);
   std::vector<Case> cases;
   auto add = [&](Case c) { cases.push_back(c); };
   { Case c; c.name = "nt_int_128x32x32";   c.M = 128; c.N = 32;  c.K = 32;  c.ints = true; add(c); }
@@ -237,6 +274,14 @@ int main(int argc, char** argv) {
   { Case c; c.name = "tn_f32_wgrad_kgather"; c.M = 384; c.N = 96; c.K = 3000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 5; c.groups = 3; c.epi = EPI_ATOMIC; c.kgather = true; add(c); }
   { Case c; c.name = "nn_dgelu_colsum";   c.M = 450; c.N = 384; c.K = 96;  c.b_mn = true; c.epi = EPI_DGELU | EPI_COLSUM; add(c); }
   { Case c; c.name = "grouped_nn_packed_colsum"; c.M = 640; c.N = 96; c.K = 384; c.sched = SCHED_GROUPED; c.groups = 4; c.b_mn = true; c.packed = true; c.epi = EPI_COLSUM; add(c); }
+  { Case c; c.name = "nt_ALLpacked";       c.M = 1000; c.N = 384; c.K = 96;  c.packed = true; c.apacked = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
+  { Case c; c.name = "nt_ALLpacked_ktail"; c.M = 333; c.N = 96;  c.K = 48;  c.packed = true; c.apacked = true; add(c); }
+  { Case c; c.name = "nt_ALLpacked_bigK";  c.M = 256; c.N = 768; c.K = 3072; c.packed = true; c.apacked = true; add(c); }
+  { Case c; c.name = "nn_ALLpacked dgrad"; c.M = 450; c.N = 384; c.K = 96;  c.b_mn = true; c.packed = true; c.apacked = true; c.epi = EPI_DGELU | EPI_COLSUM; add(c); }
+  { Case c; c.name = "grouped_ALLpacked_gather"; c.M = 1024; c.N = 384; c.K = 96; c.sched = SCHED_GROUPED; c.groups = 3; c.gather = true; c.packed = true; c.apacked = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
+  { Case c; c.name = "tn_ALLpacked_splitk"; c.M = 384; c.N = 96; c.K = 4992; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 7; c.epi = EPI_ATOMIC; c.apacked = true; add(c); }
+  { Case c; c.name = "tn_ALLpacked_ragged"; c.M = 96; c.N = 384; c.K = 1000; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 3; c.epi = EPI_ATOMIC; c.apacked = true; add(c); }
+  { Case c; c.name = "tn_ALLpacked_kgather"; c.M = 384; c.N = 192; c.K = 3008; c.a_mn = true; c.b_mn = true; c.sched = SCHED_SPLITK; c.k_splits = 5; c.epi = EPI_ATOMIC; c.kgather = true; c.apacked = true; add(c); }
   { Case c; c.name = "nt_packed";         c.M = 1000; c.N = 384; c.K = 96;  c.packed = true; c.epi = EPI_BIAS | EPI_GELU; add(c); }
   { Case c; c.name = "nt_packed_ktail48"; c.M = 333; c.N = 96;  c.K = 48;  c.packed = true; add(c); }
   { Case c; c.name = "nt_packed_bigK";    c.M = 256; c.N = 768; c.K = 3072; c.packed = true; add(c); }
@@ -250,6 +295,14 @@ int main(int argc, char** argv) {
   if (!quick) {
     int bi = 0;
 #define B_(...) do { if (bench_idx < 0 || bench_idx == bi) bench(__VA_ARGS__); ++bi; } while (0)
+    B_("ffn1 stage2 ALLPACKED", 32768, 1536, 384, false, false, EPI_BIAS | EPI_GELU, SCHED_DENSE, 1, true, true);
+    B_("ffn2 stage2 ALLPACKED", 32768, 384, 1536, false, false, EPI_BIAS, SCHED_DENSE, 1, true, true);
+    B_("ffn1 stage0 ALLPACKED", 524288, 384, 96, false, false, EPI_BIAS | EPI_GELU, SCHED_DENSE, 1, true, true);
+    B_("ffn2 stage0 ALLPACKED", 524288, 96, 384, false, false, EPI_BIAS, SCHED_DENSE, 1, true, true);
+    B_("ffn1 stage3 ALLPACKED", 8192, 3072, 768, false, false, EPI_BIAS, SCHED_DENSE, 1, true, true);
+    B_("wgrad stage2 ALLPACKED", 1536, 384, 32768, true, true, EPI_ATOMIC, SCHED_SPLITK, 16, false, true);
+    B_("wgrad stage0 ALLPACKED", 384, 96, 524288, true, true, EPI_ATOMIC, SCHED_SPLITK, 64, false, true);
+    B_("square 8192 ALLPACKED", 8192, 8192, 8192, false, false, 0, SCHED_DENSE, 1, true, true);
     B_("ffn1 stage2 PACKED", 32768, 1536, 384, false, false, EPI_BIAS | EPI_GELU, SCHED_DENSE, 1, true);
     B_("ffn2 stage2 PACKED", 32768, 384, 1536, false, false, EPI_BIAS, SCHED_DENSE, 1, true);
     B_("ffn1 stage0 PACKED", 524288, 384, 96, false, false, EPI_BIAS | EPI_GELU, SCHED_DENSE, 1, true);
