@@ -49,6 +49,33 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Branch-free GELU / GELU' for the GEMM epilogues (the exact-erf pair above costs ~2x the instructions and the
+// GELU-heavy epilogues are issue bound).  Phi(x) via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 absolute on erf,
+// i.e. <= 1e-7 on Phi -- below the 1e-5 relative error of the split-bf16 products feeding it); exp(-x^2/2) is shared
+// between Phi and the density term of the derivative.
+__device__ __forceinline__ void phi_parts(float x, float& Phi, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  e = __expf(-z * z);                       // = exp(-x^2/2)
+  const float q = 0.5f * poly * e;          // upper-tail probability of |x|
+  Phi = x >= 0.f ? 1.0f - q : q;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float Phi, e;
+  phi_parts(x, Phi, e);
+  return x * Phi;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float Phi, e;
+  phi_parts(x, Phi, e);
+  return fmaf(x * 0.39894228040143267794f, e, Phi);
+}
+
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }

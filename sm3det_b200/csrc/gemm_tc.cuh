@@ -35,10 +35,12 @@ constexpr uint32_t OFF_B_HI = 16384;
 constexpr uint32_t OFF_B_LO = 32768;
 constexpr uint32_t STAGE_BYTES = 49152;
 constexpr uint32_t BAR_BYTES = 128;
-constexpr uint32_t EPI_STAGE_ROW_FLOATS = 36;                       // 32 columns + 4 pad: conflict-free 16-byte accesses
+constexpr int EPI_CW = 16;                                          // accumulator columns per epilogue pass
+constexpr uint32_t EPI_STAGE_ROW_FLOATS = EPI_CW + 4;               // + 4 pad: conflict-free 16-byte accesses
 constexpr uint32_t EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW_FLOATS * 4;  // per epilogue warp
+constexpr int MAX_EPI_WARPS = 8;                                    // fully packed kernels: the idle producer warps 8-11 join
 constexpr int COLSUM_SMEM_COLS = 3072;                              // EPI_COLSUM accumulates per CTA in smem when N fits
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + COLSUM_SMEM_COLS * 4 + 1024;  // +1024 alignment slack
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + MAX_EPI_WARPS * EPI_STAGE_BYTES + COLSUM_SMEM_COLS * 4 + 1024;  // +1024 alignment slack
 constexpr uint32_t TMEM_COLS = 512;  // two 256-column fp32 accumulators
 
 enum Sched : int { SCHED_DENSE = 0, SCHED_GROUPED = 1, SCHED_SPLITK = 2 };
@@ -196,6 +198,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---------------------------------------------------------------------------------------------
 struct Tile {
   int m0, n0, group, k_begin, k_end;
@@ -269,7 +284,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), A_PACKED ? 1 : NUM_PROD_WARPS + (B_PACKED ? 1 : 0)); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), A_PACKED ? MAX_EPI_WARPS : NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -285,31 +300,37 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 
   const int ntiles = total_tiles(p);
 
-  if (warp < NUM_EPI_WARPS) {
+  constexpr int NE = A_PACKED ? MAX_EPI_WARPS : NUM_EPI_WARPS;
+  if (warp < NUM_EPI_WARPS || (A_PACKED && warp >= 8)) {
     // ============================== EPILOGUE ==============================================
     // TMEM -> registers (lane = row) -> per-warp smem transpose -> (lane = 4 columns) so that every global
     // access of the epilogue (stores, residual / saved-activation loads, atomics) is a coalesced 128-byte row.
     int acc = 0; uint32_t acc_phase = 0;
-    const int nchunks = p.BN / 32;
-    const uint32_t stage_base = bar_base + BAR_BYTES + (uint32_t)warp * EPI_STAGE_BYTES;
-    const int rl = lane >> 3, c4 = (lane & 7) * 4;      // this lane's row-in-group-of-4 and first column of 4
+    const int nchunks = p.BN / EPI_CW;
+    const int e_idx = (warp < NUM_EPI_WARPS) ? warp : warp - 4;       // 0..NE-1
+    const int quarter = warp & 3;                                      // TMEM lane quarter this warp may read
+    const int cgrp = e_idx >> 2, ncgrp = NE / 4;                       // column-chunk subset c = cgrp (mod ncgrp)
+    const int my_last = ((nchunks - 1 - cgrp) / ncgrp) * ncgrp + cgrp; // last chunk this warp reads
+    const uint32_t stage_base = bar_base + BAR_BYTES + (uint32_t)e_idx * EPI_STAGE_BYTES;
+    const int rl = lane >> 2, c4 = (lane & 3) * 4;      // this lane's row-in-group-of-8 and first column of 4
     // EPI_COLSUM: column sums are accumulated per CTA in shared memory across all its tiles of one group and
     // flushed with one global atomic per column (instead of one per column per tile).
-    const uint32_t cs_base = bar_base + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+    const uint32_t cs_base = bar_base + BAR_BYTES + MAX_EPI_WARPS * EPI_STAGE_BYTES;
     const bool cs_smem = (p.epi & EPI_COLSUM) && p.N <= COLSUM_SMEM_COLS;
     int cs_group = -1;
-    auto epi_bar = []() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    const int e_tid = e_idx * 32 + lane;
+    auto epi_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NE * 32) : "memory"); };
     auto cs_flush = [&](int group) {
       epi_bar();
       if (group >= 0) {
         float* cd = p.colsum + (long long)group * p.colsum_group_stride;
-        for (int n = threadIdx.x; n < p.N; n += NUM_EPI_WARPS * 32) {
+        for (int n = e_tid; n < p.N; n += NE * 32) {
           float sv;
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(cs_base + 4u * n) : "memory");
           if (sv != 0.f) atomicAdd(cd + n, sv);
         }
       }
-      for (int n = threadIdx.x; n < p.N; n += NUM_EPI_WARPS * 32)
+      for (int n = e_tid; n < p.N; n += NE * 32)
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(cs_base + 4u * n), "f"(0.f) : "memory");
       epi_bar();
     };
@@ -320,32 +341,34 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
       if (cs_smem && tl.group != cs_group) { if (cs_group >= 0) cs_flush(cs_group); cs_group = tl.group; }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row0 = tl.m0 + warp * 32;
+      const int row0 = tl.m0 + quarter * 32;
       float* dbase = p.D + (long long)tl.group * p.d_group_stride;
       const float* bias = p.bias ? p.bias + (long long)tl.group * p.bias_group_stride : nullptr;
-      for (int c = 0; c < nchunks; ++c) {
-        float v[32];
-        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c * 32), v);
-        if (c == nchunks - 1) {
+      bool arrived = false;
+      for (int c = cgrp; c < nchunks; c += ncgrp) {
+        float v[EPI_CW];
+        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c * EPI_CW), v);
+        if (c == my_last) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
+          arrived = true;
         }
         __syncwarp();                                     // previous chunk's reads of the stage are done
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < EPI_CW / 4; ++j)
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
                        ::"r"(stage_base + (uint32_t)(lane * EPI_STAGE_ROW_FLOATS + 4 * j) * 4u),
                          "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
         __syncwarp();
-        const int n = tl.n0 + c * 32 + c4;
+        const int n = tl.n0 + c * EPI_CW + c4;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), sv = make_float4(1.f, 1.f, 1.f, 1.f);
         if (p.epi & EPI_BIAS) bv = ldg_f4(bias + n);
         if (p.epi & EPI_COLSCALE) sv = ldg_f4(p.col_scale + n);
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rl;
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 8 + rl;
           const int row = row0 + r;
           if (row >= p.M) continue;
           float4 x;
@@ -355,10 +378,10 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
           if ((p.epi & (EPI_AUXSTORE | EPI_GELU)) && p.aux_out)
             *reinterpret_cast<float4*>(p.aux_out + (long long)row * p.ld_aux + n) = x;
-          if (p.epi & EPI_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+          if (p.epi & EPI_GELU) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
           if (p.epi & EPI_DGELU) {
             const float4 h = ldg_f4(p.aux_in + (long long)row * p.ld_aux + n);
-            x.x *= gelu_erf_grad(h.x); x.y *= gelu_erf_grad(h.y); x.z *= gelu_erf_grad(h.z); x.w *= gelu_erf_grad(h.w);
+            x.x *= gelu_grad_fast(h.x); x.y *= gelu_grad_fast(h.y); x.z *= gelu_grad_fast(h.z); x.w *= gelu_grad_fast(h.w);
           }
           x.x *= sv.x; x.y *= sv.y; x.z *= sv.z; x.w *= sv.w;
           if (p.epi & EPI_ROWSCALE) { const float rs = __ldg(p.row_scale + row); x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs; }
@@ -375,12 +398,13 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           }
         }
         if (p.epi & EPI_COLSUM) {
-          // lanes with the same (lane & 7) hold partial sums of the same 4 columns
-          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8);  cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8);  cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-          if (lane < 8) {
+          // lanes with the same (lane & 3) hold partial sums of the same 4 columns
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+          }
+          if (lane < 4) {
             if (cs_smem) {
               const uint32_t sa = cs_base + 4u * (uint32_t)n;
               asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sa), "f"(cs.x) : "memory");
@@ -393,6 +417,11 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
             }
           }
         }
+      }
+      if (!arrived) {               // this warp had no chunk in the tile (BN/16 < NE/4 never happens, but stay safe)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }

@@ -109,7 +109,7 @@ def pack_act(x, *, rows, cols, mn_major, tile=128, row_index=None, ld=None):
 # in-kernel split is repeated for every tile column that re-reads the operand and is latency/issue bound
 # (profiles/r01_gemm_isolation.txt); the packed main loop runs at the tensor-pipe rate.  Thresholds from measurements.
 import os as _os
-PACK_A_MIN_K = int(_os.environ.get('SM3_PACK_A_MIN_K', '192'))
+PACK_A_MIN_K = int(_os.environ.get('SM3_PACK_A_MIN_K', '96'))
 PACK_W_MIN_TILES = int(_os.environ.get('SM3_PACK_W_MIN_TILES', '2'))
 
 
