@@ -89,6 +89,14 @@ SIGNATURES = {
 _RESTYPES = {'sm3_last_error': C.c_char_p, 'sm3_gemm_packed_elems': C.c_int64, 'sm3_gemm_packed_act_elems': C.c_int64}
 
 
+class ActPackArgs(C.Structure):
+    _fields_ = [
+        ('h', c_f32p), ('da', c_f32p), ('R', C.c_int64), ('W', C.c_int32), ('mode', C.c_int32),
+        ('live_tiles', c_i32p), ('tile_group', c_i32p),
+        ('out_f32', c_f32p), ('pack_k', C.c_void_p), ('pack_mn', C.c_void_p), ('mn_tile', C.c_int32), ('colsum', c_f32p),
+    ]
+
+
 class RouterBwdArgs(C.Structure):
     _fields_ = [
         ('p', c_f32p), ('sim_matrix', c_f32p), ('temperature', c_f32p),
@@ -102,6 +110,7 @@ class RouterBwdArgs(C.Structure):
 
 
 SIGNATURES['sm3_moe_router_bwd'] = [C.POINTER(RouterBwdArgs), _P]
+SIGNATURES['sm3_act_pack'] = [C.POINTER(ActPackArgs), _P]
 
 
 def library_path() -> str:

@@ -114,6 +114,13 @@ int sm3_moe_combine(const float* o, const int32_t* slot_of, const int32_t* top_i
   return moe_combine(o, slot_of, top_idx, gate, gamma, resid, row_scale, out, y_opt, T, C, k, S(stream));
 }
 
+int sm3_act_pack(const sm3_act_pack_args* a, void* stream) {
+  if (!a) { set_last_error("sm3_act_pack: null args"); return SM3_ERR_INVALID_ARG; }
+  ActPackArgs r{};
+  r.h = a->h; r.da = a->da; r.R = a->R; r.W = a->W; r.mode = a->mode; r.live_tiles = a->live_tiles; r.tile_group = a->tile_group;
+  r.out_f32 = a->out_f32; r.pack_k = a->pack_k; r.pack_mn = a->pack_mn; r.mn_tile = a->mn_tile; r.colsum = a->colsum;
+  return act_pack(r, S(stream));
+}
 int sm3_moe_combine_bwd(const float* dout, const float* o, const int32_t* slot_of, const int32_t* top_idx,
                         const float* gate, const float* gamma, const float* row_scale, float* d_o, float* dgate,
                         float* dgamma, int32_t T, int32_t C, int32_t k, void* stream) {

@@ -99,6 +99,22 @@ struct RouterBwdArgs {
 int moe_router_bwd(const RouterBwdArgs& a, cudaStream_t stream);
 int moe_router_bwd_finalize(const float* dsim_hat, const float* sim, float* dsim, int P, int E, cudaStream_t stream);
 
+// act.cu -----------------------------------------------------------------------------------------
+struct ActPackArgs {
+  const float* h;            // [R, W] FFN hidden pre-activation
+  const float* da;           // [R, W] upstream gradient (mode 1) or null
+  long long R; int W;
+  int mode;                  // 0: gelu(h)   1: da * gelu'(h)   2: h
+  const int* live_tiles;     // optional device scalar: only rows < live_tiles*128 hold data (MoE pair space)
+  const int* tile_group;     // optional: group (expert) of each 128-row tile, for per-group column sums
+  float* out_f32;            // optional [R, W]
+  unsigned short* pack_k;    // optional K-major image (128-row tiles)
+  unsigned short* pack_mn;   // optional MN-major image (reduction index = row)
+  int mn_tile;               // tile width of pack_mn (128 for an A operand, the GEMM tile width for B)
+  float* colsum;             // optional [groups][W], accumulated
+};
+int act_pack(const ActPackArgs& a, cudaStream_t stream);
+
 // reduce.cu --------------------------------------------------------------------------------------
 int colsum(const float* a, const float* b, const float* rs, const int* seg_begin, const int* seg_end, int G,
            float* out, long long rows, int C, cudaStream_t stream);

@@ -144,20 +144,22 @@ class DenseBlockFn(Function):
         T = N * H * W
         train = any(ctx.needs_input_grad)
         u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
-        h = torch.empty((T, 4 * C), device=x.device, dtype=torch.float32) if train else None
-        a = ops.linear_fwd(v, w1, b1, epilogue=EPI_GELU, aux_out=h, packed=packs.get('w1'))
+        # GEMM1 stores the pre-activation only; GELU runs in the HBM-bound act_pack kernel, which emits the result
+        # directly as GEMM2's pre-split A operand (fp32 `a` never exists)
+        h = ops.linear_fwd(v, w1, b1, packed=packs.get('w1'))
+        a_k, _, _ = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_GELU, want_k=True)
         y2 = torch.empty((T, C), device=x.device, dtype=torch.float32) if train else None
         epi = EPI_COLSCALE | EPI_RESID | (EPI_ROWSCALE if row_scale is not None else 0) | (EPI_AUXSTORE if train else 0)
-        out = ops.linear_fwd(a, w2, b2, epilogue=epi, aux_out=y2, col_scale=gamma, row_scale=row_scale,
-                             resid=x.view(T, C), packed=packs.get('w2'))
+        out = ops.linear_fwd(None, w2, b2, rows=T, a_packed=a_k, epilogue=epi, aux_out=y2, col_scale=gamma,
+                             row_scale=row_scale, resid=x.view(T, C), packed=packs.get('w2'))
         if train:
-            ctx.save_for_backward(x, u, stats, v, h, a, y2, dww, lnw, w1, w2, gamma, row_scale)
+            ctx.save_for_backward(x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, row_scale)
             ctx.packs = packs
         return out.view(N, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, u, stats, v, h, a, y2, dww, lnw, w1, w2, gamma, rs = ctx.saved_tensors
+        x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, rs = ctx.saved_tensors
         N, H, W, C = x.shape
         T = N * H * W
         dout = dout.contiguous()
@@ -169,15 +171,21 @@ class DenseBlockFn(Function):
         ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
         db2 = csum * gamma
         w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
+        da = ops.linear_dgrad(dz, w2g, epilogue=(EPI_ROWSCALE if rs is not None else 0), row_scale=rs,
+                              packed=ops.pack_weight(w2g, transposed=True))
+        # dh = da * gelu'(h) goes straight into the two operand images (dgrad1's A, wgrad1's A) + db1 column sums
         db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
-        dh = ops.linear_dgrad(dz, w2g, epilogue=EPI_DGELU | (EPI_ROWSCALE if rs is not None else 0), aux_in=h,
-                              row_scale=rs, packed=ops.pack_weight(w2g, transposed=True), colsum=db1)
+        dh_k, dh_mn, _ = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_DGELU, da=da, want_k=True, mn_tile=128,
+                                      colsum=db1)
+        del da
+        _, a_mn, _ = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_GELU, mn_tile=ops._pick_bn(4 * C))
         dzs = dz if rs is None else ops.scale_rows(dz, row_scale=rs)
         dw2 = torch.zeros_like(w2)
-        ops.linear_wgrad(dzs, a, dw2, row_scale=gamma)
+        ops.linear_wgrad(dzs, None, dw2, rows=T, row_scale=gamma, x_packed=a_mn)
+        del a_mn
         dw1 = torch.zeros_like(w1)
-        ops.linear_wgrad(dh, v, dw1)
-        dv = ops.linear_dgrad(dh, w1, packed=ctx.packs.get('w1_t'))
+        ops.linear_wgrad(None, v, dw1, rows=T, dy_packed=dh_mn)
+        dv = ops.linear_dgrad(None, w1, rows=T, a_packed=dh_k, packed=ctx.packs.get('w1_t'))
         dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
         return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
 
@@ -214,11 +222,11 @@ class MoEBlockFn(Function):
         slot_of, pair_token = ops.moe_assign(r['top_idx'], plan, T=T, E=E, k=k)
         R = plan['max_rows']
         grouped = (plan['tile_group'], plan['num_m_tiles'])
-        h = torch.empty((R, 4 * C), device=x.device, dtype=torch.float32) if train else None
-        a = ops.linear_fwd(v, w1s[0], b1s[0], epilogue=EPI_GELU, aux_out=h, row_index=pair_token, rows=R,
-                           grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=4 * C, packed=packs.get('w1'))
-        o = ops.linear_fwd(a, w2s[0], b2s[0], rows=R, grouped=grouped, w_group_stride=4 * C * C, bias_group_stride=C,
-                           packed=packs.get('w2'))
+        h = ops.linear_fwd(v, w1s[0], b1s[0], row_index=pair_token, rows=R, grouped=grouped, w_group_stride=4 * C * C,
+                           bias_group_stride=4 * C, packed=packs.get('w1'))
+        a_k, _, _ = ops.act_pack(h, rows=R, width=4 * C, mode=ops.ACT_GELU, want_k=True, live_tiles=plan['num_m_tiles'])
+        o = ops.linear_fwd(None, w2s[0], b2s[0], rows=R, a_packed=a_k, grouped=grouped, w_group_stride=4 * C * C,
+                           bias_group_stride=C, packed=packs.get('w2'))
         out, y = ops.moe_combine(o, slot_of, r['top_idx'], r['top_gate'], gamma, x.view(T, C), row_scale, T=T, Cc=C,
                                  k=k, want_y=record is not None)
         if record is not None:
@@ -226,7 +234,7 @@ class MoEBlockFn(Function):
                                load=plan['load'], loss=plan['loss'], y=y, counts=plan['counts']))
         if train:
             ctx.noisy = noise is not None and k < E
-            ctx.save_for_backward(x, u, stats, v, h, a, o, dww, lnw, gamma, wp, sim, tau, row_scale, r['top_idx'],
+            ctx.save_for_backward(x, u, stats, v, h, o, dww, lnw, gamma, wp, sim, tau, row_scale, r['top_idx'],
                                   r['top_gate'], r['logits'], r['p'], slot_of, pair_token, plan['importance'],
                                   plan['seg_begin'], plan['seg_end'], plan['tile_group'], plan['num_m_tiles'],
                                   w1s[0], w2s[0], noise, r['sigma'], r['top_vals'], r['top_idx_m'], plan['load'],
@@ -238,7 +246,7 @@ class MoEBlockFn(Function):
 
     @staticmethod
     def backward(ctx, dout, dloss):
-        (x, u, stats, v, h, a, o, dww, lnw, gamma, wp, sim, tau, rs, top_idx, top_gate, logits, p, slot_of, pair_token,
+        (x, u, stats, v, h, o, dww, lnw, gamma, wp, sim, tau, rs, top_idx, top_gate, logits, p, slot_of, pair_token,
          importance, seg_begin, seg_end, tile_group, num_m_tiles, w1, w2, noise, sigma, top_vals, top_idx_m, load,
          w_noise) = ctx.saved_tensors
         E, k, R = ctx.E, ctx.k, ctx.R
@@ -254,18 +262,23 @@ class MoEBlockFn(Function):
         dgamma = torch.zeros((C,), device=dev, dtype=torch.float32)
         dgate = ops.moe_combine_bwd(dz, o, slot_of, top_idx, top_gate, gamma, rs, d_o, dgamma, T=T, Cc=C, k=k)
         # experts (grouped over the padded expert segments)
-        dh = torch.zeros((R, 4 * C), device=dev, dtype=torch.float32)
+        da = ops.linear_dgrad(d_o, w2, grouped=grouped, w_group_stride=4 * C * C, packed=ctx.packs.get('w2_t'))
         db1s = torch.zeros((E, 4 * C), device=dev, dtype=torch.float32)
-        ops.linear_dgrad(d_o, w2, epilogue=EPI_DGELU, aux_in=h, out=dh, grouped=grouped, w_group_stride=4 * C * C,
-                         packed=ctx.packs.get('w2_t'), colsum=db1s, colsum_group_stride=4 * C)
+        dh_k, dh_mn, _ = ops.act_pack(h, rows=R, width=4 * C, mode=ops.ACT_DGELU, da=da, want_k=True, mn_tile=128,
+                                      colsum=db1s, live_tiles=num_m_tiles, tile_group=tile_group)
+        del da
+        _, a_mn, _ = ops.act_pack(h, rows=R, width=4 * C, mode=ops.ACT_GELU, mn_tile=ops._pick_bn(4 * C),
+                                  live_tiles=num_m_tiles)
         dw2s = torch.zeros((E, C, 4 * C), device=dev, dtype=torch.float32)
-        ops.linear_wgrad(d_o, a, dw2s, rows=R, segs=segs, num_groups=E)
+        ops.linear_wgrad(d_o, None, dw2s, rows=R, segs=segs, num_groups=E, x_packed=a_mn)
+        del a_mn
         db2s = torch.zeros((E, C), device=dev, dtype=torch.float32)
         ops.colsum(d_o, db2s, rows=R, Cc=C, segs=segs, groups=E)
         dw1s = torch.zeros((E, 4 * C, C), device=dev, dtype=torch.float32)
-        ops.linear_wgrad(dh, v, dw1s, rows=R, x_row_index=pair_token, segs=segs, num_groups=E)
+        ops.linear_wgrad(None, v, dw1s, rows=R, x_row_index=pair_token, segs=segs, num_groups=E, dy_packed=dh_mn)
         dxp = torch.zeros((R, C), device=dev, dtype=torch.float32)
-        ops.linear_dgrad(dh, w1, out=dxp, grouped=grouped, w_group_stride=4 * C * C, packed=ctx.packs.get('w1_t'))
+        ops.linear_dgrad(None, w1, rows=R, a_packed=dh_k, out=dxp, grouped=grouped, w_group_stride=4 * C * C,
+                         packed=ctx.packs.get('w1_t'))
         # router
         P = wp.shape[0]
         dtau = torch.zeros((1,), device=dev, dtype=torch.float32)

@@ -105,6 +105,30 @@ def pack_act(x, *, rows, cols, mn_major, tile=128, row_index=None, ld=None):
     return out
 
 
+ACT_GELU, ACT_DGELU, ACT_COPY = 0, 1, 2
+
+
+def act_pack(h, *, rows, width, mode, da=None, want_k=False, mn_tile=0, want_f32=False, colsum=None, live_tiles=None,
+             tile_group=None):
+    """Fused activation + pre-split (sm3_act_pack).  Returns (pack_k, pack_mn, out_f32); absent outputs are None."""
+    lib = _lib.load()
+    dev = h.device
+    a = _lib.ActPackArgs()
+    pk = pm = of = None
+    if want_k:
+        pk = torch.empty((lib.sm3_gemm_packed_act_elems(rows, width, 0, 128),), device=dev, dtype=torch.int16)
+    if mn_tile:
+        pm = torch.empty((lib.sm3_gemm_packed_act_elems(rows, width, 1, mn_tile),), device=dev, dtype=torch.int16)
+    if want_f32:
+        of = torch.empty((rows, width), device=dev, dtype=torch.float32)
+    a.h = _p(h); a.da = _p(da); a.R = rows; a.W = width; a.mode = mode
+    a.live_tiles = _pi(live_tiles); a.tile_group = _pi(tile_group)
+    a.out_f32 = _p(of); a.pack_k = None if pk is None else pk.data_ptr(); a.pack_mn = None if pm is None else pm.data_ptr()
+    a.mn_tile = mn_tile; a.colsum = _p(colsum)
+    _lib.check(lib.sm3_act_pack(C.byref(a), _stream()), 'sm3_act_pack')
+    return pk, pm, of
+
+
 # When is an extra pack pass (8 B/element of HBM traffic) cheaper than splitting the operand inside the GEMM?  The
 # in-kernel split is repeated for every tile column that re-reads the operand and is latency/issue bound
 # (profiles/r01_gemm_isolation.txt); the packed main loop runs at the tensor-pipe rate.  Thresholds from measurements.
@@ -118,20 +142,25 @@ def _pack_a_pays(N, K):
 
 
 def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale=None, row_scale=None, resid=None,
-               row_index=None, rows=None, grouped=None, w_group_stride=0, bias_group_stride=0, packed=None):
-    """out[M,N] = epi(x[M,K] @ w[N,K]^T).  grouped = (tile_group, num_m_tiles) for expert segments."""
-    K = x.shape[-1]
+               row_index=None, rows=None, grouped=None, w_group_stride=0, bias_group_stride=0, packed=None,
+               a_packed=None):
+    """out[M,N] = epi(x[M,K] @ w[N,K]^T).  grouped = (tile_group, num_m_tiles) for expert segments.
+    a_packed: an already pre-split K-major image of x (then x may be None and `rows` is required)."""
+    K = w.shape[-1]
     N = w.shape[-2]
     M = rows if rows is not None else x.shape[0]
     if out is None:
-        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        out = torch.empty((M, N), device=w.device, dtype=torch.float32)
     epi = epilogue | (EPI_BIAS if bias is not None else 0)
     kw = {}
     if grouped is not None:
         kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
     if packed is not None:
         kw.update(b_packed=packed[0], b_packed_group_stride=packed[1])
-        if _pack_a_pays(N, K):
+        if a_packed is not None:
+            kw.update(a_packed=a_packed)
+            row_index = None
+        elif _pack_a_pays(N, K):
             kw.update(a_packed=pack_act(x, rows=M, cols=K, mn_major=False, row_index=row_index))
             row_index = None
     gemm(A=x, a_smn=K, a_sk=1, B=w, b_smn=K, b_sk=1, b_group_stride=w_group_stride, M=M, N=N, K=K, D=out, ldd=N,
@@ -141,18 +170,22 @@ def linear_fwd(x, w, bias=None, *, epilogue=0, out=None, aux_out=None, col_scale
 
 
 def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, resid=None, grouped=None,
-                 w_group_stride=0, packed=None, colsum=None, colsum_group_stride=0):
-    """dx[M,K] = epi(dy[M,N] @ w[N,K])   (w used as an MN-major B operand; no transposed copy)."""
-    M, N = dy.shape
+                 w_group_stride=0, packed=None, colsum=None, colsum_group_stride=0, a_packed=None, rows=None):
+    """dx[M,K] = epi(dy[M,N] @ w[N,K])   (w used as an MN-major B operand; no transposed copy).
+    a_packed: pre-split K-major image of dy (then dy may be None and `rows` is required)."""
+    N = w.shape[-2]
+    M = rows if rows is not None else dy.shape[0]
     K = w.shape[-1]
     if out is None:
-        out = torch.empty((M, K), device=dy.device, dtype=torch.float32)
+        out = torch.empty((M, K), device=w.device, dtype=torch.float32)
     kw = {}
     if grouped is not None:
         kw = dict(sched=SCHED_GROUPED, tile_group=grouped[0], num_m_tiles=grouped[1])
     if packed is not None:
         kw.update(b_packed=packed[0], b_packed_group_stride=packed[1])
-        if _pack_a_pays(K, N):
+        if a_packed is not None:
+            kw.update(a_packed=a_packed)
+        elif _pack_a_pays(K, N):
             kw.update(a_packed=pack_act(dy, rows=M, cols=N, mn_major=False))
     gemm(A=dy, a_smn=N, a_sk=1, B=w, b_smn=1, b_sk=K, b_group_stride=w_group_stride, M=M, N=K, K=N, D=out, ldd=K,
          epilogue=epilogue | (EPI_COLSUM if colsum is not None else 0), aux_in=aux_in, ld_aux=K, row_scale=row_scale,
@@ -160,25 +193,29 @@ def linear_dgrad(dy, w, *, epilogue=0, out=None, aux_in=None, row_scale=None, re
     return out
 
 
-def linear_wgrad(dy, x, dw, *, rows=None, x_row_index=None, row_scale=None, segs=None, num_groups=1):
+def linear_wgrad(dy, x, dw, *, rows=None, x_row_index=None, row_scale=None, segs=None, num_groups=1, dy_packed=None,
+                 x_packed=None):
     """dw[g][N,K] += dy[rows_g, N]^T @ x[rows_g, K]  (split-K with fp32 atomics; dw must be pre-zeroed).
 
     row_scale (optional, [N]) scales the rows of dw (e.g. layer-scale gamma folded into the epilogue).
     segs = (seg_begin, seg_end) device int32 arrays selecting each group's row range.
     """
     R = rows if rows is not None else dy.shape[0]
-    N = dy.shape[1]
-    K = x.shape[1]
+    N = dw.shape[-2]
+    K = dw.shape[-1]
     tiles = ((N + 127) // 128) * (K // _pick_bn(K)) * num_groups
     # ~3 work items per SM (the per-expert segments are unequal), but at least 1024 reduction rows per split
     splits = -(-3 * num_sms() // max(1, tiles))
     splits = max(1, min(64, splits, max(1, (R // num_groups) // 1024)))
     epi = EPI_ATOMIC | (EPI_ROWSCALE if row_scale is not None else 0)
     kw = {}
-    if ((N + 127) // 128) * (K // _pick_bn(K)) >= PACK_W_MIN_TILES:
+    if dy_packed is not None or x_packed is not None or ((N + 127) // 128) * (K // _pick_bn(K)) >= PACK_W_MIN_TILES:
         # both operands are re-read by several output tiles: split them once (MN-major images), gather included
-        kw = dict(a_packed=pack_act(dy, rows=R, cols=N, mn_major=True, tile=128),
-                  b_packed=pack_act(x, rows=R, cols=K, mn_major=True, tile=_pick_bn(K), row_index=x_row_index))
+        if dy_packed is None:
+            dy_packed = pack_act(dy, rows=R, cols=N, mn_major=True, tile=128)
+        if x_packed is None:
+            x_packed = pack_act(x, rows=R, cols=K, mn_major=True, tile=_pick_bn(K), row_index=x_row_index)
+        kw = dict(a_packed=dy_packed, b_packed=x_packed)
         x_row_index = None
     gemm(A=dy, a_smn=1, a_sk=N, B=x, b_smn=1, b_sk=K, M=N, N=K, K=R, D=dw, ldd=K, d_group_stride=N * K,
          b_k_index=x_row_index, **kw, sched=SCHED_SPLITK, k_splits=splits, num_groups=num_groups,
