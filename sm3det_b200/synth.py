@@ -74,8 +74,19 @@ def make_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0,
                     not key.startswith(('downsample_layers.1.1', 'downsample_layers.2.1', 'downsample_layers.3.1'))))
         if key.startswith('downsample_layers.0.0') and len(shapes[key.rsplit('.', 1)[0] + '.weight']) == 4:
             is_norm = False                                    # plain ConvNeXt_moe: .0.0 is the stem conv
+        if (key.rsplit('.', 1)[0] + '.running_mean') in shapes:
+            is_norm = True                                     # BatchNorm affine (LSKNet: norm1/2, patch_embed*.norm)
         if leaf == 'gamma':
             t = torch.rand(shape, generator=g) * 0.9 + 0.1 if trained_like else torch.full(shape, 1e-6)
+        elif leaf.startswith('layer_scale_'):                  # lsk_moe.py:381-385 (init 1e-2)
+            t = torch.rand(shape, generator=g) * 0.9 + 0.1 if trained_like else torch.full(shape, 1e-2)
+        elif leaf == 'running_mean':
+            t = torch.randn(shape, generator=g) * 0.1 if trained_like else torch.zeros(shape)
+        elif leaf == 'running_var':
+            t = torch.rand(shape, generator=g) + 0.5 if trained_like else torch.ones(shape)
+        elif leaf == 'num_batches_tracked':
+            sd[key] = torch.tensor(0, dtype=torch.long)
+            continue
         elif leaf == 'temperature':
             t = torch.full(shape, math.log(10.0) if trained_like else math.log(2.0))
         elif leaf == 'sim_matrix':
