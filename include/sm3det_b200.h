@@ -138,7 +138,8 @@ int sm3_dwconv7_wgrad(const float* x, const float* dy, float* dweight_t, float* 
  * sm3_moe_assign : pair (token, j) -> slot, and pair_token[slot] = token (caller pre-fills -1).
  * sm3_moe_combine: SparseDispatcher.combine :269-284 + layer scale :367-368 + shortcut/drop-path
  *                  :370: out = resid + row_scale * gamma * sum_j gate_j * o[slot_j]  (ascending
- *                  expert order, no atomics).
+ *                  expert order, no atomics).  gamma / resid / row_scale may be NULL (LSKNet MoE fc1,
+ *                  lsk_moe.py:243-263: plain gate-weighted sum).
  */
 typedef struct sm3_router_args {
   const float* v; const float* proj_weight; const float* proj_bias; const float* sim_matrix;
@@ -208,6 +209,47 @@ int sm3_gather_sum(const float* src, const int32_t* slot_of, const float* add, f
                    int32_t k, void* stream);
 int sm3_scale_rows(const float* x, const float* row_scale, const float* col_scale, float* out, int64_t rows,
                    int32_t C, void* stream);
+
+/* ---- LSKNet-MoE backbone (BASELINE config 5; mmrotate/models/backbones/lsk_moe.py) -------------------
+ * sm3_dwconv_fwd / _wgrad : depthwise ks x ks conv, dilation dil, "same" padding, NHWC; weight_t = taps as
+ *                           [ks*ks][C].  Replaces LSKblock.conv0 (5x5) :322, conv_spatial (7x7 dil 3) :323 and
+ *                           DWConv (3x3) :583; dgrad = the same call on dy with flipped taps (+ resid).
+ *                           Instantiated (ks,dil): (3,1) (5,1) (7,3).
+ * sm3_colstat             : s1[c] += sum_r (x-sh1), s2[c] += sum_r (x-sh1) * (y ? (y-sh2)*sc2 : (x-sh1)).
+ *                           BatchNorm2d batch statistics (shifted by running_mean, one pass) and the two
+ *                           reductions of its backward (sum dy, sum dy*xhat).  Block.norm1/2 :369-374.
+ * sm3_affine              : out = a1[c]*x1 + a2[c]*x2 + b[c] + add  -- BN normalise, BN backward, layer-scale +
+ *                           residual (:388-395); NULL operands are skipped (a1 NULL = 1).
+ * sm3_mul                 : out = a*b (+ add)  -- x * attn :343 and its backward.
+ * sm3_lsk_agg             : channel mean / max (+argmax) of cat(attn1, attn2) :336-338.
+ * sm3_conv7_c2 / _wgrad   : conv_squeeze Conv2d(2,2,7,padding=3) (+ sigmoid when act=1) :339; dgrad = the same call
+ *                           with transposed + flipped weights, act=0.
+ * sm3_lsk_mix (+bwd)      : attn1*sig[:,0] + attn2*sig[:,1] :340 and its backward into the sigmoid input / attn1,2.
+ * sm3_im2col / sm3_col2im : OverlapPatchEmbed.proj (7x7/s4 stem from NCHW, 3x3/s2 downsamples from NHWC) :405-406
+ *                           lowered to sm3_gemm; columns ordered (kh, kw, ci), zero padded to Kp.
+ */
+int sm3_dwconv_fwd(const float* x, const float* weight_t, const float* bias, const float* resid, float* y, int32_t N,
+                   int32_t H, int32_t W, int32_t C, int32_t ks, int32_t dil, void* stream);
+int sm3_dwconv_wgrad(const float* x, const float* dy, float* dweight_t, float* dbias, int32_t N, int32_t H, int32_t W,
+                     int32_t C, int32_t ks, int32_t dil, void* stream);
+int sm3_colstat(const float* x, const float* sh1, const float* y, const float* sh2, const float* sc2, float* s1, float* s2,
+                int64_t rows, int32_t C, void* stream);
+int sm3_affine(const float* x1, const float* a1, const float* x2, const float* a2, const float* b, const float* add,
+               float* out, int64_t rows, int32_t C, void* stream);
+int sm3_mul(const float* a, const float* b, const float* add, float* out, int64_t n, void* stream);
+int sm3_lsk_agg(const float* a1, const float* a2, float* agg, int32_t* amax, int64_t T, int32_t Ch, void* stream);
+int sm3_conv7_c2(const float* x, const float* w, const float* b, float* y, int32_t N, int32_t H, int32_t W, int32_t act,
+                 void* stream);
+int sm3_conv7_c2_wgrad(const float* x, const float* dpre, float* dw, float* db, int32_t N, int32_t H, int32_t W, void* stream);
+int sm3_lsk_mix(const float* a1, const float* a2, const float* sig, float* out, int64_t T, int32_t Ch, void* stream);
+int sm3_lsk_mix_bwd_sig(const float* dout, const float* a1, const float* a2, const float* sig, float* dpre, int64_t T,
+                        int32_t Ch, void* stream);
+int sm3_lsk_mix_bwd_in(const float* dout, const float* sig, const float* dagg, const int32_t* amax, float* da1, float* da2,
+                       int64_t T, int32_t Ch, void* stream);
+int sm3_im2col(const float* x, float* col, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
+               int32_t pad, int32_t Kp, int32_t nchw, void* stream);
+int sm3_col2im(const float* dcol, float* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
+               int32_t pad, int32_t Kp, void* stream);
 
 #ifdef __cplusplus
 }

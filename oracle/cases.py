@@ -52,3 +52,57 @@ def summarize_grad(g: torch.Tensor):
         return dict(full=g.clone())
     idx = torch.linspace(0, g.numel() - 1, 256).long()
     return dict(sample=g[idx].clone(), idx=idx, l2=g.double().norm().item(), s=g.double().sum().item())
+
+
+# ---- LSKNet-MoE (BASELINE config 5 family; oracle/lsk_moe_oracle.py) --------------------------------------------
+LSK_MINI = dict(embed_dims=[64, 64, 128, 128], depths=[1, 1, 2, 1], mlp_ratios=[4, 4, 2, 2])
+LSK_CASES = {
+    'lsk_mini_dense_eval': dict(kw=dict(**LSK_MINI), img=(2, 64, 64), mode='eval'),
+    'lsk_mini_moe_e4k2_eval': dict(kw=dict(**LSK_MINI, MoE_Block_inds_fc1=[[], [0], [0, 1], [0]],
+                                           MoE_Block_inds_fc2=[[], [0], [0, 1], [0]], num_experts=4, top_k=2),
+                               img=(2, 64, 96), mode='eval'),
+    'lsk_mini_moe_e4k2_train_clean': dict(kw=dict(**LSK_MINI, MoE_Block_inds_fc1=[[0], [0], [0, 1], [0]],
+                                                  MoE_Block_inds_fc2=[[], [0], [1], [0]], num_experts=4, top_k=2,
+                                                  noisy_gating=False),
+                                      img=(2, 64, 64), mode='train'),
+    'lsk_mini_moe_e3k1_train_noisy_drop': dict(kw=dict(**LSK_MINI, MoE_Block_inds_fc1=[[], [0], [0], [0]],
+                                                       MoE_Block_inds_fc2=[[], [0], [0, 1], []], num_experts=3, top_k=1,
+                                                       drop_rate=0.1),
+                                           img=(3, 64, 64), mode='train_noisy'),
+}
+
+
+def lsk_plan(cfg, n, h, w):
+    """Per MoE layer (in forward order) its token count, and per dropout call its tensor shape [N,C,H,W]."""
+    tokens, drops = [], []
+    for i in range(cfg.num_stages):
+        hh, ww = h // (4 * 2 ** i), w // (4 * 2 ** i)
+        hid = int(cfg.embed_dims[i] * cfg.mlp_ratios[i])
+        for j in range(cfg.depths[i]):
+            if j in cfg.moe_fc1(i):
+                tokens.append(n * hh * ww)
+            if j in cfg.moe_fc2(i):
+                tokens.append(n * hh * ww)
+            drops.append((n, hid, hh, ww))
+            drops.append((n, cfg.embed_dims[i], hh, ww))
+    return tokens, drops
+
+
+def make_drop_masks(shapes, rate, seed=31):
+    out = []
+    for i, s in enumerate(shapes):
+        g = torch.Generator().manual_seed(seed + i)
+        out.append((torch.rand(s, generator=g) >= rate).float() / (1.0 - rate))
+    return out
+
+
+def lsk_injections(cfg, gold):
+    """(noise list, dropout mask list) a fixture's training mode injects, in forward order (None when inactive)."""
+    n, h, w = gold['img']
+    tokens, dshapes = lsk_plan(cfg, n, h, w)
+    noise = drops = None
+    if gold['mode'] == 'train_noisy':
+        noise = [torch.randn(t, cfg.num_experts, generator=torch.Generator().manual_seed(7 + i)) for i, t in enumerate(tokens)]
+    if cfg.drop_rate > 0 and gold['mode'] != 'eval':
+        drops = make_drop_masks(dshapes, cfg.drop_rate)
+    return noise, drops

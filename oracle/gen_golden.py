@@ -99,8 +99,98 @@ def run_case(name, spec):
     print(f'{name}: ok, {os.path.getsize(path) / 1024:.0f} KiB, moe layers {len(record)}')
 
 
+def run_lsk_case(name, spec):
+    """LSKNet-MoE: run the unmodified reference lsk_moe.py, assert the restated oracle reproduces it bit-for-bit
+    (outputs, gate loss, routing, parameter gradients, BatchNorm running statistics), save the fixture."""
+    import torch.nn.functional as F
+    from oracle.cases import lsk_plan, make_drop_masks
+    from oracle.lsk_moe_oracle import LskConfig, lsk_backbone_forward, lsk_param_shapes
+    kw = dict(spec['kw'])
+    cfg = LskConfig(**kw)
+    mod = ref_shim.load_reference_module('lsk_moe')
+    torch.manual_seed(0)
+    net = mod.LSKNet_moe_MultiInput(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
+    shapes = lsk_param_shapes(cfg)
+    rsd = net.state_dict()
+    assert set(shapes) == set(rsd), set(shapes) ^ set(rsd)
+    for k, sh in shapes.items():
+        assert tuple(rsd[k].shape) == tuple(sh), k
+    sd = make_state_dict(shapes, seed=0, trained_like=True)
+    net.load_state_dict(sd, strict=True)
+    n, h, w = spec['img']
+    x = make_images(n, h, w, seed=1234)
+    mode = spec['mode']
+    gold = dict(name=name, kw=kw, img=spec['img'], mode=mode, weights='trained', family='lsk',
+                sd_checksum=state_dict_checksum({k: v.float() for k, v in sd.items()}), x_checksum=float(x.double().abs().sum()))
+    record, bn_state = [], {}
+    no_grad_keys = ('running_', 'num_batches', '.mean', '.std')
+    if mode == 'eval':
+        net.eval()
+        with torch.no_grad():
+            ref = net(x)
+            orc = lsk_backbone_forward(sd, cfg, x, train=False, record=record)
+    else:
+        net.train()
+        noise = drops = None
+        tokens, dshapes = lsk_plan(cfg, n, h, w)
+        orig_randn, orig_drop = torch.randn_like, F.dropout
+        if mode == 'train_noisy':
+            noise = [torch.randn(t, cfg.num_experts, generator=torch.Generator().manual_seed(7 + i)) for i, t in enumerate(tokens)]
+            it = iter(noise)
+            torch.randn_like = lambda t, *a, **k: next(it).to(t.dtype)
+        if cfg.drop_rate > 0:
+            drops = make_drop_masks(dshapes, cfg.drop_rate)
+            dit = iter(drops)
+            F.dropout = lambda t, p=0.5, training=True, inplace=False: t * next(dit) if training else t
+        try:
+            ref = net(x)
+        finally:
+            torch.randn_like, F.dropout = orig_randn, orig_drop
+        sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not any(t in k for t in no_grad_keys) else v)
+               for k, v in sd.items()}
+        orc = lsk_backbone_forward(sdg, cfg, x, train=True, noise=noise, drop_masks=drops, record=record, bn_state=bn_state)
+    has_loss = isinstance(ref, tuple) and len(ref) == 2 and isinstance(ref[0], tuple)
+    r_outs, r_loss = (ref if has_loss else (ref, None))
+    o_outs, o_loss = (orc if has_loss else (orc, None))
+    for a, b in zip(r_outs, o_outs):
+        assert torch.equal(a, b), f'{name}: oracle output differs from reference by {(a - b).abs().max()}'
+    if has_loss:
+        assert torch.equal(r_loss, o_loss), (r_loss, o_loss)
+        gold['gate_loss'] = r_loss.detach().clone()
+    gold['outs'] = [o.detach().clone() for o in r_outs]
+    gold['stride'] = 1
+    gold['moe'] = [dict(prefix=r['prefix'], top_idx=r['top_idx'].to(torch.int16), top_gates=r['top_gates'],
+                        importance=r['importance'], load=r['load'], loss=r['loss']) for r in record]
+    if mode != 'eval':
+        ups = upstream_grads(r_outs)
+        (sum((o * g).sum() for o, g in zip(r_outs, ups)) + (r_loss if has_loss else 0.0)).backward()
+        (sum((o * g).sum() for o, g in zip(o_outs, ups)) + (o_loss if has_loss else 0.0)).backward()
+        grads = {}
+        for pname, p in net.named_parameters():
+            og = sdg[pname].grad
+            if p.grad is None:
+                assert og is None or float(og.abs().max()) == 0.0, pname
+                continue
+            assert og is not None, pname
+            assert torch.equal(p.grad, og), f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
+            grads[pname] = summarize_grad(p.grad)
+        gold['grads'] = grads
+        new_sd = net.state_dict()
+        for k, v in bn_state.items():
+            assert torch.equal(v, new_sd[k]), k
+        gold['bn'] = {k: v.clone() for k, v in bn_state.items()}
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + '.pt')
+    torch.save(gold, path)
+    print(f'{name}: ok, {os.path.getsize(path) / 1024:.0f} KiB, moe layers {len(record)}')
+
+
 if __name__ == '__main__':
+    from oracle.cases import LSK_CASES
     torch.set_num_threads(8)
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(LSK_CASES))
     for nm in names:
-        run_case(nm, CASES[nm])
+        if nm in LSK_CASES:
+            run_lsk_case(nm, LSK_CASES[nm])
+        else:
+            run_case(nm, CASES[nm])

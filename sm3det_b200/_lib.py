@@ -85,6 +85,20 @@ SIGNATURES = {
     'sm3_gather_sum': [_P, _P, _P, _P, _I32, _I32, _I32, _P],
     'sm3_scale_rows': [_P, _P, _P, _P, _I64, _I32, _P],
     'sm3_moe_router_bwd': [_P, _P],
+    # LSKNet-MoE
+    'sm3_dwconv_fwd': [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    'sm3_dwconv_wgrad': [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    'sm3_colstat': [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    'sm3_affine': [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    'sm3_mul': [_P, _P, _P, _P, _I64, _P],
+    'sm3_lsk_agg': [_P, _P, _P, _P, _I64, _I32, _P],
+    'sm3_conv7_c2': [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    'sm3_conv7_c2_wgrad': [_P, _P, _P, _P, _I32, _I32, _I32, _P],
+    'sm3_lsk_mix': [_P, _P, _P, _P, _I64, _I32, _P],
+    'sm3_lsk_mix_bwd_sig': [_P, _P, _P, _P, _P, _I64, _I32, _P],
+    'sm3_lsk_mix_bwd_in': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    'sm3_im2col': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    'sm3_col2im': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 _RESTYPES = {'sm3_last_error': C.c_char_p, 'sm3_gemm_packed_elems': C.c_int64, 'sm3_gemm_packed_act_elems': C.c_int64}
 

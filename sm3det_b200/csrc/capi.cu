@@ -150,4 +150,53 @@ int sm3_scale_rows(const float* x, const float* rs, const float* cs, float* out,
   return scale_rows(x, rs, cs, out, rows, C, S(stream));
 }
 
+int sm3_dwconv_fwd(const float* x, const float* wt, const float* bias, const float* resid, float* y, int32_t N, int32_t H,
+                   int32_t W, int32_t C, int32_t ks, int32_t dil, void* stream) {
+  return dwconv_fwd(x, wt, bias, resid, y, N, H, W, C, ks, dil, S(stream));
+}
+int sm3_dwconv_wgrad(const float* x, const float* dy, float* dwt, float* dbias, int32_t N, int32_t H, int32_t W, int32_t C,
+                     int32_t ks, int32_t dil, void* stream) {
+  return dwconv_wgrad(x, dy, dwt, dbias, N, H, W, C, ks, dil, S(stream));
+}
+int sm3_colstat(const float* x, const float* sh1, const float* y, const float* sh2, const float* sc2, float* s1, float* s2,
+                int64_t rows, int32_t C, void* stream) {
+  return colstat(x, sh1, y, sh2, sc2, s1, s2, rows, C, S(stream));
+}
+int sm3_affine(const float* x1, const float* a1, const float* x2, const float* a2, const float* b, const float* add,
+               float* out, int64_t rows, int32_t C, void* stream) {
+  return affine(x1, a1, x2, a2, b, add, out, rows, C, S(stream));
+}
+int sm3_mul(const float* a, const float* b, const float* add, float* out, int64_t n, void* stream) {
+  return mul(a, b, add, out, n, S(stream));
+}
+int sm3_lsk_agg(const float* a1, const float* a2, float* agg, int32_t* amax, int64_t T, int32_t Ch, void* stream) {
+  return lsk_agg(a1, a2, agg, amax, T, Ch, S(stream));
+}
+int sm3_conv7_c2(const float* x, const float* w, const float* b, float* y, int32_t N, int32_t H, int32_t W, int32_t act,
+                 void* stream) {
+  return conv7_c2(x, w, b, y, N, H, W, act, S(stream));
+}
+int sm3_conv7_c2_wgrad(const float* x, const float* dpre, float* dw, float* db, int32_t N, int32_t H, int32_t W, void* stream) {
+  return conv7_c2_wgrad(x, dpre, dw, db, N, H, W, S(stream));
+}
+int sm3_lsk_mix(const float* a1, const float* a2, const float* sig, float* out, int64_t T, int32_t Ch, void* stream) {
+  return lsk_mix(a1, a2, sig, out, T, Ch, S(stream));
+}
+int sm3_lsk_mix_bwd_sig(const float* dout, const float* a1, const float* a2, const float* sig, float* dpre, int64_t T,
+                        int32_t Ch, void* stream) {
+  return lsk_mix_bwd_sig(dout, a1, a2, sig, dpre, T, Ch, S(stream));
+}
+int sm3_lsk_mix_bwd_in(const float* dout, const float* sig, const float* dagg, const int32_t* amax, float* da1, float* da2,
+                       int64_t T, int32_t Ch, void* stream) {
+  return lsk_mix_bwd_in(dout, sig, dagg, amax, da1, da2, T, Ch, S(stream));
+}
+int sm3_im2col(const float* x, float* col, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
+               int32_t pad, int32_t Kp, int32_t nchw, void* stream) {
+  return im2col(x, col, N, H, W, Cin, ks, stride, pad, Kp, nchw, S(stream));
+}
+int sm3_col2im(const float* dcol, float* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
+               int32_t pad, int32_t Kp, void* stream) {
+  return col2im(dcol, dx, N, H, W, Cin, ks, stride, pad, Kp, S(stream));
+}
+
 }  // extern "C"

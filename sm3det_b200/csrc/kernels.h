@@ -123,4 +123,27 @@ int gather_sum(const float* src, const int* slot_of, const float* add, float* ou
 int scale_rows(const float* x, const float* rs, const float* cs, float* out, long long rows, int C,
                cudaStream_t stream);
 
+// lsk.cu (LSKNet-MoE, BASELINE config 5) --------------------------------------------------------------
+// wt: depthwise taps transposed to [ks*ks][C]; "same" padding dil*(ks-1)/2.  Instantiated: (3,1) (5,1) (7,3).
+int dwconv_fwd(const float* x, const float* wt, const float* bias, const float* resid, float* y, int N, int H, int W, int C,
+               int ks, int dil, cudaStream_t stream);
+int dwconv_wgrad(const float* x, const float* dy, float* dwt, float* dbias, int N, int H, int W, int C, int ks, int dil,
+                 cudaStream_t stream);
+int colstat(const float* x, const float* sh1, const float* y, const float* sh2, const float* sc2, float* s1, float* s2,
+            long long rows, int C, cudaStream_t stream);
+int affine(const float* x1, const float* a1, const float* x2, const float* a2, const float* b, const float* add, float* out,
+           long long rows, int C, cudaStream_t stream);
+int mul(const float* a, const float* b, const float* add, float* out, long long n, cudaStream_t stream);
+int lsk_agg(const float* a1, const float* a2, float* agg, int* amax, long long T, int Ch, cudaStream_t stream);
+int conv7_c2(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int act, cudaStream_t stream);
+int conv7_c2_wgrad(const float* x, const float* dpre, float* dw, float* db, int N, int H, int W, cudaStream_t stream);
+int lsk_mix(const float* a1, const float* a2, const float* sig, float* out, long long T, int Ch, cudaStream_t stream);
+int lsk_mix_bwd_sig(const float* dout, const float* a1, const float* a2, const float* sig, float* dpre, long long T, int Ch,
+                    cudaStream_t stream);
+int lsk_mix_bwd_in(const float* dout, const float* sig, const float* dagg, const int* amax, float* da1, float* da2,
+                   long long T, int Ch, cudaStream_t stream);
+int im2col(const float* x, float* col, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, int nchw,
+           cudaStream_t stream);
+int col2im(const float* dcol, float* dx, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, cudaStream_t stream);
+
 }  // namespace sm3

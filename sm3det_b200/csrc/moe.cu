@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(256) moe_combine_kernel(const float* __restric
     y.z = __fadd_rn(y.z, __fmul_rn(g, v.z)); y.w = __fadd_rn(y.w, __fmul_rn(g, v.w));
   }
   if (y_opt) *reinterpret_cast<float4*>(y_opt + t * C + c) = y;
-  const float4 gm = ldg_f4(gamma + c);
+  const float4 gm = gamma ? ldg_f4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
   const float rs = row_scale ? __ldg(row_scale + t) : 1.0f;
-  const float4 r = ldg_f4(resid + t * C + c);
+  const float4 r = resid ? ldg_f4(resid + t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 res;
   res.x = __fadd_rn(r.x, __fmul_rn(__fmul_rn(y.x, gm.x), rs)); res.y = __fadd_rn(r.y, __fmul_rn(__fmul_rn(y.y, gm.y), rs));
   res.z = __fadd_rn(r.z, __fmul_rn(__fmul_rn(y.z, gm.z), rs)); res.w = __fadd_rn(r.w, __fmul_rn(__fmul_rn(y.w, gm.w), rs));
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256) moe_combine_kernel(const float* __restric
 
 int moe_combine(const float* o, const int* slot_of, const int* top_idx, const float* gate, const float* gamma, const float* resid,
                 const float* row_scale, float* out, float* y_opt, int T, int C, int k, cudaStream_t stream) {
-  SM3_REQUIRE(o && slot_of && top_idx && gate && gamma && resid && out, SM3_ERR_INVALID_ARG, "moe_combine: null argument");
+  SM3_REQUIRE(o && slot_of && top_idx && gate && out, SM3_ERR_INVALID_ARG, "moe_combine: null argument");   // gamma / resid optional (LSK fc1)
   SM3_REQUIRE(C % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "moe_combine: C=%d", C);
   const long long total = (long long)T * (C / 4);
   moe_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(o, slot_of, top_idx, gate, gamma, resid, row_scale, out, y_opt, total, C, k);
@@ -408,12 +408,66 @@ __global__ void __launch_bounds__(256) moe_combine_bwd_kernel(const float* __res
   for (int i = 0; i < V; ++i) atomicAdd(dgamma + lane + 32 * i, adg[i]);
 }
 
+// Any C (multiple of 4), optional gamma: warp per token, lanes stride over float4 channel quads; dgamma (if requested) is
+// accumulated with one atomic per channel per token-group -- used by the LSKNet MoE layers whose output width is the MLP
+// hidden size (up to 2048) and which have no layer scale of their own (lsk_moe.py:195-228).
+__global__ void __launch_bounds__(256) moe_combine_bwd_generic_kernel(const float* __restrict__ dout, const float* __restrict__ o,
+                                                                     const int* __restrict__ slot_of, const float* __restrict__ gate,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ row_scale,
+                                                                     float* __restrict__ d_o, float* __restrict__ dgate,
+                                                                     float* __restrict__ dgamma, int T, int C, int k) {
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const float rs = row_scale ? __ldg(row_scale + t) : 1.0f;
+  for (int j = 0; j < k; ++j) {
+    const int s = __ldg(slot_of + t * k + j);
+    if (s < 0) { if (lane == 0) dgate[t * k + j] = 0.f; continue; }
+    const float g = __ldg(gate + t * k + j);
+    float dot = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 dy = ldg_f4(dout + t * C + c);
+      dy.x *= rs; dy.y *= rs; dy.z *= rs; dy.w *= rs;
+      if (gamma) { const float4 gm = ldg_f4(gamma + c); dy.x *= gm.x; dy.y *= gm.y; dy.z *= gm.z; dy.w *= gm.w; }
+      const float4 ov = ldg_f4(o + (long long)s * C + c);
+      dot = fmaf(ov.x, dy.x, fmaf(ov.y, dy.y, fmaf(ov.z, dy.z, fmaf(ov.w, dy.w, dot))));
+      *reinterpret_cast<float4*>(d_o + (long long)s * C + c) = make_float4(g * dy.x, g * dy.y, g * dy.z, g * dy.w);
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) dgate[t * k + j] = dot;
+  }
+  if (dgamma) {
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < k; ++j) {
+        const int s = __ldg(slot_of + t * k + j);
+        if (s < 0) continue;
+        const float g = __ldg(gate + t * k + j);
+        const float4 ov = ldg_f4(o + (long long)s * C + c);
+        y.x = fmaf(g, ov.x, y.x); y.y = fmaf(g, ov.y, y.y); y.z = fmaf(g, ov.z, y.z); y.w = fmaf(g, ov.w, y.w);
+      }
+      const float4 dz = ldg_f4(dout + t * C + c);
+      atomicAdd(dgamma + c, dz.x * rs * y.x); atomicAdd(dgamma + c + 1, dz.y * rs * y.y);
+      atomicAdd(dgamma + c + 2, dz.z * rs * y.z); atomicAdd(dgamma + c + 3, dz.w * rs * y.w);
+    }
+  }
+}
+
 int moe_combine_bwd(const float* dout, const float* o, const int* slot_of, const int* top_idx, const float* gate,
                     const float* gamma, const float* row_scale, float* d_o, float* dgate, float* dgamma, int T, int C,
                     int k, cudaStream_t stream) {
   (void)top_idx;
-  SM3_REQUIRE(dout && o && slot_of && gate && gamma && d_o && dgate && dgamma, SM3_ERR_INVALID_ARG, "moe_combine_bwd: null argument");
-  SM3_REQUIRE(C % 32 == 0 && C <= 1024, SM3_ERR_UNSUPPORTED_SHAPE, "moe_combine_bwd: C=%d", C);
+  SM3_REQUIRE(dout && o && slot_of && gate && d_o && dgate, SM3_ERR_INVALID_ARG, "moe_combine_bwd: null argument");
+  SM3_REQUIRE((gamma == nullptr) == (dgamma == nullptr), SM3_ERR_INVALID_ARG, "moe_combine_bwd: gamma and dgamma go together");
+  static const int vlist[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
+  bool fast = gamma && C % 32 == 0;
+  if (fast) { fast = false; for (int v : vlist) if (C / 32 == v) fast = true; }
+  if (!fast) {
+    SM3_REQUIRE(C % 4 == 0, SM3_ERR_UNSUPPORTED_SHAPE, "moe_combine_bwd: C=%d must be a multiple of 4", C);
+    moe_combine_bwd_generic_kernel<<<(unsigned)(((long long)T * 32 + 255) / 256), 256, 0, stream>>>(
+        dout, o, slot_of, gate, gamma, row_scale, d_o, dgate, dgamma, T, C, k);
+    return check_launch("moe_combine_bwd_generic");
+  }
   long long warps = (long long)num_sms() * 32;
   int tpw = (int)((T + warps - 1) / warps);
   if (tpw < 8) tpw = 8;

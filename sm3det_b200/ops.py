@@ -398,3 +398,106 @@ def scale_rows(x, row_scale=None, col_scale=None, out=None):
         out = torch.empty_like(x)
     _lib.check(lib.sm3_scale_rows(_p(x), _p(row_scale), _p(col_scale), _p(out), rows, Cc, _stream()), 'sm3_scale_rows')
     return out
+
+
+# ---- LSKNet-MoE (BASELINE config 5) ---------------------------------------------------------------------------
+def dwconv(x, wt, bias=None, resid=None, *, ks, dil=1, out=None):
+    """Depthwise ks x ks conv (dilation dil, "same" padding) on NHWC x; wt = taps [ks*ks, C]."""
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.sm3_dwconv_fwd(_p(x), _p(wt), _p(bias), _p(resid), _p(out), N, H, W, Cc, ks, dil, _stream()), 'sm3_dwconv_fwd')
+    return out
+
+
+def dwconv_wgrad(x, dy, dwt, dbias, *, ks, dil=1):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    _lib.check(lib.sm3_dwconv_wgrad(_p(x), _p(dy), _p(dwt), _p(dbias), N, H, W, Cc, ks, dil, _stream()), 'sm3_dwconv_wgrad')
+
+
+def colstat(x, *, rows, Cc, sh1=None, y=None, sh2=None, sc2=None, want_s1=True, want_s2=True):
+    """(s1, s2): s1[c] = sum_r (x-sh1), s2[c] = sum_r (x-sh1) * (y ? (y-sh2)*sc2 : (x-sh1))."""
+    lib = _lib.load()
+    s = torch.zeros((2, Cc), device=x.device, dtype=torch.float32)
+    _lib.check(lib.sm3_colstat(_p(x), _p(sh1), _p(y), _p(sh2), _p(sc2), s[0].data_ptr() if want_s1 else None,
+                               s[1].data_ptr() if want_s2 else None, rows, Cc, _stream()), 'sm3_colstat')
+    return s[0], s[1]
+
+
+def affine(x1, a1=None, x2=None, a2=None, b=None, add=None, out=None):
+    """out = a1[c]*x1 + a2[c]*x2 + b[c] + add  (channels-last; None operands skipped)."""
+    lib = _lib.load()
+    Cc = x1.shape[-1]
+    rows = x1.numel() // Cc
+    if out is None:
+        out = torch.empty_like(x1)
+    _lib.check(lib.sm3_affine(_p(x1), _p(a1), _p(x2), _p(a2), _p(b), _p(add), _p(out), rows, Cc, _stream()), 'sm3_affine')
+    return out
+
+
+def mul(a, b, add=None, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty_like(a)
+    _lib.check(lib.sm3_mul(_p(a), _p(b), _p(add), _p(out), a.numel(), _stream()), 'sm3_mul')
+    return out
+
+
+def lsk_agg(a1, a2, *, T, Ch, want_idx=True):
+    lib = _lib.load()
+    agg = torch.empty((T, 2), device=a1.device, dtype=torch.float32)
+    amax = torch.empty((T,), device=a1.device, dtype=torch.int32) if want_idx else None
+    _lib.check(lib.sm3_lsk_agg(_p(a1), _p(a2), _p(agg), _pi(amax), T, Ch, _stream()), 'sm3_lsk_agg')
+    return agg, amax
+
+
+def conv7_c2(x, w, b, *, N, H, W, act):
+    lib = _lib.load()
+    y = torch.empty((N * H * W, 2), device=x.device, dtype=torch.float32)
+    _lib.check(lib.sm3_conv7_c2(_p(x), _p(w), _p(b), _p(y), N, H, W, act, _stream()), 'sm3_conv7_c2')
+    return y
+
+
+def conv7_c2_wgrad(x, dpre, dw, db, *, N, H, W):
+    lib = _lib.load()
+    _lib.check(lib.sm3_conv7_c2_wgrad(_p(x), _p(dpre), _p(dw), _p(db), N, H, W, _stream()), 'sm3_conv7_c2_wgrad')
+
+
+def lsk_mix(a1, a2, sig, *, T, Ch):
+    lib = _lib.load()
+    out = torch.empty((T, Ch), device=a1.device, dtype=torch.float32)
+    _lib.check(lib.sm3_lsk_mix(_p(a1), _p(a2), _p(sig), _p(out), T, Ch, _stream()), 'sm3_lsk_mix')
+    return out
+
+
+def lsk_mix_bwd_sig(dout, a1, a2, sig, *, T, Ch):
+    lib = _lib.load()
+    dpre = torch.empty((T, 2), device=a1.device, dtype=torch.float32)
+    _lib.check(lib.sm3_lsk_mix_bwd_sig(_p(dout), _p(a1), _p(a2), _p(sig), _p(dpre), T, Ch, _stream()), 'sm3_lsk_mix_bwd_sig')
+    return dpre
+
+
+def lsk_mix_bwd_in(dout, sig, dagg, amax, *, T, Ch):
+    lib = _lib.load()
+    da1 = torch.empty((T, Ch), device=dout.device, dtype=torch.float32)
+    da2 = torch.empty((T, Ch), device=dout.device, dtype=torch.float32)
+    _lib.check(lib.sm3_lsk_mix_bwd_in(_p(dout), _p(sig), _p(dagg), _pi(amax), _p(da1), _p(da2), T, Ch, _stream()),
+               'sm3_lsk_mix_bwd_in')
+    return da1, da2
+
+
+def im2col(x, *, N, H, W, Cin, ks, stride, pad, Kp, nchw):
+    lib = _lib.load()
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=torch.float32)
+    _lib.check(lib.sm3_im2col(_p(x), _p(col), N, H, W, Cin, ks, stride, pad, Kp, 1 if nchw else 0, _stream()), 'sm3_im2col')
+    return col, Ho, Wo
+
+
+def col2im(dcol, *, N, H, W, Cin, ks, stride, pad, Kp):
+    lib = _lib.load()
+    dx = torch.empty((N, H, W, Cin), device=dcol.device, dtype=torch.float32)
+    _lib.check(lib.sm3_col2im(_p(dcol), _p(dx), N, H, W, Cin, ks, stride, pad, Kp, _stream()), 'sm3_col2im')
+    return dx

@@ -1,0 +1,233 @@
+"""GPU parity of the LSKNet-MoE path (BASELINE config 5): each new C-ABI kernel against plain torch fp32 on the CPU,
+and the whole backbone (forward, routing, gate loss, every parameter gradient, BatchNorm running statistics) against the
+reference-generated goldens / the CPU oracle.  Tolerance: 1e-3 max-norm relative (north-star), router indices exact."""
+import glob
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.cases import LSK_CASES, lsk_injections, upstream_grads
+from oracle.lsk_moe_oracle import LskConfig, lsk_backbone_forward, lsk_param_shapes
+from sm3det_b200.synth import make_images, make_state_dict
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from sm3det_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize('ks,dil', [(3, 1), (5, 1), (7, 3)])
+@pytest.mark.parametrize('C,H,W', [(32, 8, 8), (64, 19, 33), (128, 16, 16)])
+def test_dwconv_generic(ops, ks, dil, C, H, W):
+    g = torch.Generator().manual_seed(C + H + ks)
+    N = 2
+    x = torch.randn(N, C, H, W, generator=g, requires_grad=True)
+    w = (torch.randn(C, 1, ks, ks, generator=g) * 0.2).requires_grad_(True)
+    b = (torch.randn(C, generator=g) * 0.1).requires_grad_(True)
+    y = F.conv2d(x, w, b, padding=dil * (ks // 2), dilation=dil, groups=C)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    xd = x.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    wt = w.detach().reshape(C, -1).t().contiguous().cuda()
+    yd = ops.dwconv(xd, wt, b.detach().cuda(), ks=ks, dil=dil)
+    assert rel(yd.permute(0, 3, 1, 2), y) < 1e-5
+    dyd = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    wf = w.detach().flip(2, 3).reshape(C, -1).t().contiguous().cuda()
+    dxd = ops.dwconv(dyd, wf, None, ks=ks, dil=dil)
+    assert rel(dxd.permute(0, 3, 1, 2), x.grad) < 1e-5
+    dwt = torch.zeros(ks * ks, C, device='cuda'); db = torch.zeros(C, device='cuda')
+    ops.dwconv_wgrad(xd, dyd, dwt, db, ks=ks, dil=dil)
+    assert rel(dwt.t().reshape(C, 1, ks, ks), w.grad) < 2e-5 and rel(db, b.grad) < 2e-5
+
+
+@pytest.mark.parametrize('C,rows', [(64, 1000), (320, 77), (2048, 513)])
+def test_colstat_affine_batchnorm(ops, C, rows):
+    from sm3det_b200.lsk_functional import BatchNormFn
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(rows, C, generator=g) * 1.7 + 0.6)
+    w = torch.rand(C, generator=g) + 0.5; b = torch.randn(C, generator=g) * 0.1
+    rm = torch.randn(C, generator=g) * 0.1; rv = torch.rand(C, generator=g) + 0.5
+    dy = torch.randn(rows, C, generator=g)
+    for train in (True, False):
+        xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+        rm_c, rv_c = rm.clone(), rv.clone()
+        ref = F.batch_norm(xr.t().reshape(1, C, rows), rm_c, rv_c, wr, br, train, 0.1, 1e-5).reshape(C, rows).t()
+        ref.backward(dy)
+        xg = x.cuda().requires_grad_(True); wg = w.cuda().requires_grad_(True); bg = b.cuda().requires_grad_(True)
+        rm_g, rv_g = rm.cuda(), rv.cuda()
+        y = BatchNormFn.apply(xg.view(1, 1, rows, C), wg, bg, rm_g, rv_g, train, 0.1, 1e-5, False)
+        y.backward(dy.cuda().view(1, 1, rows, C))
+        assert rel(y.view(rows, C), ref) < 2e-5
+        assert rel(xg.grad, xr.grad) < 5e-5 and rel(wg.grad, wr.grad) < 5e-5 and rel(bg.grad, br.grad) < 5e-5
+        assert rel(rm_g, rm_c) < 1e-5 and rel(rv_g, rv_c) < 1e-5
+    s1, s2 = ops.colstat(x.cuda(), rows=rows, Cc=C)
+    assert rel(s1, x.sum(0)) < 1e-5 and rel(s2, (x * x).sum(0)) < 1e-5
+    out = ops.affine(x.cuda(), a1=w.cuda(), x2=dy.cuda(), a2=b.cuda(), b=rm.cuda(), add=x.cuda())
+    assert rel(out, x * w + dy * b + rm + x) < 1e-6
+
+
+@pytest.mark.parametrize('Ch,H,W', [(32, 8, 8), (64, 13, 21), (160, 16, 16)])
+def test_lsk_select(ops, Ch, H, W):
+    from sm3det_b200.lsk_functional import LSKSelectFn
+    g = torch.Generator().manual_seed(Ch + H)
+    N = 2
+    a1 = torch.randn(N, Ch, H, W, generator=g, requires_grad=True)
+    a2 = torch.randn(N, Ch, H, W, generator=g, requires_grad=True)
+    wsq = (torch.randn(2, 2, 7, 7, generator=g) * 0.2).requires_grad_(True)
+    bsq = (torch.randn(2, generator=g) * 0.1).requires_grad_(True)
+    attn = torch.cat([a1, a2], 1)
+    agg = torch.cat([attn.mean(1, keepdim=True), attn.max(1, keepdim=True)[0]], 1)
+    sig = F.conv2d(agg, wsq, bsq, padding=3).sigmoid()
+    ref = a1 * sig[:, 0:1] + a2 * sig[:, 1:2]
+    d = torch.randn(ref.shape, generator=g)
+    ref.backward(d)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    a1g, a2g = nhwc(a1).requires_grad_(True), nhwc(a2).requires_grad_(True)
+    wg, bg = wsq.detach().cuda().requires_grad_(True), bsq.detach().cuda().requires_grad_(True)
+    out = LSKSelectFn.apply(a1g, a2g, wg, bg)
+    out.backward(nhwc(d))
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-5
+    assert rel(a1g.grad.permute(0, 3, 1, 2), a1.grad) < 2e-5 and rel(a2g.grad.permute(0, 3, 1, 2), a2.grad) < 2e-5
+    assert rel(wg.grad, wsq.grad) < 5e-5 and rel(bg.grad, bsq.grad) < 5e-5
+
+
+@pytest.mark.parametrize('Ci,Co,ks,stride,nchw', [(3, 64, 7, 4, True), (64, 128, 3, 2, False), (128, 320, 3, 2, False)])
+def test_patch_embed(ops, Ci, Co, ks, stride, nchw):
+    from sm3det_b200.lsk_functional import PatchEmbedFn
+    g = torch.Generator().manual_seed(Ci + Co)
+    N, H, W = 2, 32, 48
+    x = torch.randn(N, Ci, H, W, generator=g, requires_grad=True)
+    w = (torch.randn(Co, Ci, ks, ks, generator=g) / (Ci * ks * ks) ** 0.5).requires_grad_(True)
+    b = (torch.randn(Co, generator=g) * 0.1).requires_grad_(True)
+    ref = F.conv2d(x, w, b, stride=stride, padding=ks // 2)
+    d = torch.randn(ref.shape, generator=g)
+    ref.backward(d)
+    xin = x.detach().cuda() if nchw else x.detach().permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+    wg, bg = w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+    y = PatchEmbedFn.apply(xin, wg, bg, stride, nchw)
+    y.backward(d.permute(0, 2, 3, 1).contiguous().cuda())
+    assert rel(y.permute(0, 3, 1, 2), ref) < 5e-5
+    assert rel(wg.grad, w.grad) < 1e-4 and rel(bg.grad, b.grad) < 1e-4
+    if not nchw:
+        assert rel(xin.grad.permute(0, 3, 1, 2), x.grad) < 1e-4
+
+
+def test_linear_gelu_mul_axpy(ops):
+    from sm3det_b200.lsk_functional import AxpyFn, GeluFn, LinearFn, MulFn
+    g = torch.Generator().manual_seed(3)
+    T, K, N = 300, 64, 160
+    x = torch.randn(T, K, generator=g, requires_grad=True)
+    w = (torch.randn(N, K, 1, 1, generator=g) / 8).requires_grad_(True)
+    b = (torch.randn(N, generator=g) * 0.1).requires_grad_(True)
+    ls = (torch.rand(N, generator=g) + 0.1).requires_grad_(True)
+    sc = torch.randn(T, N, generator=g, requires_grad=True)
+    rs = (torch.rand(T, generator=g) > 0.3).float() / 0.7
+    h = F.gelu(F.linear(x, w.view(N, K), b))
+    ref = sc + rs[:, None] * ls * (F.gelu(h) * sc)
+    d = torch.randn(T, N, generator=g)
+    ref.backward(d)
+    xg, wg, bg, lg, sg = (t.detach().cuda().requires_grad_(True) for t in (x, w, b, ls, sc))
+    hg = LinearFn.apply(xg, wg, bg, True)
+    out = AxpyFn.apply(MulFn.apply(GeluFn.apply(hg), sg), sg, lg, rs.cuda())
+    out.backward(d.cuda())
+    assert rel(out, ref) < 5e-5
+    for a, r, name in ((xg, x, 'x'), (wg, w, 'w'), (bg, b, 'b'), (lg, ls, 'ls'), (sg, sc, 'sc')):
+        assert rel(a.grad, r.grad) < 2e-4, name
+
+
+# ------------------------------------------------------------------------------------------------
+def build(kw, seed=0):
+    from sm3det_b200 import LSKNet_moe_MultiInput
+    cfg = LskConfig(**kw)
+    sd = make_state_dict(lsk_param_shapes(cfg), seed, True)
+    net = LSKNet_moe_MultiInput(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
+    net.load_state_dict(sd, strict=True)
+    return cfg, sd, net.cuda()
+
+
+def inject(net, cfg, noise, drops):
+    ni = iter(noise or [])
+    di = iter(drops or [])
+    for i in range(cfg.num_stages):
+        for blk in getattr(net, f'block{i + 1}'):
+            for fc in (blk.mlp.fc1, blk.mlp.fc2):
+                if hasattr(fc, 'experts') and noise is not None:
+                    fc._injected_noise = next(ni)
+            if drops is not None:
+                m1, m2 = next(di), next(di)
+                blk.mlp._injected_drop_masks = [m1.permute(0, 2, 3, 1).contiguous(), m2.permute(0, 2, 3, 1).contiguous()]
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'lsk_*.pt'))), ids=lambda p: os.path.basename(p)[:-3])
+def test_lsk_backbone_matches_reference_golden(path):
+    gold = torch.load(path, weights_only=False)
+    cfg, sd, net = build(gold['kw'])
+    n, h, w = gold['img']
+    x = make_images(n, h, w, seed=1234).cuda()
+    train = gold['mode'] != 'eval'
+    net.train(train)
+    noise, drops = lsk_injections(cfg, gold)
+    inject(net, cfg, noise, drops)
+    rec = []
+    res = net(x, record=rec)
+    has_loss = 'gate_loss' in gold
+    outs, loss = res if has_loss else (res, None)
+    flips = 0
+    for r, g in zip(rec, gold['moe']):
+        flips += int((r['top_idx'].cpu().long().sort(1).values != g['top_idx'].long().sort(1).values).any(1).sum())
+    errs = [rel(o, g) for o, g in zip(outs, gold['outs'])]
+    print(os.path.basename(path), 'rel errs', errs, 'flips', flips)
+    assert flips == 0, 'router indices must be bit-exact on these fixtures'
+    assert max(errs) < TOL
+    if has_loss:
+        assert abs(loss.item() - gold['gate_loss'].item()) <= 1e-4 * abs(gold['gate_loss'].item()) + 1e-8
+    if not train:
+        return
+    ups = upstream_grads([o.cpu() for o in outs])
+    (sum((o * g.cuda()).sum() for o, g in zip(outs, ups)) + (loss if has_loss else 0.0)).backward()
+    worst = ('', 0.0)
+    for name, p in net.named_parameters():
+        gg = gold['grads'].get(name)
+        if gg is None:
+            continue
+        got = p.grad.detach().float().cpu().reshape(-1)
+        if 'full' in gg:
+            want = gg['full']
+        else:
+            want, got = gg['sample'], got[gg['idx']]
+        scale = (gg['l2'] / (p.numel() ** 0.5)) if 'l2' in gg else want.abs().max().item()
+        e = ((got - want).abs().max() / (max(want.abs().max().item(), scale) + 1e-30)).item()
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < 3e-3, (name, e)
+    print('worst grad', worst)
+    new_sd = net.state_dict()
+    for k, v in gold['bn'].items():
+        assert rel(new_sd[k], v) < 1e-4, k
+
+
+def test_lsk_eval_list_input_and_plain_class():
+    """list input is concatenated on the batch (lsk_moe.py:751-754); LSKNet_moe (plain) returns the same maps."""
+    spec = LSK_CASES['lsk_mini_moe_e4k2_eval']
+    cfg, sd, net = build(spec['kw'])
+    net.eval()
+    x = make_images(2, 64, 64, seed=9)
+    with torch.no_grad():
+        o1, l1 = net(x.cuda())
+        o2, l2 = net([x[:1].cuda(), x[1:].cuda()], datasets=['a', 'b'])
+        ref, rl = lsk_backbone_forward(sd, cfg, x, train=False)
+    assert all(torch.equal(a, b) for a, b in zip(o1, o2))
+    assert max(rel(a, b) for a, b in zip(o1, ref)) < TOL and abs(l1.item() - rl.item()) < 1e-4 * abs(rl.item())
+    assert all(o.is_contiguous() and o.shape[0] == 2 for o in o1)
