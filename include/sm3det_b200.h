@@ -249,7 +249,7 @@ int sm3_lsk_mix_bwd_in(const float* dout, const float* sig, const float* dagg, c
 int sm3_im2col(const float* x, float* col, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
                int32_t pad, int32_t Kp, int32_t nchw, void* stream);
 int sm3_col2im(const float* dcol, float* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
-               int32_t pad, int32_t Kp, void* stream);
+               int32_t pad, int32_t Kp, int32_t nchw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,7 +98,7 @@ SIGNATURES = {
     'sm3_lsk_mix_bwd_sig': [_P, _P, _P, _P, _P, _I64, _I32, _P],
     'sm3_lsk_mix_bwd_in': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     'sm3_im2col': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
-    'sm3_col2im': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    'sm3_col2im': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 _RESTYPES = {'sm3_last_error': C.c_char_p, 'sm3_gemm_packed_elems': C.c_int64, 'sm3_gemm_packed_act_elems': C.c_int64}
 

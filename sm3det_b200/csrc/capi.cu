@@ -195,8 +195,8 @@ int sm3_im2col(const float* x, float* col, int32_t N, int32_t H, int32_t W, int3
   return im2col(x, col, N, H, W, Cin, ks, stride, pad, Kp, nchw, S(stream));
 }
 int sm3_col2im(const float* dcol, float* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
-               int32_t pad, int32_t Kp, void* stream) {
-  return col2im(dcol, dx, N, H, W, Cin, ks, stride, pad, Kp, S(stream));
+               int32_t pad, int32_t Kp, int32_t nchw, void* stream) {
+  return col2im(dcol, dx, N, H, W, Cin, ks, stride, pad, Kp, nchw, S(stream));
 }
 
 }  // extern "C"

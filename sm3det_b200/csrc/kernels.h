@@ -144,6 +144,7 @@ int lsk_mix_bwd_in(const float* dout, const float* sig, const float* dagg, const
                    long long T, int Ch, cudaStream_t stream);
 int im2col(const float* x, float* col, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, int nchw,
            cudaStream_t stream);
-int col2im(const float* dcol, float* dx, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, cudaStream_t stream);
+int col2im(const float* dcol, float* dx, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, int nchw,
+           cudaStream_t stream);
 
 }  // namespace sm3

@@ -538,15 +538,21 @@ int im2col(const float* x, float* col, int N, int H, int W, int Cin, int ks, int
 }
 
 // dx[n,h,w,ci] = sum over taps (kh,kw) with (h + pad - kh) % stride == 0 of dcol[t_out, (kh*ks+kw)*Cin + ci]   (gather form)
+// nchw = 1 writes dx as [N,Cin,H,W] (the previous stage's returned feature map is the conv input, lsk_moe.py:555-557).
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int N, int H, int W,
-                                                    int Cin, int ks, int stride, int pad, int Ho, int Wo, int Kp,
+                                                    int Cin, int ks, int stride, int pad, int Ho, int Wo, int Kp, int nchw,
                                                     long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int Q = Cin >> 2;
-  const int c = (int)(i % Q) * 4;
-  const long long p = i / Q;
-  const int w = (int)(p % W); const long long r = p / W; const int h = (int)(r % H); const long long n = r / H;
+  int c, w, h; long long n;
+  if (nchw) {
+    w = (int)(i % W); long long r = i / W; h = (int)(r % H); r /= H; c = (int)(r % Cin); n = r / Cin;
+  } else {
+    const int Q = Cin >> 2;
+    c = (int)(i % Q) * 4;
+    const long long p = i / Q;
+    w = (int)(p % W); const long long r = p / W; h = (int)(r % H); n = r / H;
+  }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int kh = 0; kh < ks; ++kh) {
     const int hn = h + pad - kh;
@@ -558,18 +564,21 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
       if (wn < 0 || wn % stride) continue;
       const int wo = wn / stride;
       if (wo >= Wo) continue;
-      const float4 v = ldg_f4(dcol + ((n * Ho + ho) * Wo + wo) * Kp + (kh * ks + kw) * Cin + c);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      const float* src = dcol + ((n * Ho + ho) * Wo + wo) * Kp + (kh * ks + kw) * Cin + c;
+      if (nchw) { acc.x += __ldg(src); }
+      else { const float4 v = ldg_f4(src); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
     }
   }
-  *reinterpret_cast<float4*>(dx + p * Cin + c) = acc;
+  if (nchw) dx[i] = acc.x;
+  else *reinterpret_cast<float4*>(dx + (((n * H + h) * W + w) * Cin) + c) = acc;
 }
 
-int col2im(const float* dcol, float* dx, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, cudaStream_t stream) {
-  SM3_REQUIRE(dcol && dx && Cin % 4 == 0 && Kp % 4 == 0, SM3_ERR_INVALID_ARG, "col2im: bad argument (Cin must be a multiple of 4)");
+int col2im(const float* dcol, float* dx, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, int nchw,
+           cudaStream_t stream) {
+  SM3_REQUIRE(dcol && dx && (nchw || Cin % 4 == 0) && Kp % 4 == 0, SM3_ERR_INVALID_ARG, "col2im: bad argument (NHWC needs Cin % 4 == 0)");
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
-  const long long total = (long long)N * H * W * (Cin / 4);
-  col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dcol, dx, N, H, W, Cin, ks, stride, pad, Ho, Wo, Kp, total);
+  const long long total = nchw ? (long long)N * Cin * H * W : (long long)N * H * W * (Cin / 4);
+  col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dcol, dx, N, H, W, Cin, ks, stride, pad, Ho, Wo, Kp, nchw, total);
   return check_launch("col2im_kernel");
 }
 

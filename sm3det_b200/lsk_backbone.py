@@ -331,13 +331,14 @@ class LSKNet_moe(BaseModule):
             if gate_loss is not None:
                 gate_losses.append(gate_loss)
         nl = getattr(self, f'norm{i + 1}')
-        outs.append(Fn.OutNormFn.apply(x, nl.weight, nl.bias, nl.eps))    # LayerNorm over C + NHWC->NCHW (:555-557)
-        return x
+        # LayerNorm over C + NHWC->NCHW (:555-557); the NORMED map is both the returned feature and the next stage's input
+        outs.append(Fn.OutNormFn.apply(x, nl.weight, nl.bias, nl.eps))
+        return outs[-1]
 
     def forward_features(self, x, record=None):
         outs, gate_losses = [], []
         for i in range(self.num_stages):
-            x = getattr(self, f'patch_embed{i + 1}')(x, nchw=(i == 0))
+            x = getattr(self, f'patch_embed{i + 1}')(x, nchw=True)
             x = self._stage_tail(i, x, outs, gate_losses, record)
         if len(gate_losses) > 0:
             return tuple(outs), sum(gate_losses) / len(gate_losses)
@@ -378,7 +379,7 @@ class LSKNet_moe_MultiInput(LSKNet_moe):
         outs, gate_losses = [], []
         for i in range(self.num_stages):
             pe = getattr(self, f'patch_embed{i + 1}')
-            x = _bn(pe, x) if i == 0 else pe(x, nchw=False)
+            x = _bn(pe, x) if i == 0 else pe(x, nchw=True)
             x = self._stage_tail(i, x, outs, gate_losses, record)
         if len(gate_losses) > 0:
             return tuple(outs), sum(gate_losses) / len(gate_losses)

@@ -270,10 +270,8 @@ class PatchEmbedFn(Function):
         ops.colsum(dy2, db, rows=T, Cc=Co)
         dx = None
         if ctx.needs_input_grad[0]:
-            if nchw:
-                raise NotImplementedError('sm3det_b200: gradient w.r.t. the NCHW network input is not implemented')
             dcol = ops.linear_dgrad(dy2, w2)
-            dx = ops.col2im(dcol, N=N, H=H, W=W, Cin=Ci, ks=ks, stride=stride, pad=ks // 2, Kp=Kp)
+            dx = ops.col2im(dcol, N=N, H=H, W=W, Cin=Ci, ks=ks, stride=stride, pad=ks // 2, Kp=Kp, nchw=nchw)
         dw = dw2[:, :K].reshape(Co, ks, ks, Ci).permute(0, 3, 1, 2).contiguous()
         return dx, dw, db, None, None
 

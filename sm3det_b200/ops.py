@@ -496,8 +496,8 @@ def im2col(x, *, N, H, W, Cin, ks, stride, pad, Kp, nchw):
     return col, Ho, Wo
 
 
-def col2im(dcol, *, N, H, W, Cin, ks, stride, pad, Kp):
+def col2im(dcol, *, N, H, W, Cin, ks, stride, pad, Kp, nchw=False):
     lib = _lib.load()
-    dx = torch.empty((N, H, W, Cin), device=dcol.device, dtype=torch.float32)
-    _lib.check(lib.sm3_col2im(_p(dcol), _p(dx), N, H, W, Cin, ks, stride, pad, Kp, _stream()), 'sm3_col2im')
+    dx = torch.empty((N, Cin, H, W) if nchw else (N, H, W, Cin), device=dcol.device, dtype=torch.float32)
+    _lib.check(lib.sm3_col2im(_p(dcol), _p(dx), N, H, W, Cin, ks, stride, pad, Kp, 1 if nchw else 0, _stream()), 'sm3_col2im')
     return dx

@@ -103,7 +103,7 @@ def test_lsk_select(ops, Ch, H, W):
     assert rel(wg.grad, wsq.grad) < 5e-5 and rel(bg.grad, bsq.grad) < 5e-5
 
 
-@pytest.mark.parametrize('Ci,Co,ks,stride,nchw', [(3, 64, 7, 4, True), (64, 128, 3, 2, False), (128, 320, 3, 2, False)])
+@pytest.mark.parametrize('Ci,Co,ks,stride,nchw', [(3, 64, 7, 4, True), (64, 128, 3, 2, False), (128, 320, 3, 2, False), (64, 64, 3, 2, True)])
 def test_patch_embed(ops, Ci, Co, ks, stride, nchw):
     from sm3det_b200.lsk_functional import PatchEmbedFn
     g = torch.Generator().manual_seed(Ci + Co)
@@ -114,14 +114,14 @@ def test_patch_embed(ops, Ci, Co, ks, stride, nchw):
     ref = F.conv2d(x, w, b, stride=stride, padding=ks // 2)
     d = torch.randn(ref.shape, generator=g)
     ref.backward(d)
-    xin = x.detach().cuda() if nchw else x.detach().permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+    xin = (x.detach().cuda() if nchw else x.detach().permute(0, 2, 3, 1).contiguous().cuda()).requires_grad_(Ci != 3)
     wg, bg = w.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
     y = PatchEmbedFn.apply(xin, wg, bg, stride, nchw)
     y.backward(d.permute(0, 2, 3, 1).contiguous().cuda())
     assert rel(y.permute(0, 3, 1, 2), ref) < 5e-5
     assert rel(wg.grad, w.grad) < 1e-4 and rel(bg.grad, b.grad) < 1e-4
-    if not nchw:
-        assert rel(xin.grad.permute(0, 3, 1, 2), x.grad) < 1e-4
+    if Ci != 3:
+        assert rel(xin.grad if nchw else xin.grad.permute(0, 3, 1, 2), x.grad) < 1e-4
 
 
 def test_linear_gelu_mul_axpy(ops):
@@ -197,7 +197,7 @@ def test_lsk_backbone_matches_reference_golden(path):
         return
     ups = upstream_grads([o.cpu() for o in outs])
     (sum((o * g.cuda()).sum() for o, g in zip(outs, ups)) + (loss if has_loss else 0.0)).backward()
-    worst = ('', 0.0)
+    bad = []
     for name, p in net.named_parameters():
         gg = gold['grads'].get(name)
         if gg is None:
@@ -208,11 +208,17 @@ def test_lsk_backbone_matches_reference_golden(path):
         else:
             want, got = gg['sample'], got[gg['idx']]
         scale = (gg['l2'] / (p.numel() ** 0.5)) if 'l2' in gg else want.abs().max().item()
-        e = ((got - want).abs().max() / (max(want.abs().max().item(), scale) + 1e-30)).item()
-        if e > worst[1]:
-            worst = (name, e)
-        assert e < 3e-3, (name, e)
-    print('worst grad', worst)
+        # floor 1e-5: conv biases feeding a training-mode BatchNorm have an exactly-zero true gradient (fp32 noise ~1e-8)
+        e = ((got - want).abs().max() / max(want.abs().max().item(), scale, 1e-5)).item()
+        if name.endswith('proj.bias') or name == 'dataset_stems.single.bias':
+            # a conv bias in front of a training-mode BatchNorm: the true gradient is exactly 0, both sides hold fp32 noise
+            assert (got - want).abs().max().item() < 1e-5, name
+            continue
+        tol = 1e-2 if name.endswith('w_gate.temperature') else 3e-3     # scalar sum over all tokens with heavy cancellation
+        bad.append((e / tol, e, name))
+    bad.sort(reverse=True)
+    print('worst grads', bad[:5])
+    assert bad[0][0] < 1.0, bad[:8]
     new_sd = net.state_dict()
     for k, v in gold['bn'].items():
         assert rel(new_sd[k], v) < 1e-4, k
