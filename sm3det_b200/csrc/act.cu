@@ -31,6 +31,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 // grid: (column-chunk groups of 32, row bands); block 256 = 32 chunk lanes x 8 row lanes
+template <int MODE, bool CS>
 __global__ void __launch_bounds__(256) act_pack_kernel(const ActPackArgs a, int rows_per_band) {
   __shared__ float s_cs[8][32 * 8 + 8];
   const int cl = threadIdx.x & 31, rlane = threadIdx.x >> 5;
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(256) act_pack_kernel(const ActPackArgs a, int 
     if (row_ok) {
       const float4 h0 = ldg_f4(a.h + r * a.W + col), h1 = ldg_f4(a.h + r * a.W + col + 4);
       const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-      if (a.mode == 0) {
+      if (MODE == 0) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = gelu_fast(hv[e]);
-      } else if (a.mode == 1) {
+      } else if (MODE == 1) {
         const float4 d0 = ldg_f4(a.da + r * a.W + col), d1 = ldg_f4(a.da + r * a.W + col + 4);
         const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) act_pack_kernel(const ActPackArgs a, int 
         for (int e = 0; e < 8; ++e) y[e] = hv[e];
       }
     }
-    if (a.colsum) {
+    if (CS) {
       // per-group sums (expert bias gradients): rows of one 128-row tile share a group; flush when it changes
       const int g = (a.tile_group && r < live) ? __ldg(a.tile_group + (int)(r >> 7)) : 0;
       if (g != cur_group) {
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) act_pack_kernel(const ActPackArgs a, int 
       *reinterpret_cast<uint4*>(img + pb_mn + o) = lo;
     }
   }
-  if (a.colsum) {
+  if (CS) {
     // combine the 8 row lanes of the block (same group at the end of the band in all but pathological cases:
     // each lane flushes its own group, so correctness does not depend on it)
     if (cur_group >= 0 && col_ok) {
@@ -149,7 +150,16 @@ int act_pack(const ActPackArgs& a, cudaStream_t stream) {
   rpb = (rpb + 127) / 128 * 128;                   // whole tiles per band keeps a band inside few groups
   bands = (R_pad + rpb - 1) / rpb;
   dim3 grid((unsigned)gx, (unsigned)bands);
-  act_pack_kernel<<<grid, 256, 0, stream>>>(a, (int)rpb);
+  const bool cs = a.colsum != nullptr;
+#define SM3_ACT_LAUNCH(M)                                                          \
+  do {                                                                             \
+    if (cs) act_pack_kernel<M, true><<<grid, 256, 0, stream>>>(a, (int)rpb);       \
+    else act_pack_kernel<M, false><<<grid, 256, 0, stream>>>(a, (int)rpb);         \
+  } while (0)
+  if (a.mode == 0) SM3_ACT_LAUNCH(0);
+  else if (a.mode == 1) SM3_ACT_LAUNCH(1);
+  else SM3_ACT_LAUNCH(2);
+#undef SM3_ACT_LAUNCH
   return check_launch("act_pack_kernel");
 }
 

@@ -55,7 +55,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // between Phi and the density term of the derivative.
 __device__ __forceinline__ void phi_parts(float x, float& Phi, float& e) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;                                  // MUFU.RCP (1 ulp): __frcp_rn costs a Newton step + a slow-path call per element
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);

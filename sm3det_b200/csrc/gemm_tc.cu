@@ -229,6 +229,16 @@ int launch(Params p, cudaStream_t stream) {
     const long long b_ext = packed ? 0 : b_mn ? (long long)(p.b_k_index ? 1 : p.K) * p.b_sk + p.N : (long long)p.N * p.b_smn;
     SM3_REQUIRE(a_ext < (1LL << 32) && b_ext < (1LL << 32), SM3_ERR_UNSUPPORTED_SHAPE, "gemm: operand larger than 2^32 elements");
   }
+  // smem ring: 4 stages of 48 KB when a producer warp group writes the stage; fully packed operands only need
+  // 16 KB (A) + the two B planes per stage, so narrow tiles get a deeper ring (more bytes in flight per SM -- the
+  // narrow GEMMs of stages 0/1 are HBM-bound streams of the packed A image).
+  p.nstages = STAGES; p.stage_bytes = STAGE_BYTES;
+  if (apacked) {
+    const unsigned sb = (16384u + 2u * plane_bytes(p.BN, b_mn) + 1023u) & ~1023u;
+    int ns = (int)((unsigned)(STAGES * STAGE_BYTES) / sb);
+    if (ns > MAX_STAGES) ns = MAX_STAGES;
+    if (ns >= STAGES) { p.nstages = ns; p.stage_bytes = sb; }
+  }
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   if (grid < 1) grid = 1;

@@ -34,7 +34,8 @@ constexpr uint32_t OFF_A_LO = 8192;
 constexpr uint32_t OFF_B_HI = 16384;
 constexpr uint32_t OFF_B_LO = 32768;
 constexpr uint32_t STAGE_BYTES = 49152;
-constexpr uint32_t BAR_BYTES = 128;
+constexpr int MAX_STAGES = 8;             // fully packed kernels use as many stages as fit (narrow tiles need less smem per stage)
+constexpr uint32_t BAR_BYTES = 256;
 constexpr int EPI_CW = 16;                                          // accumulator columns per epilogue pass
 constexpr uint32_t EPI_STAGE_ROW_FLOATS = EPI_CW + 4;               // + 4 pad: conflict-free 16-byte accesses
 constexpr uint32_t EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW_FLOATS * 4;  // per epilogue warp
@@ -83,6 +84,7 @@ struct Params {
   const float* col_scale; const float* row_scale;
   const float* resid; long long ld_resid;
   float* colsum; long long colsum_group_stride;
+  int nstages; unsigned stage_bytes;   // filled by launch(): smem ring depth / stride (4 x 48 KB unless fully packed)
   int debug;   // perf experiments only: bit0 skip A loads+stores, bit1 skip the packed-B bulk copy, bit2 skip MMAs
 };
 
@@ -275,15 +277,17 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
-  auto tfull_bar = [&](int a) { return bar_base + 64u + 8u * a; };
-  auto tempty_bar = [&](int a) { return bar_base + 80u + 8u * a; };
-  const uint32_t tmem_slot = bar_base + 96u;
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 160u;
+  const int NST = p.nstages;
+  const uint32_t STB = p.stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), A_PACKED ? 1 : NUM_PROD_WARPS + (B_PACKED ? 1 : 0)); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), A_PACKED ? 1 : NUM_PROD_WARPS + (B_PACKED ? 1 : 0)); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), A_PACKED ? MAX_EPI_WARPS : NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -443,7 +447,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sb = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = smem_base + stage * STB;
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
             const uint64_t ahi = make_smem_desc(sb + OFF_A_HI + j * a_kstep, A_MN);
@@ -459,7 +463,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           }
           tc_commit(empty_bar(stage));
           if (kb == nkb - 1) tc_commit(tfull_bar(acc));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
@@ -482,13 +486,13 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
                                 ((long long)(tl.n0 / p.BN) * kblocks + kb0) * b_bytes;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sb = smem_base + stage * STAGE_BYTES;
+            const uint32_t sb = smem_base + stage * STB;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)), "r"(a_bytes + b_bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(sb + OFF_A_HI), "l"(srcA + (long long)kb * a_bytes), "r"(a_bytes), "r"(full_bar(stage)) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(sb + OFF_B_HI), "l"(srcB + (long long)kb * b_bytes), "r"(b_bytes), "r"(full_bar(stage)) : "memory");
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -646,16 +650,16 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
         const uint16_t* src = pub_src + (long long)pub_kb * (2LL * p.BN * BK);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_base + stage * STAGE_BYTES + OFF_B_HI), "l"(src), "r"(bytes), "r"(full_bar(stage)) : "memory");
+                     ::"r"(smem_base + stage * STB + OFF_B_HI), "l"(src), "r"(bytes), "r"(full_bar(stage)) : "memory");
       }
       if (p.debug & 8) {            // loads only: consume the registers without the split / stores
 #pragma unroll
         for (int i = 0; i < MU; ++i) asm volatile("" ::"f"(r[i][0].x), "f"(r[i][1].w));
-      } else if (!(p.debug & 1)) store_kb(r, smem_base + stage * STAGE_BYTES);
+      } else if (!(p.debug & 1)) store_kb(r, smem_base + stage * STB);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
     };
 
     // PF k-blocks of global loads are kept in flight per thread (register ring, statically indexed): one

@@ -119,62 +119,123 @@ int layernorm_fwd(const float* x, const float* w, const float* b, float* y, floa
 //   xhat = (x-mean)*rstd ; g = dy*w ; dx = rstd*(g - mean_c(g) - xhat*mean_c(g*xhat))
 //   dw += sum_t dy*xhat ; db += sum_t dy     (per-block partials in registers -> atomics per block)
 // If dx_accum != 0 the result is added to dx (residual branches meeting at one tensor).
+// One token of the backward: d[] = dy for this lane's channels.  Accumulates the parameter partials, writes dx.
+template <int V>
+__device__ __forceinline__ void ln_bwd_token(const float (&d)[V], const float* __restrict__ xr, float mean, float rstd,
+                                             const float (&wv)[V], float (&adw)[V], float (&adb)[V], float* __restrict__ dxr,
+                                             int C, int lane, int dx_accum) {
+  float g[V], xh[V];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    xh[i] = (__ldg(xr + lane + 32 * i) - mean) * rstd;
+    adw[i] = fmaf(d[i], xh[i], adw[i]);
+    adb[i] += d[i];
+    g[i] = d[i] * wv[i];
+    s1 += g[i];
+    s2 = fmaf(g[i], xh[i], s2);
+  }
+  s1 = warp_sum(s1) / (float)C;
+  s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = lane + 32 * i;
+    const float r = rstd * (g[i] - s1 - xh[i] * s2);
+    dxr[c] = dx_accum ? dxr[c] + r : r;
+  }
+}
+
+// parameter partials of the 8 warps of a block -> shared memory -> one atomic per channel per block
+template <int V>
+__device__ __forceinline__ void ln_bwd_flush(const float (&adw)[V], const float (&adb)[V], float* red /*[2][8][C]*/,
+                                             float* __restrict__ dw, float* __restrict__ db, int C, int warp, int lane) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    red[warp * C + lane + 32 * i] = adw[i];
+    red[(8 + warp) * C + lane + 32 * i] = adb[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    const int which = c / C, cc = c % C;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[(which * 8 + w) * C + cc];
+    atomicAdd((which ? db : dw) + cc, t);
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                     const float* __restrict__ stats, const float* __restrict__ w,
                                                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
                                                     int T, int C, int in_mode, int H, int W, int dx_accum,
                                                     int tokens_per_warp) {
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float red[];                   // [2][8][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * 8 + warp;
   float adw[V], adb[V], wv[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { adw[i] = 0.f; adb[i] = 0.f; wv[i] = __ldg(w + lane + 32 * i); }
   const long long tb = (long long)gwarp * tokens_per_warp;
+  const int HW = H * W;
   for (int k = 0; k < tokens_per_warp; ++k) {
     const long long t = tb + k;
     if (t >= T) break;
     const float mean = __ldg(stats + 2 * t), rstd = __ldg(stats + 2 * t + 1);
-    const float* xr = x + t * C;
-    float g[V], xh[V];
-    float s1 = 0.f, s2 = 0.f;
-    const int HW = H * W;
+    const float* dr;
+    if (in_mode == LN_OUT_PATCH2) {
+      const int wq = (int)(t % W), hq = (int)((t / W) % H); const long long n = t / HW;
+      const long long row = (n * (H / 2) + hq / 2) * (W / 2) + wq / 2;
+      dr = dy + row * (4LL * C) + (long long)((hq & 1) * 2 + (wq & 1)) * C;
+    } else {
+      dr = dy + t * C;
+    }
+    float d[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int c = lane + 32 * i;
-      float d;
-      if (in_mode == LN_OUT_NCHW) {
+    for (int i = 0; i < V; ++i) d[i] = __ldg(dr + lane + 32 * i);
+    ln_bwd_token<V>(d, x + t * C, mean, rstd, wv, adw, adb, dx + t * C, C, lane, dx_accum);
+  }
+  ln_bwd_flush<V>(adw, adb, red, dw, db, C, warp, lane);
+}
+
+// dy in NCHW (the output norms): a block stages 32 consecutive tokens x C channels of dy through shared memory with
+// coalesced reads along hw (lane = token) and then works token-major (lane = channel) like the kernel above.
+template <int V>
+__global__ void __launch_bounds__(256) ln_bwd_nchw_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ stats, const float* __restrict__ w,
+                                                         float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                                         int T, int C, int HW, int dx_accum, int chunks_per_block) {
+  extern __shared__ float smem[];
+  float* tile = smem;                              // [C][33]
+  float* red = smem + C * 33;                      // [2][8][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float adw[V], adb[V], wv[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { adw[i] = 0.f; adb[i] = 0.f; wv[i] = __ldg(w + lane + 32 * i); }
+  for (int q = 0; q < chunks_per_block; ++q) {
+    const long long t0 = ((long long)blockIdx.x * chunks_per_block + q) * 32;
+    if (t0 >= T) break;
+    __syncthreads();                               // previous chunk's tile fully consumed
+    {
+      const long long t = t0 + lane;
+      if (t < T) {
         const long long n = t / HW, hw = t % HW;
-        d = __ldg(dy + (n * C + c) * HW + hw);
-      } else if (in_mode == LN_OUT_PATCH2) {
-        const int wq = (int)(t % W), hq = (int)((t / W) % H); const long long n = t / HW;
-        const long long row = (n * (H / 2) + hq / 2) * (W / 2) + wq / 2;
-        d = __ldg(dy + row * (4LL * C) + (long long)((hq & 1) * 2 + (wq & 1)) * C + c);
-      } else {
-        d = __ldg(dy + t * C + c);
+        for (int c = warp; c < C; c += 8) tile[c * 33 + lane] = __ldg(dy + (n * C + c) * HW + hw);
       }
-      xh[i] = (__ldg(xr + c) - mean) * rstd;
-      adw[i] += d * xh[i];
-      adb[i] += d;
-      g[i] = d * wv[i];
-      s1 += g[i];
-      s2 += g[i] * xh[i];
     }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
-    float* dxr = dx + t * C;
+    __syncthreads();
+#pragma unroll 1
+    for (int tt = warp * 4; tt < warp * 4 + 4; ++tt) {
+      const long long t = t0 + tt;
+      if (t >= T) break;
+      const float mean = __ldg(stats + 2 * t), rstd = __ldg(stats + 2 * t + 1);
+      float d[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int c = lane + 32 * i;
-      const float r = rstd * (g[i] - s1 - xh[i] * s2);
-      dxr[c] = dx_accum ? dxr[c] + r : r;
+      for (int i = 0; i < V; ++i) d[i] = tile[(lane + 32 * i) * 33 + tt];
+      ln_bwd_token<V>(d, x + t * C, mean, rstd, wv, adw, adb, dx + t * C, C, lane, dx_accum);
     }
   }
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    atomicAdd(dw + lane + 32 * i, adw[i]);
-    atomicAdd(db + lane + 32 * i, adb[i]);
-  }
+  ln_bwd_flush<V>(adw, adb, red, dw, db, C, warp, lane);
 }
 
 int layernorm_bwd(const float* dy, const float* x, const float* stats, const float* w, float* dx, float* dw,
@@ -182,13 +243,32 @@ int layernorm_bwd(const float* dy, const float* x, const float* stats, const flo
   SM3_REQUIRE(dy && x && stats && w && dx && dw && db && T > 0, SM3_ERR_INVALID_ARG, "layernorm_bwd: null/empty argument");
   SM3_REQUIRE(C % 32 == 0 && C <= 32 * LN_MAXV, SM3_ERR_UNSUPPORTED_SHAPE, "layernorm_bwd: C=%d", C);
   const int V_ = C / 32;
-  // ~ 8 warps/block, enough warps to fill the GPU, >= 16 tokens per warp to amortise the param atomics
-  long long warps = (long long)num_sms() * 32;
-  int tpw = (int)((T + warps - 1) / warps);
-  if (tpw < 16) tpw = 16;
-  warps = (T + tpw - 1) / tpw;
+  // Latency-bound per token (two dependent load rounds + two warp reductions): keep >= 2 full waves of resident warps
+  // busy (register use grows with V, so fewer warps fit for wide rows) and reduce the parameter partials per BLOCK.
+  const int warps_per_sm = V_ <= 6 ? 64 : V_ <= 12 ? 32 : 16;
+  const long long target = (long long)num_sms() * warps_per_sm * 2;
+  if (in_mode == LN_OUT_NCHW) {
+    SM3_REQUIRE(H > 0 && W > 0, SM3_ERR_INVALID_ARG, "layernorm_bwd: NCHW input needs H, W");
+    const long long chunks = (T + 31) / 32;
+    long long cpb = (chunks * 8 + target - 1) / target;          // a chunk keeps 8 warps busy
+    if (cpb < 1) cpb = 1;
+    const int blocks = (int)((chunks + cpb - 1) / cpb);
+    const size_t smem = (size_t)C * (33 + 16) * sizeof(float);
+    SM3_V_DISPATCH(V_, {
+      cudaFuncSetAttribute(ln_bwd_nchw_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      ln_bwd_nchw_kernel<V><<<blocks, 256, smem, stream>>>(dy, x, stats, w, dx, dw, db, (int)T, C, H * W, dx_accum, (int)cpb);
+    });
+    return check_launch("layernorm_bwd_nchw");
+  }
+  int tpw = (int)((T + target - 1) / target);
+  if (tpw < 2) tpw = 2;
+  const long long warps = (T + tpw - 1) / tpw;
   const int blocks = (int)((warps + 7) / 8);
-  SM3_V_DISPATCH(V_, (ln_bwd_kernel<V><<<blocks, 256, 0, stream>>>(dy, x, stats, w, dx, dw, db, (int)T, C, in_mode, H, W, dx_accum, tpw)));
+  const size_t smem = (size_t)16 * C * sizeof(float);
+  SM3_V_DISPATCH(V_, {
+    cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ln_bwd_kernel<V><<<blocks, 256, smem, stream>>>(dy, x, stats, w, dx, dw, db, (int)T, C, in_mode, H, W, dx_accum, tpw);
+  });
   return check_launch("layernorm_bwd");
 }
 

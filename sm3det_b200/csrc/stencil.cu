@@ -101,6 +101,23 @@ __device__ __forceinline__ void dw_load_tile(float* xs, const float* __restrict_
   __syncthreads();
 }
 
+// Packed-FP32 helpers: Blackwell issues FFMA2 (two fp32 FMAs per lane per instruction), which doubles the FMA rate of
+// this issue-bound stencil.  A "pair" is two adjacent channels held in one 64-bit register.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  return (f32x2_t)__float_as_uint(lo) | ((f32x2_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float2 unpack2(f32x2_t v) {
+  return make_float2(__uint_as_float((uint32_t)v), __uint_as_float((uint32_t)(v >> 32)));
+}
+
+// lane = (row selector l/16, channel pair l%16): a half-warp owns one output row of the 16x16 tile and two channels per
+// lane, so every LDS.64 / FFMA2 does the work of two of the scalar version's instructions.
 __global__ void __launch_bounds__(256) dwconv7_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt,
                                                           const float* __restrict__ bias, const float* __restrict__ resid,
                                                           float* __restrict__ y, int H, int W, int C, int tiles_w,
@@ -112,41 +129,38 @@ __global__ void __launch_bounds__(256) dwconv7_tile_kernel(const float* __restri
   const int h0 = th * DT, w0 = tw * DT;
   dw_load_tile(xs, x, n, h0, w0, c0, H, W, C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = c0 + lane;
-  const float b = bias ? __ldg(bias + c) : 0.f;
+  const int cp = lane & 15, r = warp * 2 + (lane >> 4);
+  const int c = c0 + 2 * cp;
+  const int h = h0 + r;
+  if (h >= H) return;
+  const f32x2_t b2 = bias ? __ldg(reinterpret_cast<const f32x2_t*>(bias + c)) : 0ull;
+  f32x2_t acc[DT];
+#pragma unroll
+  for (int o = 0; o < DT; ++o) acc[o] = b2;
 #pragma unroll 1
-  for (int rr = 0; rr < 2; ++rr) {
-    const int r = warp * 2 + rr;
-    const int h = h0 + r;
-    if (h >= H) break;
-    float acc[DT];
+  for (int i = 0; i < 7; ++i) {
+    f32x2_t wv[7];
 #pragma unroll
-    for (int o = 0; o < DT; ++o) acc[o] = b;
-#pragma unroll 1
-    for (int i = 0; i < 7; ++i) {
-      float wv[7];
+    for (int j = 0; j < 7; ++j) wv[j] = __ldg(reinterpret_cast<const f32x2_t*>(wt + (i * 7 + j) * C + c));
+    const f32x2_t* xr = reinterpret_cast<const f32x2_t*>(xs + ((r + i) * DTI) * DCC) + cp;
 #pragma unroll
-      for (int j = 0; j < 7; ++j) wv[j] = __ldg(wt + (i * 7 + j) * C + c);
-      const float* xr = xs + ((r + i) * DTI) * DCC + lane;
+    for (int cc = 0; cc < DTI; ++cc) {
+      const f32x2_t v = xr[cc * (DCC / 2)];
 #pragma unroll
-      for (int cc = 0; cc < DTI; ++cc) {
-        const float v = xr[cc * DCC];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          const int o = cc - j;
-          if (o >= 0 && o < DT) acc[o] = fmaf(v, wv[j], acc[o]);
-        }
+      for (int j = 0; j < 7; ++j) {
+        const int o = cc - j;
+        if (o >= 0 && o < DT) acc[o] = ffma2(v, wv[j], acc[o]);
       }
     }
-    const long long rowoff = (((long long)n * H + h) * W) * C + c;
+  }
+  const long long rowoff = (((long long)n * H + h) * W) * C + c;
 #pragma unroll
-    for (int o = 0; o < DT; ++o) {
-      const int w = w0 + o;
-      if (w < W) {
-        float v = acc[o];
-        if (resid) v += __ldg(resid + rowoff + (long long)w * C);
-        y[rowoff + (long long)w * C] = v;
-      }
+  for (int o = 0; o < DT; ++o) {
+    const int w = w0 + o;
+    if (w < W) {
+      float2 v = unpack2(acc[o]);
+      if (resid) { const float2 rr = __ldg(reinterpret_cast<const float2*>(resid + rowoff + (long long)w * C)); v.x += rr.x; v.y += rr.y; }
+      *reinterpret_cast<float2*>(y + rowoff + (long long)w * C) = v;
     }
   }
 }
@@ -238,11 +252,12 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_tile_kernel(const float* __
   float* xs = smem;                               // [DTI][DTI][DCC]
   float* ds = smem + DTI * DTI * DCC;             // [DT][DT][DCC]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * DCC, c = c0 + lane;
-  float acc[49];
+  const int c0 = blockIdx.y * DCC;
+  const int cp = lane & 15, half = lane >> 4;           // channel pair, row selector (FFMA2: two channels per lane)
+  f32x2_t acc[49];
 #pragma unroll
-  for (int i = 0; i < 49; ++i) acc[i] = 0.f;
-  float accb = 0.f;
+  for (int i = 0; i < 49; ++i) acc[i] = 0ull;
+  float2 accb = make_float2(0.f, 0.f);
   const int tiles = N * tiles_h * tiles_w;
   for (int t = blockIdx.x; t < tiles; t += blocks_per_chunk) {
     const int n = t / (tiles_h * tiles_w), rem = t % (tiles_h * tiles_w);
@@ -261,39 +276,41 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_tile_kernel(const float* __
       }
     }
     dw_load_tile(xs, x, n, h0, w0, c0, H, W, C);  // commits + waits for both tiles, then __syncthreads
-#pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = warp * 2 + rr;
-      float d[DT];
+    const int r = warp * 2 + half;
+    f32x2_t d[DT];
 #pragma unroll
-      for (int o = 0; o < DT; ++o) { d[o] = ds[(r * DT + o) * DCC + lane]; accb += d[o]; }
+    for (int o = 0; o < DT; ++o) {
+      d[o] = reinterpret_cast<const f32x2_t*>(ds + (r * DT + o) * DCC)[cp];
+      const float2 dv = unpack2(d[o]);
+      accb.x += dv.x; accb.y += dv.y;
+    }
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const float* xr = xs + ((r + i) * DTI) * DCC + lane;
+    for (int i = 0; i < 7; ++i) {
+      const f32x2_t* xr = reinterpret_cast<const f32x2_t*>(xs + ((r + i) * DTI) * DCC) + cp;
 #pragma unroll
-        for (int cc = 0; cc < DTI; ++cc) {
-          const float v = xr[cc * DCC];
+      for (int cc = 0; cc < DTI; ++cc) {
+        const f32x2_t v = xr[cc * (DCC / 2)];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            const int o = cc - j;
-            if (o >= 0 && o < DT) acc[i * 7 + j] = fmaf(v, d[o], acc[i * 7 + j]);
-          }
+        for (int j = 0; j < 7; ++j) {
+          const int o = cc - j;
+          if (o >= 0 && o < DT) acc[i * 7 + j] = ffma2(v, d[o], acc[i * 7 + j]);
         }
       }
     }
   }
-  // reduce the 8 warps of the block through shared memory, then one atomic per (tap, channel)
+  // reduce the 16 half-warps of the block through shared memory, then one atomic per (tap, channel)
   __syncthreads();
-  float* red = smem;                              // [8][50][32]
+  float* red = smem;                              // [16][50][32]
+  const int hw = warp * 2 + half;
 #pragma unroll
-  for (int i = 0; i < 49; ++i) red[(warp * 50 + i) * 32 + lane] = acc[i];
-  red[(warp * 50 + 49) * 32 + lane] = accb;
+  for (int i = 0; i < 49; ++i) reinterpret_cast<f32x2_t*>(red + (hw * 50 + i) * 32)[cp] = acc[i];
+  reinterpret_cast<float2*>(red + (hw * 50 + 49) * 32)[cp] = accb;
   __syncthreads();
   for (int idx = threadIdx.x; idx < 50 * 32; idx += blockDim.x) {
     const int i = idx / 32, l = idx % 32;
     float sum = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) sum += red[(w * 50 + i) * 32 + l];
+    for (int w = 0; w < 16; ++w) sum += red[(w * 50 + i) * 32 + l];
     if (i < 49) atomicAdd(dwt + i * C + c0 + l, sum);
     else if (dbias) atomicAdd(dbias + c0 + l, sum);
   }
@@ -310,7 +327,8 @@ int dwconv7_wgrad(const float* x, const float* dy, float* dwt, float* dbias, int
     int bpc = (num_sms() * 2 + chunks - 1) / chunks;          // ~2 waves of blocks over all channel chunks
     if (bpc > tiles) bpc = (int)tiles;
     if (bpc < 1) bpc = 1;
-    const size_t smem = (size_t)(DTI * DTI + DT * DT) * DCC * sizeof(float);
+    size_t smem = (size_t)(DTI * DTI + DT * DT) * DCC * sizeof(float);
+    if (smem < (size_t)16 * 50 * 32 * sizeof(float)) smem = (size_t)16 * 50 * 32 * sizeof(float);   // final reduction buffer
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     dim3 grid((unsigned)bpc, (unsigned)chunks);
