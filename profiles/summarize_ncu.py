@@ -28,20 +28,38 @@ def main(path):
                 print(f'  {h} [{u}] = {v}')
     src = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    try:
-        h = rows[1]
-        ix = {k: i for i, k in enumerate(h)}
-        data = [r for r in rows[2:] if len(r) == len(h)]
-        stall_cols = [c for c in h if c.startswith('stall_') and 'Not Issued' not in c]
-        tot = {c: sum(int(r[ix[c]]) for r in data) for c in stall_cols}
-        print('warp-stall samples by reason (all warps):')
+    # the source page repeats its header for every kernel of the report: aggregate per kernel section
+    sections, cur, ix = [], None, None
+    for r in rows:
+        if 'Source' in r and '# Samples' in r:
+            ix = {k: i for i, k in enumerate(r)}
+            cur = dict(ix=ix, hdr=r, data=[])
+            sections.append(cur)
+        elif cur is not None and len(r) == len(cur['hdr']):
+            try:
+                int(r[ix['# Samples']])
+            except ValueError:
+                continue
+            cur['data'].append(r)
+    for si, sec in enumerate(sections):
+        ix, data = sec['ix'], sec['data']
+        if not data:
+            continue
+        stall_cols = [c for c in sec['hdr'] if c.startswith('stall_') and 'Not Issued' not in c]
+        tot = {}
+        for c in stall_cols:
+            try:
+                tot[c] = sum(int(r[ix[c]]) for r in data)
+            except ValueError:
+                pass
+        print(f'[kernel #{si}] warp-stall samples by reason (all warps):')
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:8]:
             print(f'  {k}: {v}')
-        print('hottest SASS instructions (samples, executed, text):')
-        for r in sorted(data, key=lambda r: -int(r[ix['# Samples']]))[:12]:
-            print(f"  {r[ix['# Samples']]:>7} {r[ix['Instructions Executed']]:>10}  {r[ix['Source']].strip()[:90]}")
-    except Exception as e:  # report without source page
-        print('no source page:', e)
+        print(f'[kernel #{si}] hottest SASS instructions (samples, executed, text):')
+        for r in sorted(data, key=lambda r: -int(r[ix['# Samples']]))[:14]:
+            print(f"  {r[ix['# Samples']]:>7} {r[ix['Instructions Executed']]:>10}  {r[ix['Source']].strip()[:100]}")
+    if not sections:
+        print('no source page in this report')
 
 
 if __name__ == '__main__':

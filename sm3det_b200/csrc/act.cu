@@ -32,7 +32,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 
 // grid: (column-chunk groups of 32, row bands); block 256 = 32 chunk lanes x 8 row lanes
 template <int MODE, bool CS>
-__global__ void __launch_bounds__(256) act_pack_kernel(const ActPackArgs a, int rows_per_band) {
+__global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, int rows_per_band) {
   __shared__ float s_cs[8][32 * 8 + 8];
   const int cl = threadIdx.x & 31, rlane = threadIdx.x >> 5;
   const int chunk = blockIdx.x * 32 + cl;            // 8-column chunk index
@@ -49,19 +49,30 @@ __global__ void __launch_bounds__(256) act_pack_kernel(const ActPackArgs a, int 
 #pragma unroll
   for (int e = 0; e < 8; ++e) cs[e] = 0.f;
   int cur_group = -1;
+  // Software-pipelined over rows: the loads of row r+8 are in flight while row r is evaluated and stored (one row =
+  // 32-64 B per thread is not enough memory-level parallelism to cover HBM latency at 4 blocks / SM).
+  auto row_live = [&](long long r) { return col_ok && r < a.R && r < live; };
+  float4 nh0 = make_float4(0.f, 0.f, 0.f, 0.f), nh1 = nh0, nd0 = nh0, nd1 = nh0;
+  auto load_row = [&](long long r) {
+    if (r < r_end && row_live(r)) {
+      nh0 = ldg_f4(a.h + r * a.W + col); nh1 = ldg_f4(a.h + r * a.W + col + 4);
+      if (MODE == 1) { nd0 = ldg_f4(a.da + r * a.W + col); nd1 = ldg_f4(a.da + r * a.W + col + 4); }
+    }
+  };
+  load_row(r_begin + rlane);
   for (long long r = r_begin + rlane; r < r_end; r += 8) {
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = 0.f;
-    const bool row_ok = col_ok && r < a.R && r < live;
+    const bool row_ok = row_live(r);
+    const float4 h0 = nh0, h1 = nh1, d0 = nd0, d1 = nd1;
+    load_row(r + 8);
     if (row_ok) {
-      const float4 h0 = ldg_f4(a.h + r * a.W + col), h1 = ldg_f4(a.h + r * a.W + col + 4);
       const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
       if (MODE == 0) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = gelu_fast(hv[e]);
       } else if (MODE == 1) {
-        const float4 d0 = ldg_f4(a.da + r * a.W + col), d1 = ldg_f4(a.da + r * a.W + col + 4);
         const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = dv[e] * gelu_grad_fast(hv[e]);
