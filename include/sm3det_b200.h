@@ -210,6 +210,15 @@ int sm3_gather_sum(const float* src, const int32_t* slot_of, const float* add, f
 int sm3_scale_rows(const float* x, const float* row_scale, const float* col_scale, float* out, int64_t rows,
                    int32_t C, void* stream);
 
+/* ---- expert parallelism over NVLink peer memory (BASELINE config 4; beyond the reference) -----------
+ * sm3_gather_rows_peer: out[r,:] = scale[r] * bases[src_rank[r]][row*C ..], row = src_row[r] or, when token_lists is
+ * given, token_lists[src_rank[r]][src_row[r]].  `bases` / `token_lists` are DEVICE arrays of `world` device pointers
+ * into P2P-mapped (symmetric) buffers of the peer GPUs: the dispatch and combine all-to-alls of SparseDispatcher
+ * (convnext_moe.py:264-284) become direct NVLink loads -- no staging copy, no NCCL call on the data path.
+ * src_rank < 0 or row < 0 -> zero row. */
+int sm3_gather_rows_peer(const float* const* bases, const int32_t* const* token_lists, const int32_t* src_rank,
+                         const int32_t* src_row, const float* scale, float* out, int64_t rows, int32_t C, void* stream);
+
 /* ---- LSKNet-MoE backbone (BASELINE config 5; mmrotate/models/backbones/lsk_moe.py) -------------------
  * sm3_dwconv_fwd / _wgrad : depthwise ks x ks conv, dilation dil, "same" padding, NHWC; weight_t = taps as
  *                           [ks*ks][C].  Replaces LSKblock.conv0 (5x5) :322, conv_spatial (7x7 dil 3) :323 and

@@ -85,6 +85,7 @@ SIGNATURES = {
     'sm3_gather_sum': [_P, _P, _P, _P, _I32, _I32, _I32, _P],
     'sm3_scale_rows': [_P, _P, _P, _P, _I64, _I32, _P],
     'sm3_moe_router_bwd': [_P, _P],
+    'sm3_gather_rows_peer': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     # LSKNet-MoE
     'sm3_dwconv_fwd': [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     'sm3_dwconv_wgrad': [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],

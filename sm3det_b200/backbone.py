@@ -185,6 +185,20 @@ class ConvNeXtBlock(nn.Module):
         ep = m.expert_params()
         E = m.num_experts
         w1s, w2s = ep[0:E], ep[2 * E:3 * E]
+        epc = getattr(self, '_ep', None)
+        if epc is not None:
+            # expert parallel (sm3det_b200.expert_parallel): this rank only packs / runs the experts it owns
+            from .expert_parallel import EPMoEBlockFn
+            El = E // epc.world
+            o1, o2 = w1s[epc.rank * El:(epc.rank + 1) * El], w2s[epc.rank * El:(epc.rank + 1) * El]
+            packs = {'w1': pc.get('w1', o1, False), 'w2': pc.get('w2', o2, False)}
+            if grad:
+                packs['w1_t'] = pc.get('w1', o1, True)
+                packs['w2_t'] = pc.get('w2', o2, True)
+                packs['wp_t'] = pc.get('wp', [g.cosine_projector.weight], True)
+            return EPMoEBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias, self.gamma,
+                                      g.cosine_projector.weight, g.cosine_projector.bias, g.sim_matrix, g.temperature,
+                                      m.w_noise, rs, noise, eps, E, m.k, record, packs, epc, self._ep_key, *ep)
         packs = {'w1': pc.get('w1', w1s, False), 'w2': pc.get('w2', w2s, False)}
         if grad:
             packs['w1_t'] = pc.get('w1', w1s, True)

@@ -150,6 +150,10 @@ int sm3_scale_rows(const float* x, const float* rs, const float* cs, float* out,
   return scale_rows(x, rs, cs, out, rows, C, S(stream));
 }
 
+int sm3_gather_rows_peer(const float* const* bases, const int32_t* const* token_lists, const int32_t* src_rank,
+                         const int32_t* src_row, const float* scale, float* out, int64_t rows, int32_t C, void* stream) {
+  return gather_rows_peer(bases, reinterpret_cast<const int* const*>(token_lists), src_rank, src_row, scale, out, rows, C, S(stream));
+}
 int sm3_dwconv_fwd(const float* x, const float* wt, const float* bias, const float* resid, float* y, int32_t N, int32_t H,
                    int32_t W, int32_t C, int32_t ks, int32_t dil, void* stream) {
   return dwconv_fwd(x, wt, bias, resid, y, N, H, W, C, ks, dil, S(stream));

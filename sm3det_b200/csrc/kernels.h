@@ -123,6 +123,9 @@ int gather_sum(const float* src, const int* slot_of, const float* add, float* ou
 int scale_rows(const float* x, const float* rs, const float* cs, float* out, long long rows, int C,
                cudaStream_t stream);
 
+int gather_rows_peer(const float* const* bases, const int* const* token_lists, const int* src_rank, const int* src_row,
+                     const float* scale, float* out, long long rows, int C, cudaStream_t stream);
+
 // lsk.cu (LSKNet-MoE, BASELINE config 5) --------------------------------------------------------------
 // wt: depthwise taps transposed to [ks*ks][C]; "same" padding dil*(ks-1)/2.  Instantiated: (3,1) (5,1) (7,3).
 int dwconv_fwd(const float* x, const float* wt, const float* bias, const float* resid, float* y, int N, int H, int W, int C,

@@ -103,4 +103,40 @@ int scale_rows(const float* x, const float* rs, const float* cs, float* out, lon
   return check_launch("scale_rows");
 }
 
+// Peer row gather over NVLink (expert-parallel dispatch / combine): out[r,:] = scale[r] * base[src_rank[r]][row*C ..]
+// where row = src_row[r], or token_list[src_rank[r]][src_row[r]] when token lists are given (the dispatch reads the source
+// rank's expert-sorted pair list and then the token row, both through peer pointers).  src_rank < 0 -> zero row.
+// bases / token_lists are device arrays of `world` device pointers into symmetric (P2P-mapped) buffers.
+__global__ void __launch_bounds__(256) gather_rows_peer_kernel(const float* const* __restrict__ bases,
+                                                              const int* const* __restrict__ token_lists,
+                                                              const int* __restrict__ src_rank, const int* __restrict__ src_row,
+                                                              const float* __restrict__ scale, float* __restrict__ out,
+                                                              long long total, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int Q = C >> 2;
+  const long long r = i / Q;
+  const int c = (int)(i % Q) * 4;
+  const int s = __ldg(src_rank + r);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s >= 0) {
+    long long row = __ldg(src_row + r);
+    if (token_lists) row = token_lists[s][row];
+    if (row >= 0) {
+      v = *reinterpret_cast<const float4*>(bases[s] + row * C + c);      // plain (coherent) load: peer memory
+      if (scale) { const float g = __ldg(scale + r); v.x *= g; v.y *= g; v.z *= g; v.w *= g; }
+    }
+  }
+  *reinterpret_cast<float4*>(out + r * C + c) = v;
+}
+
+int gather_rows_peer(const float* const* bases, const int* const* token_lists, const int* src_rank, const int* src_row,
+                     const float* scale, float* out, long long rows, int C, cudaStream_t stream) {
+  SM3_REQUIRE(bases && src_rank && src_row && out && C % 4 == 0 && rows >= 0, SM3_ERR_INVALID_ARG, "gather_rows_peer: bad argument");
+  if (rows == 0) return SM3_OK;
+  const long long total = rows * (C / 4);
+  gather_rows_peer_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(bases, token_lists, src_rank, src_row, scale, out, total, C);
+  return check_launch("gather_rows_peer");
+}
+
 }  // namespace sm3

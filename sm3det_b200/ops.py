@@ -501,3 +501,14 @@ def col2im(dcol, *, N, H, W, Cin, ks, stride, pad, Kp, nchw=False):
     dx = torch.empty((N, Cin, H, W) if nchw else (N, H, W, Cin), device=dcol.device, dtype=torch.float32)
     _lib.check(lib.sm3_col2im(_p(dcol), _p(dx), N, H, W, Cin, ks, stride, pad, Kp, 1 if nchw else 0, _stream()), 'sm3_col2im')
     return dx
+
+
+def gather_rows_peer(bases, src_rank, src_row, *, rows, Cc, token_lists=None, scale=None, out=None):
+    """out[r] = scale[r] * peer_buffer[src_rank[r]][row]  (bases / token_lists: int64 device tensors of peer pointers)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((rows, Cc), device=src_rank.device, dtype=torch.float32)
+    _lib.check(lib.sm3_gather_rows_peer(_p(bases, torch.int64), None if token_lists is None else _p(token_lists, torch.int64),
+                                        _pi(src_rank), _pi(src_row), _p(scale), _p(out), rows, Cc, _stream()),
+               'sm3_gather_rows_peer')
+    return out

@@ -1,0 +1,17 @@
+"""world_size-2 gloo test (CPU) of the expert-parallel exchange plan: ragged token counts, an expert with no traffic from
+one rank, 128-row padding, source-major segment order, and the slot -> (owner, row) map of the combine."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_ep_exchange_plan_world2_gloo():
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29541',
+                        os.path.join(ROOT, 'tests', 'dist', 'ep_plan_worker.py'), ROOT],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count('ep plan ok') == 2, r.stdout[-2000:]
