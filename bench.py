@@ -172,6 +172,70 @@ def gemm_roofline(net, x, peaks):
                     if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 'peak = fallback 1.59 PFLOP/s'}
 
 
+def moe_roofline(net, x, peaks):
+    """BASELINE metric (2): achieved HBM GB/s of the MoE dispatch(+expert) path of one forward, against the measured copy
+    bandwidth.  Timed with CUDA events around (a) the whole 3-kernel-sequence the north star names -- dispatch gather
+    (fused into the operand pack), grouped expert GEMM pair, combine scatter -- and (b) the dispatch kernels alone
+    (gather-pack + combine).  Algorithmic bytes: SURVEY.md 8(d): (5k+1)*T*C*4 + E*(8C^2+5C)*4 + 8kT for the sequence,
+    (3k+1)*T*C*4 for gather + scatter."""
+    from sm3det_b200 import ops
+    seq, disp = [], []
+    o_assign, o_combine, o_pack = ops.moe_assign, ops.moe_combine, ops.pack_act
+    state = {}
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def assign(top_idx, plan, *, T, E, k):
+        r = o_assign(top_idx, plan, T=T, E=E, k=k)
+        state.update(t0=ev(), T=T, E=E, k=k)
+        return r
+
+    def pack(x_, **kw):
+        if kw.get('row_index') is not None and 't0' in state:
+            a = ev(); r = o_pack(x_, **kw); b = ev()
+            state['gather'] = (a, b)
+            return r
+        return o_pack(x_, **kw)
+
+    def combine(o, slot_of, top_idx, gate, gamma, resid, row_scale, *, T, Cc, k, want_y=False):
+        a = ev()
+        r = o_combine(o, slot_of, top_idx, gate, gamma, resid, row_scale, T=T, Cc=Cc, k=k, want_y=want_y)
+        b = ev()
+        E = state['E']
+        seq.append((state.pop('t0'), b, ((5 * k + 1) * T * Cc * 4 + E * (8 * Cc * Cc + 5 * Cc) * 4 + 8 * k * T), 16.0 * k * T * Cc * Cc))
+        g = state.pop('gather', None)
+        if g is not None:
+            disp.append((g[0], g[1], a, b, (3 * k + 1) * T * Cc * 4))
+        return r
+
+    ops.moe_assign, ops.moe_combine, ops.pack_act = assign, combine, pack
+    try:
+        with torch.no_grad():
+            net(x)
+        torch.cuda.synchronize()
+    finally:
+        ops.moe_assign, ops.moe_combine, ops.pack_act = o_assign, o_combine, o_pack
+    peak = peaks.get('hbm_gbs') or 6550.0
+    ms = sum(a.elapsed_time(b) for a, b, *_ in seq)
+    by = sum(r[2] for r in seq)
+    fl = sum(r[3] for r in seq)
+    dms = sum(a.elapsed_time(b) + c.elapsed_time(d) for a, b, c, d, _ in disp)
+    dby = sum(r[4] for r in disp)
+    out = {'bound': 'hbm', 'kernel': 'MoE dispatch+expert path (gather-pack -> grouped GEMM x2 -> combine), all MoE layers of one forward',
+           'layers': len(seq), 'achieved': by / (ms * 1e-3) / 1e9 if ms else 0.0, 'peak': peak, 'unit': 'GB/s',
+           'ms': ms, 'algorithmic_bytes': by, 'expert_tflops': fl / (ms * 1e-3) / 1e12 if ms else 0.0,
+           'note': 'the expert GEMM pair is tensor-bound (16kTC^2 FLOP on 3-pass split-bf16), so the sequence cannot reach the '
+                   'HBM roofline; dispatch_only isolates the HBM-bound gather + scatter kernels'}
+    out['frac'] = out['achieved'] / peak
+    if dms:
+        out['dispatch_only'] = {'achieved': dby / (dms * 1e-3) / 1e9, 'frac': dby / (dms * 1e-3) / 1e9 / peak, 'ms': dms,
+                                'algorithmic_bytes': dby}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from sm3det_b200 import ConvNeXt_moe_MultiInput, _lib
@@ -276,13 +340,20 @@ def run_ours(args):
             pass
         roof = gemm_roofline(net, dev_x, peaks)
         net.zero_grad(set_to_none=True)
+        try:   # measured DRAM traffic of the GEMM launches of one step (ncu dram__bytes_read+write, profiles/)
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
+            roof['traffic'] = tr['bytes_per_launch']
+            roof['traffic_note'] = tr['note']
+        except Exception:
+            pass
+        roof_moe = moe_roofline(net, dev_x, peaks)
         line = {'metric': METRIC, 'value': B * world / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32 (bf16 hi+lo split operands on tcgen05, fp32 accumulate; SIMT fp32 elsewhere)',
                 'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks,
                 'e2e': {'value': B * world / (ms_e2e * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
-                'gpu_launches': launches, 'roofline': roof}
+                'gpu_launches': launches, 'roofline': roof, 'roofline_moe': roof_moe}
         if world == 1 and not args.no_cpu_baseline:
             ips, dt, threads = time_cpu_reference(args, args.cpu_images, 1, 0)
             line['cpu_baseline'] = {'value': ips, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
