@@ -144,7 +144,7 @@ def gemm_roofline(net, x, peaks):
         if kw.get('sched', 0) == ops.SCHED_GROUPED:
             rows = kw.get('_live_rows', rows)
         flops = 2.0 * rows * kw['N'] * kw['K']
-        rec.append((e0, e1, flops, kw['M'], kw['N'], kw['K'], kw.get('sched', 0)))
+        rec.append((e0, e1, flops, kw['M'], kw['N'], kw['K'], kw.get('sched', 0), 4.0 * (rows * kw['K'] + kw['N'] * kw['K'] + rows * kw['N'])))
         return r
 
     ops.gemm = timed
@@ -157,7 +157,7 @@ def gemm_roofline(net, x, peaks):
     tot_ms = sum(a.elapsed_time(b) for a, b, *_ in rec)
     if os.environ.get('SM3_GEMM_TABLE'):
         with open(os.environ['SM3_GEMM_TABLE'], 'w') as f:
-            for a, b, fl, M, N, K, sched in rec:
+            for a, b, fl, M, N, K, sched, _ in rec:
                 ms = a.elapsed_time(b)
                 f.write(f'M={M} N={N} K={K} sched={sched} ms={ms:.4f} tflops={fl / ms * 1e-9:.1f}\n')
     # grouped / split-K launches: M (or K) is the padded pair space; close enough for the aggregate (pad <= 1.5 %)
@@ -166,6 +166,7 @@ def gemm_roofline(net, x, peaks):
     ach = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
     return {'bound': 'tensor', 'kernel': 'gemm_bf16x3_kernel (all launches of one fwd+bwd step)', 'achieved': ach,
             'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None, 'launches': len(rec),
+            'algorithmic_bytes_per_launch': sum(r[7] for r in rec) / max(len(rec), 1),
             'gemm_ms_per_step': tot_ms,
             'note': 'algorithmic fp32 FLOPs; each costs 3 bf16 tensor-core MACs (hi*hi+hi*lo+lo*hi), so the tensor pipe '
                     'runs at 3x this rate; peak = measured cuBLAS bf16 (sustained) from MEASURED_PEAKS.json'
