@@ -242,18 +242,30 @@ int launch(Params p, cudaStream_t stream) {
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   if (grid < 1) grid = 1;
-#define SM3_GEMM_LAUNCH(AMN, BMN, BPK, APK)                                                                                \
-  do {                                                                                                                   \
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<AMN, BMN, BPK, APK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES); \
-    gemm_bf16x3_kernel<AMN, BMN, BPK, APK><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);                                     \
+#define SM3_GEMM_LAUNCH_E(AMN, BMN, BPK, APK, EPIT)                                                                             \
+  do {                                                                                                                          \
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<AMN, BMN, BPK, APK, EPIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES); \
+    gemm_bf16x3_kernel<AMN, BMN, BPK, APK, EPIT><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);                                     \
   } while (0)
+#define SM3_GEMM_LAUNCH(AMN, BMN, BPK, APK) SM3_GEMM_LAUNCH_E(AMN, BMN, BPK, APK, -1)
   if (apacked) {
     SM3_REQUIRE(packed && a_mn == b_mn && p.BN == pick_bn(p.N) && !p.a_row_index && !p.b_k_index, SM3_ERR_INVALID_ARG,
                 "gemm: packed A needs packed B of the same majorness (gathers are applied by the pack kernels)");
     SM3_REQUIRE(aligned16(p.a_packed) && aligned16(p.b_packed) && (p.b_packed_group_stride % 8) == 0, SM3_ERR_INVALID_ARG,
                 "gemm: packed operands must be 16B aligned");
-    if (a_mn) SM3_GEMM_LAUNCH(true, true, true, true);
-    else SM3_GEMM_LAUNCH(false, false, true, true);
+    // the flag sets of the hot launches get their own instantiation (compile-time epilogue)
+    constexpr int E_FFN2_TRAIN = EPI_BIAS | EPI_COLSCALE | EPI_RESID | EPI_AUXSTORE, E_FFN2_EVAL = EPI_BIAS | EPI_COLSCALE | EPI_RESID;
+    if (a_mn) {
+      if (p.epi == EPI_ATOMIC) SM3_GEMM_LAUNCH_E(true, true, true, true, EPI_ATOMIC);
+      else if (p.epi == (EPI_ATOMIC | EPI_ROWSCALE)) SM3_GEMM_LAUNCH_E(true, true, true, true, EPI_ATOMIC | EPI_ROWSCALE);
+      else SM3_GEMM_LAUNCH(true, true, true, true);
+    } else {
+      if (p.epi == 0) SM3_GEMM_LAUNCH_E(false, false, true, true, 0);
+      else if (p.epi == EPI_BIAS) SM3_GEMM_LAUNCH_E(false, false, true, true, EPI_BIAS);
+      else if (p.epi == E_FFN2_TRAIN) SM3_GEMM_LAUNCH_E(false, false, true, true, E_FFN2_TRAIN);
+      else if (p.epi == E_FFN2_EVAL) SM3_GEMM_LAUNCH_E(false, false, true, true, E_FFN2_EVAL);
+      else SM3_GEMM_LAUNCH(false, false, true, true);
+    }
   }
   else if (packed) {
     SM3_REQUIRE(!a_mn && p.sched != SCHED_SPLITK && p.BN == pick_bn(p.N), SM3_ERR_INVALID_ARG,
@@ -266,6 +278,7 @@ int launch(Params p, cudaStream_t stream) {
   else if (!a_mn && b_mn) SM3_GEMM_LAUNCH(false, true, false, false);
   else if (a_mn && b_mn) SM3_GEMM_LAUNCH(true, true, false, false);
   else SM3_REQUIRE(false, SM3_ERR_UNSUPPORTED_SHAPE, "gemm: MN-major A with K-major B is not instantiated");
+#undef SM3_GEMM_LAUNCH_E
 #undef SM3_GEMM_LAUNCH
   return check_launch("gemm_bf16x3_kernel");
 }

@@ -200,18 +200,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// asynchronous TMEM load of 16 accumulator columns (one row per lane); the registers are valid after tc_wait_ld()
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 struct Tile {
@@ -271,8 +269,12 @@ __device__ __forceinline__ void split4(const float4& x, uint32_t& h01, uint32_t&
 // 2 k-rows x 128 mn (MN-major); unit u of a k-block belongs to producer warp u % 7.  All per-tile
 // address arithmetic is hoisted: a thread keeps one 32-bit element offset per (unit, half) and
 // advances it by a constant per k-block.
-template <bool A_MN, bool B_MN, bool B_PACKED, bool A_PACKED>
+// EPI_T >= 0: the epilogue flag set is a compile-time constant (the hot FFN / expert / wgrad variants: the epilogue warps
+// are the bottleneck of the HBM-bound GEMMs and spend a fifth of their issue slots resolving the runtime flag branches);
+// EPI_T = -1: generic, flags read from Params.
+template <bool A_MN, bool B_MN, bool B_PACKED, bool A_PACKED, int EPI_T>
 __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Params p) {
+  const int EPI = (EPI_T >= 0) ? EPI_T : p.epi;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -320,7 +322,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
     // EPI_COLSUM: column sums are accumulated per CTA in shared memory across all its tiles of one group and
     // flushed with one global atomic per column (instead of one per column per tile).
     const uint32_t cs_base = bar_base + BAR_BYTES + MAX_EPI_WARPS * EPI_STAGE_BYTES;
-    const bool cs_smem = (p.epi & EPI_COLSUM) && p.N <= COLSUM_SMEM_COLS;
+    const bool cs_smem = (EPI & EPI_COLSUM) && p.N <= COLSUM_SMEM_COLS;
     int cs_group = -1;
     const int e_tid = e_idx * 32 + lane;
     auto epi_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NE * 32) : "memory"); };
@@ -349,9 +351,11 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
       float* dbase = p.D + (long long)tl.group * p.d_group_stride;
       const float* bias = p.bias ? p.bias + (long long)tl.group * p.bias_group_stride : nullptr;
       bool arrived = false;
+      uint32_t vr[EPI_CW];
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+      if (cgrp < nchunks) tc_ld16_issue(tbase + (uint32_t)(cgrp * EPI_CW), vr);
       for (int c = cgrp; c < nchunks; c += ncgrp) {
-        float v[EPI_CW];
-        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c * EPI_CW), v);
+        tc_wait_ld();
         if (c == my_last) {
           tc_fence_before();
           __syncwarp();
@@ -361,16 +365,17 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
         __syncwarp();                                     // previous chunk's reads of the stage are done
 #pragma unroll
         for (int j = 0; j < EPI_CW / 4; ++j)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
                        ::"r"(stage_base + (uint32_t)(lane * EPI_STAGE_ROW_FLOATS + 4 * j) * 4u),
-                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+                         "r"(vr[4 * j]), "r"(vr[4 * j + 1]), "r"(vr[4 * j + 2]), "r"(vr[4 * j + 3]) : "memory");
+        if (c + ncgrp < nchunks) tc_ld16_issue(tbase + (uint32_t)((c + ncgrp) * EPI_CW), vr);   // in flight while this chunk is written out
         __syncwarp();
         const int n = tl.n0 + c * EPI_CW + c4;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), sv = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (p.epi & EPI_BIAS) bv = ldg_f4(bias + n);
-        if (p.epi & EPI_COLSCALE) sv = ldg_f4(p.col_scale + n);
+        if (EPI & EPI_BIAS) bv = ldg_f4(bias + n);
+        if (EPI & EPI_COLSCALE) sv = ldg_f4(p.col_scale + n);
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+#pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int r = it * 8 + rl;
           const int row = row0 + r;
@@ -380,28 +385,28 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
                        : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                        : "r"(stage_base + (uint32_t)(r * EPI_STAGE_ROW_FLOATS + c4) * 4u) : "memory");
           x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-          if ((p.epi & (EPI_AUXSTORE | EPI_GELU)) && p.aux_out)
+          if ((EPI & (EPI_AUXSTORE | EPI_GELU)) && p.aux_out)
             *reinterpret_cast<float4*>(p.aux_out + (long long)row * p.ld_aux + n) = x;
-          if (p.epi & EPI_GELU) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
-          if (p.epi & EPI_DGELU) {
+          if (EPI & EPI_GELU) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+          if (EPI & EPI_DGELU) {
             const float4 h = ldg_f4(p.aux_in + (long long)row * p.ld_aux + n);
             x.x *= gelu_grad_fast(h.x); x.y *= gelu_grad_fast(h.y); x.z *= gelu_grad_fast(h.z); x.w *= gelu_grad_fast(h.w);
           }
           x.x *= sv.x; x.y *= sv.y; x.z *= sv.z; x.w *= sv.w;
-          if (p.epi & EPI_ROWSCALE) { const float rs = __ldg(p.row_scale + row); x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs; }
-          if (p.epi & EPI_RESID) {
+          if (EPI & EPI_ROWSCALE) { const float rs = __ldg(p.row_scale + row); x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs; }
+          if (EPI & EPI_RESID) {
             const float4 rr = ldg_f4(p.resid + (long long)row * p.ld_resid + n);
             x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
           }
           cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
           float* dst = dbase + (long long)row * p.ldd + n;
-          if (p.epi & EPI_ATOMIC) {
+          if (EPI & EPI_ATOMIC) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
           } else {
             *reinterpret_cast<float4*>(dst) = x;
           }
         }
-        if (p.epi & EPI_COLSUM) {
+        if (EPI & EPI_COLSUM) {
           // lanes with the same (lane & 3) hold partial sums of the same 4 columns
 #pragma unroll
           for (int o = 4; o < 32; o <<= 1) {

@@ -53,7 +53,21 @@ class StemFn(Function):
         T = conv.numel() // C0
         dlnw, dlnb = _zeros_like_param(lnw), _zeros_like_param(lnw)
         du = ops.layernorm_bwd(dy, conv, stats, lnw, dlnw, dlnb, tokens=T, C=C0)
-        K = ctx.wshape[1] * ctx.wshape[2] * ctx.wshape[3]
+        # weight gradient on the tensor cores: patches gathered once (im2col of the non-overlapping ps x ps patches, columns
+        # ordered (kh, kw, ci), zero padded to a multiple of 32) and reduced over all tokens by the split-K GEMM -- 5x faster
+        # than the SIMT stem_wgrad kernel at 1024^2 (0.25 vs 1.15 ms per step)
+        N, Cin, H, W = x.shape
+        ps = ctx.ps
+        K = Cin * ps * ps
+        Kp = (K + 31) // 32 * 32
+        if C0 % 8 == 0:
+            col, _, _ = ops.im2col(x, N=N, H=H, W=W, Cin=Cin, ks=ps, stride=ps, pad=0, Kp=Kp, nchw=True)
+            dw2 = torch.zeros((C0, Kp), device=x.device, dtype=torch.float32)
+            ops.linear_wgrad(du, col, dw2)
+            db = torch.zeros((C0,), device=x.device, dtype=torch.float32)
+            ops.colsum(du, db, rows=T, Cc=C0)
+            dw = dw2[:, :K].reshape(C0, ps, ps, Cin).permute(0, 3, 1, 2).contiguous()
+            return None, dw, db, dlnw, dlnb, None, None
         dwt = torch.zeros((K, C0), device=x.device, dtype=torch.float32)
         db = torch.zeros((C0,), device=x.device, dtype=torch.float32)
         ops.stem_wgrad(x, du, dwt, db, ctx.ps)

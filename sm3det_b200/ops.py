@@ -206,7 +206,7 @@ def linear_wgrad(dy, x, dw, *, rows=None, x_row_index=None, row_scale=None, segs
     tiles = ((N + 127) // 128) * (K // _pick_bn(K)) * num_groups
     # ~3 work items per SM (the per-expert segments are unequal), but at least 1024 reduction rows per split
     splits = -(-3 * num_sms() // max(1, tiles))
-    splits = max(1, min(64, splits, max(1, (R // num_groups) // 1024)))
+    splits = max(1, min(64 if tiles > 1 else 2 * num_sms(), splits, max(1, (R // num_groups) // 1024)))
     epi = EPI_ATOMIC | (EPI_ROWSCALE if row_scale is not None else 0)
     kw = {}
     if dy_packed is not None or x_packed is not None or ((N + 127) // 128) * (K // _pick_bn(K)) >= PACK_W_MIN_TILES:
