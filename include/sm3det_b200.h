@@ -166,7 +166,7 @@ int sm3_moe_combine(const float* expert_out, const int32_t* slot_of, const int32
                     int32_t T, int32_t C, int32_t k, void* stream);
 
 /* ---- fused activation + operand pre-split ---------------------------------------------------------
- * y = gelu(h) (mode 0) | da * gelu'(h) (mode 1) | h (mode 2) for the FFN hidden tensor, written directly as
+ * y = gelu(h) (mode 0) | da * gelu'(h) (mode 1) | h (mode 2) | both (mode 3: the whole backward in one pass over h) for the FFN hidden tensor, written directly as
  * the bf16 hi/lo tile images the following GEMMs bulk-copy (K-major image = A operand of GEMM2 / dgrad1,
  * MN-major image = wgrad operands), optionally also as fp32 and with per-group column sums (bias gradients).
  * Replaces nn.GELU() (convnext_moe.py:390,400) and its autograd backward; fp32 a / dh never reach HBM. */
@@ -174,6 +174,7 @@ typedef struct sm3_act_pack_args {
   const float* h; const float* da; int64_t R; int32_t W; int32_t mode;
   const int32_t* live_tiles; const int32_t* tile_group;
   float* out_f32; uint16_t* pack_k; uint16_t* pack_mn; int32_t mn_tile; float* colsum;
+  uint16_t* pack_mn2; int32_t mn_tile2;   /* mode 3 only: MN-major image of gelu(h) (wgrad2's B operand) */
 } sm3_act_pack_args;
 int sm3_act_pack(const sm3_act_pack_args* args, void* stream);
 

@@ -109,6 +109,7 @@ class ActPackArgs(C.Structure):
         ('h', c_f32p), ('da', c_f32p), ('R', C.c_int64), ('W', C.c_int32), ('mode', C.c_int32),
         ('live_tiles', c_i32p), ('tile_group', c_i32p),
         ('out_f32', c_f32p), ('pack_k', C.c_void_p), ('pack_mn', C.c_void_p), ('mn_tile', C.c_int32), ('colsum', c_f32p),
+        ('pack_mn2', C.c_void_p), ('mn_tile2', C.c_int32),
     ]
 
 

@@ -56,14 +56,14 @@ __global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, i
   auto load_row = [&](long long r) {
     if (r < r_end && row_live(r)) {
       nh0 = ldg_f4(a.h + r * a.W + col); nh1 = ldg_f4(a.h + r * a.W + col + 4);
-      if (MODE == 1) { nd0 = ldg_f4(a.da + r * a.W + col); nd1 = ldg_f4(a.da + r * a.W + col + 4); }
+      if (MODE == 1 || MODE == 3) { nd0 = ldg_f4(a.da + r * a.W + col); nd1 = ldg_f4(a.da + r * a.W + col + 4); }
     }
   };
   load_row(r_begin + rlane);
   for (long long r = r_begin + rlane; r < r_end; r += 8) {
-    float y[8];
+    float y[8], y2[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = 0.f;
+    for (int e = 0; e < 8; ++e) { y[e] = 0.f; y2[e] = 0.f; }
     const bool row_ok = row_live(r);
     const float4 h0 = nh0, h1 = nh1, d0 = nd0, d1 = nd1;
     load_row(r + 8);
@@ -76,6 +76,15 @@ __global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, i
         const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = dv[e] * gelu_grad_fast(hv[e]);
+      } else if (MODE == 3) {
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {          // Phi and exp(-x^2/2) shared by gelu and gelu'
+          float Phi, ex;
+          phi_parts(hv[e], Phi, ex);
+          y2[e] = hv[e] * Phi;
+          y[e] = dv[e] * fmaf(hv[e] * 0.39894228040143267794f, ex, Phi);
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = hv[e];
@@ -120,6 +129,16 @@ __global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, i
       *reinterpret_cast<uint4*>(img + o) = hi;
       *reinterpret_cast<uint4*>(img + pb_mn + o) = lo;
     }
+    if (MODE == 3) {          // second MN-major image: gelu(h), tile width mn_tile2
+      uint4 hi2, lo2;
+      split8(y2, hi2, lo2);
+      const uint32_t pb2 = gemm::plane_bytes(a.mn_tile2, true);
+      const int mt = col / a.mn_tile2; const uint32_t mc = (uint32_t)((col % a.mn_tile2) >> 3);
+      uint8_t* img = reinterpret_cast<uint8_t*>(a.pack_mn2) + ((long long)mt * kblocks_mn + (r >> 5)) * (2LL * pb2);
+      const uint32_t o = gemm::mnmajor_sw128_offset((uint32_t)(r & 31), mc);
+      *reinterpret_cast<uint4*>(img + o) = hi2;
+      *reinterpret_cast<uint4*>(img + pb2 + o) = lo2;
+    }
   }
   if (CS) {
     // combine the 8 row lanes of the block (same group at the end of the band in all but pathological cases:
@@ -150,7 +169,9 @@ __global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, i
 
 int act_pack(const ActPackArgs& a, cudaStream_t stream) {
   SM3_REQUIRE(a.h && a.R > 0 && a.W > 0 && a.W % 8 == 0, SM3_ERR_INVALID_ARG, "act_pack: bad argument (W must be a multiple of 8)");
-  SM3_REQUIRE(a.mode >= 0 && a.mode <= 2 && (a.mode != 1 || a.da), SM3_ERR_INVALID_ARG, "act_pack: mode/da");
+  SM3_REQUIRE(a.mode >= 0 && a.mode <= 3 && ((a.mode != 1 && a.mode != 3) || a.da), SM3_ERR_INVALID_ARG, "act_pack: mode/da");
+  SM3_REQUIRE(a.mode != 3 || (a.pack_mn2 && a.mn_tile2 >= 32 && a.mn_tile2 <= 256 && a.mn_tile2 % 32 == 0), SM3_ERR_INVALID_ARG,
+              "act_pack: mode 3 needs pack_mn2 / mn_tile2");
   SM3_REQUIRE(!a.pack_mn || (a.mn_tile >= 32 && a.mn_tile <= 256 && a.mn_tile % 32 == 0), SM3_ERR_INVALID_ARG, "act_pack: mn_tile");
   SM3_REQUIRE(a.pack_k || a.pack_mn || a.out_f32 || a.colsum, SM3_ERR_INVALID_ARG, "act_pack: no output requested");
   const long long R_pad = (a.R + 31) / 32 * 32;
@@ -169,6 +190,7 @@ int act_pack(const ActPackArgs& a, cudaStream_t stream) {
   } while (0)
   if (a.mode == 0) SM3_ACT_LAUNCH(0);
   else if (a.mode == 1) SM3_ACT_LAUNCH(1);
+  else if (a.mode == 3) SM3_ACT_LAUNCH(3);
   else SM3_ACT_LAUNCH(2);
 #undef SM3_ACT_LAUNCH
   return check_launch("act_pack_kernel");

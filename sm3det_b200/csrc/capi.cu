@@ -119,6 +119,7 @@ int sm3_act_pack(const sm3_act_pack_args* a, void* stream) {
   ActPackArgs r{};
   r.h = a->h; r.da = a->da; r.R = a->R; r.W = a->W; r.mode = a->mode; r.live_tiles = a->live_tiles; r.tile_group = a->tile_group;
   r.out_f32 = a->out_f32; r.pack_k = a->pack_k; r.pack_mn = a->pack_mn; r.mn_tile = a->mn_tile; r.colsum = a->colsum;
+  r.pack_mn2 = a->pack_mn2; r.mn_tile2 = a->mn_tile2;
   return act_pack(r, S(stream));
 }
 int sm3_moe_combine_bwd(const float* dout, const float* o, const int32_t* slot_of, const int32_t* top_idx,

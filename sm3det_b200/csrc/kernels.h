@@ -104,7 +104,7 @@ struct ActPackArgs {
   const float* h;            // [R, W] FFN hidden pre-activation
   const float* da;           // [R, W] upstream gradient (mode 1) or null
   long long R; int W;
-  int mode;                  // 0: gelu(h)   1: da * gelu'(h)   2: h
+  int mode;                  // 0: gelu(h)   1: da * gelu'(h)   2: h   3: mode 1 + gelu(h) into pack_mn2 (one pass)
   const int* live_tiles;     // optional device scalar: only rows < live_tiles*128 hold data (MoE pair space)
   const int* tile_group;     // optional: group (expert) of each 128-row tile, for per-group column sums
   float* out_f32;            // optional [R, W]
@@ -112,6 +112,8 @@ struct ActPackArgs {
   unsigned short* pack_mn;   // optional MN-major image (reduction index = row)
   int mn_tile;               // tile width of pack_mn (128 for an A operand, the GEMM tile width for B)
   float* colsum;             // optional [groups][W], accumulated
+  unsigned short* pack_mn2;  // mode 3: MN-major image of gelu(h) with tile width mn_tile2
+  int mn_tile2;
 };
 int act_pack(const ActPackArgs& a, cudaStream_t stream);
 

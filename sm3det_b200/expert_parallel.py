@@ -224,11 +224,10 @@ class EPMoEBlockFn(Function):
         if R_d > 0:
             dor = ops.gather_rows_peer(B['do_ptrs'], P['src_rank'], P['src_slot'], rows=R_d, Cc=C)
             da = ops.linear_dgrad(dor, w2, grouped=grouped, w_group_stride=4 * C * C, packed=ctx.packs.get('w2_t'))
-            dh_k, dh_mn, _ = ops.act_pack(h, rows=R_d, width=4 * C, mode=ops.ACT_DGELU, da=da, want_k=True, mn_tile=128,
-                                          colsum=db1s[own:own + E_loc], live_tiles=P['num_tiles'], tile_group=P['tile_group'])
+            # one pass over h: dh = da * gelu'(h) as dgrad1's / wgrad1's operands (+ db1) and a = gelu(h) as wgrad2's operand
+            dh_k, dh_mn, a_mn = ops.act_pack(h, rows=R_d, width=4 * C, mode=ops.ACT_BWD, da=da, want_k=True, mn_tile=128,
+                                          mn_tile2=ops._pick_bn(4 * C), colsum=db1s[own:own + E_loc], live_tiles=P['num_tiles'], tile_group=P['tile_group'])
             del da
-            _, a_mn, _ = ops.act_pack(h, rows=R_d, width=4 * C, mode=ops.ACT_GELU, mn_tile=ops._pick_bn(4 * C),
-                                      live_tiles=P['num_tiles'])
             ops.linear_wgrad(dor, None, dw2s[own:own + E_loc], rows=R_d, segs=segs, num_groups=E_loc, x_packed=a_mn)
             del a_mn
             ops.colsum(dor, db2s[own:own + E_loc], rows=R_d, Cc=C, segs=segs, groups=E_loc)

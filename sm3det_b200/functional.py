@@ -86,7 +86,9 @@ class DownsampleFn(Function):
         _, stats = ops.layernorm_fwd(x, lnw, lnb, eps, tokens=T, C=C, out=xn, out_mode=LN_PATCH2, H=H, W=W,
                                      save_stats=train)
         w2 = w.permute(0, 2, 3, 1).reshape(Co, 4 * C).contiguous()      # [Co, (kh, kw, ci)]
-        y = ops.linear_fwd(xn, w2, b)          # w2 is a per-call re-ordered copy: packed on the fly by the producers
+        # w2 is a per-call re-ordered copy of the conv weight: split it once here (a few us) so both operands take the
+        # bulk-copy main loop (4x the throughput of the in-kernel split on these shapes)
+        y = ops.linear_fwd(xn, w2, b, packed=ops.pack_weight(w2, transposed=False))
         if train:
             ctx.save_for_backward(x, stats, xn, lnw, w2)
             ctx.dims = (N, H, W, C, Co)
@@ -98,7 +100,7 @@ class DownsampleFn(Function):
         N, H, W, C, Co = ctx.dims
         T = N * H * W
         dy2 = dy.contiguous().view(T // 4, Co)
-        dxn = ops.linear_dgrad(dy2, w2)
+        dxn = ops.linear_dgrad(dy2, w2, packed=ops.pack_weight(w2, transposed=True))
         dw2 = torch.zeros_like(w2)
         ops.linear_wgrad(dy2, xn, dw2)
         db = torch.zeros((Co,), device=x.device, dtype=torch.float32)
@@ -189,10 +191,10 @@ class DenseBlockFn(Function):
                               packed=ops.pack_weight(w2g, transposed=True))
         # dh = da * gelu'(h) goes straight into the two operand images (dgrad1's A, wgrad1's A) + db1 column sums
         db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
-        dh_k, dh_mn, _ = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_DGELU, da=da, want_k=True, mn_tile=128,
-                                      colsum=db1)
+        # one pass over h: dh = da * gelu'(h) as dgrad1's / wgrad1's operands (+ db1) and a = gelu(h) as wgrad2's operand
+        dh_k, dh_mn, a_mn = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_BWD, da=da, want_k=True, mn_tile=128,
+                                      mn_tile2=ops._pick_bn(4 * C), colsum=db1)
         del da
-        _, a_mn, _ = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_GELU, mn_tile=ops._pick_bn(4 * C))
         dzs = dz if rs is None else ops.scale_rows(dz, row_scale=rs)
         dw2 = torch.zeros_like(w2)
         ops.linear_wgrad(dzs, None, dw2, rows=T, row_scale=gamma, x_packed=a_mn)
@@ -278,11 +280,10 @@ class MoEBlockFn(Function):
         # experts (grouped over the padded expert segments)
         da = ops.linear_dgrad(d_o, w2, grouped=grouped, w_group_stride=4 * C * C, packed=ctx.packs.get('w2_t'))
         db1s = torch.zeros((E, 4 * C), device=dev, dtype=torch.float32)
-        dh_k, dh_mn, _ = ops.act_pack(h, rows=R, width=4 * C, mode=ops.ACT_DGELU, da=da, want_k=True, mn_tile=128,
-                                      colsum=db1s, live_tiles=num_m_tiles, tile_group=tile_group)
+        # one pass over h: dh = da * gelu'(h) as dgrad1's / wgrad1's operands (+ db1) and a = gelu(h) as wgrad2's operand
+        dh_k, dh_mn, a_mn = ops.act_pack(h, rows=R, width=4 * C, mode=ops.ACT_BWD, da=da, want_k=True, mn_tile=128,
+                                      mn_tile2=ops._pick_bn(4 * C), colsum=db1s, live_tiles=num_m_tiles, tile_group=tile_group)
         del da
-        _, a_mn, _ = ops.act_pack(h, rows=R, width=4 * C, mode=ops.ACT_GELU, mn_tile=ops._pick_bn(4 * C),
-                                  live_tiles=num_m_tiles)
         dw2s = torch.zeros((E, C, 4 * C), device=dev, dtype=torch.float32)
         ops.linear_wgrad(d_o, None, dw2s, rows=R, segs=segs, num_groups=E, x_packed=a_mn)
         del a_mn

@@ -105,12 +105,14 @@ def pack_act(x, *, rows, cols, mn_major, tile=128, row_index=None, ld=None):
     return out
 
 
-ACT_GELU, ACT_DGELU, ACT_COPY = 0, 1, 2
+ACT_GELU, ACT_DGELU, ACT_COPY, ACT_BWD = 0, 1, 2, 3
 
 
 def act_pack(h, *, rows, width, mode, da=None, want_k=False, mn_tile=0, want_f32=False, colsum=None, live_tiles=None,
-             tile_group=None):
-    """Fused activation + pre-split (sm3_act_pack).  Returns (pack_k, pack_mn, out_f32); absent outputs are None."""
+             tile_group=None, mn_tile2=0):
+    """Fused activation + pre-split (sm3_act_pack).  Returns (pack_k, pack_mn, out_f32); absent outputs are None.
+    mode=ACT_BWD (needs mn_tile2): one pass over h emits da*gelu'(h) as pack_k / pack_mn AND gelu(h) as a second MN image;
+    returns (pack_k, pack_mn, pack_mn2)."""
     lib = _lib.load()
     dev = h.device
     a = _lib.ActPackArgs()
@@ -125,7 +127,13 @@ def act_pack(h, *, rows, width, mode, da=None, want_k=False, mn_tile=0, want_f32
     a.live_tiles = _pi(live_tiles); a.tile_group = _pi(tile_group)
     a.out_f32 = _p(of); a.pack_k = None if pk is None else pk.data_ptr(); a.pack_mn = None if pm is None else pm.data_ptr()
     a.mn_tile = mn_tile; a.colsum = _p(colsum)
+    pm2 = None
+    if mode == ACT_BWD:
+        pm2 = torch.empty((lib.sm3_gemm_packed_act_elems(rows, width, 1, mn_tile2),), device=dev, dtype=torch.int16)
+        a.pack_mn2 = pm2.data_ptr(); a.mn_tile2 = mn_tile2
     _lib.check(lib.sm3_act_pack(C.byref(a), _stream()), 'sm3_act_pack')
+    if mode == ACT_BWD:
+        return pk, pm, pm2
     return pk, pm, of
 
 
