@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
   const int P = 32 * PJ, PR = a.P, E = a.E, C = a.C, k = a.k;   // PR = real width; padding columns are zero
   float* s_p = smem;                         // [RT][P+1]   projected tokens
   float* s_sim = s_p + RT * (P + 1);         // [E][P+1]    column-normalised sim matrix
-  float* s_a = s_sim + E * (P + 1);          // [RT][R_KC+1]
-  float* s_b = s_a + RT * (R_KC + 1);        // [R_KC][P+1]
+  float* s_a = s_sim + E * (P + 1);          // [R_KC][RT+2]  (8-byte aligned rows: token pairs are read as one LDS.64)
+  s_a += ((RT + E) * (P + 1)) & 1;           // (RT+E)*(P+1) floats precede it: keep the pairs 8-byte aligned for odd E
+  float* s_b = s_a + R_KC * (RT + 2);        // [R_KC][P+1]
   float* s_red = s_b + R_KC * (P + 1);       // [8][3*R_MAXE]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t0 = (long long)blockIdx.x * RT;
@@ -42,34 +43,39 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
   }
 
   // ---- projection: p[t, :] = Wp v[t] + bp  (fp32 FMA; thread tile 8 tokens x PJ outputs) --------
-  float acc[8][PJ];
+  unsigned long long acc2[4][PJ];            // (token 2i, token 2i+1) x output j
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < PJ; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < PJ; ++j) acc2[i][j] = 0ull;
   for (int k0 = 0; k0 < C; k0 += R_KC) {
     __syncthreads();
     for (int idx = tid; idx < RT * R_KC; idx += 256) {
       const int tt = idx / R_KC, kk = idx % R_KC;
       const long long t = t0 + tt;
-      s_a[tt * (R_KC + 1) + kk] = (t < a.T) ? __ldg(a.v + t * C + k0 + kk) : 0.f;
+      s_a[kk * (RT + 2) + tt] = (t < a.T) ? __ldg(a.v + t * C + k0 + kk) : 0.f;    // [kk][token]: token pairs are adjacent
     }
     for (int idx = tid; idx < P * R_KC; idx += 256) {
       const int p = idx / R_KC, kk = idx % R_KC;
       s_b[kk * (P + 1) + p] = (p < PR) ? __ldg(a.wp + (long long)p * C + k0 + kk) : 0.f;
     }
     __syncthreads();
+    // FFMA2 (fma.rn.f32x2 = two IEEE fp32 FMAs per lane per issue, bit-identical to fmaf): accumulators are token pairs
 #pragma unroll 4
     for (int kk = 0; kk < R_KC; ++kk) {
-      float av[8], bv[PJ];
+      unsigned long long av2[4], bv2[PJ];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) av[i] = s_a[(warp * 8 + i) * (R_KC + 1) + kk];
+      for (int i = 0; i < 4; ++i) av2[i] = *reinterpret_cast<const unsigned long long*>(s_a + kk * (RT + 2) + warp * 8 + 2 * i);
 #pragma unroll
-      for (int j = 0; j < PJ; ++j) bv[j] = s_b[kk * (P + 1) + lane + 32 * j];
+      for (int j = 0; j < PJ; ++j) {
+        const unsigned int b = __float_as_uint(s_b[kk * (P + 1) + lane + 32 * j]);
+        bv2[j] = (unsigned long long)b | ((unsigned long long)b << 32);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < PJ; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < PJ; ++j)
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(av2[i]), "l"(bv2[j]));
     }
   }
 #pragma unroll
@@ -78,7 +84,8 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
     const float bj = pin ? __ldg(a.bp + lane + 32 * j) : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float pv = pin ? acc[i][j] + bj : 0.f;
+      const float acc_ij = __uint_as_float((unsigned int)(acc2[i >> 1][j] >> ((i & 1) * 32)));
+      const float pv = pin ? acc_ij + bj : 0.f;
       s_p[(warp * 8 + i) * (P + 1) + lane + 32 * j] = pv;
       const long long t = t0 + warp * 8 + i;
       if (a.p_out && pin && t < a.T) a.p_out[t * PR + lane + 32 * j] = pv;
@@ -209,7 +216,7 @@ int moe_router(const RouterArgs& a, cudaStream_t stream) {
   SM3_REQUIRE(!a.noise || a.w_noise, SM3_ERR_INVALID_ARG, "moe_router: noise needs w_noise");
   const int soft = (a.noise && a.k < a.E) ? 1 : 0;
   const int P = (a.P + 31) / 32 * 32, E = a.E;
-  const size_t smem = sizeof(float) * ((size_t)RT * (P + 1) + (size_t)E * (P + 1) + RT * (R_KC + 1) + (size_t)R_KC * (P + 1) + 8 * 3 * R_MAXE);
+  const size_t smem = sizeof(float) * ((size_t)RT * (P + 1) + (size_t)E * (P + 1) + R_KC * (RT + 2) + 1 + (size_t)R_KC * (P + 1) + 8 * 3 * R_MAXE);
   const int blocks = router_blocks(a.T);
 #define SM3_ROUTER_CASE(PJ)                                                                                   \
   case PJ:                                                                                                    \

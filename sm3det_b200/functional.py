@@ -181,10 +181,13 @@ class DenseBlockFn(Function):
         dout = dout.contiguous()
         dz = dout.view(T, C)
         dev = x.device
-        dgamma = torch.zeros((C,), device=dev, dtype=torch.float32)
-        ops.colsum(dz, dgamma, rows=T, Cc=C, b=y2, row_scale=rs)
-        csum = torch.zeros((C,), device=dev, dtype=torch.float32)
-        ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
+        if rs is None:
+            csum, dgamma = ops.colstat(dz, rows=T, Cc=C, y=y2)            # one pass: sum dz and sum dz * y2
+        else:
+            dgamma = torch.zeros((C,), device=dev, dtype=torch.float32)
+            ops.colsum(dz, dgamma, rows=T, Cc=C, b=y2, row_scale=rs)
+            csum = torch.zeros((C,), device=dev, dtype=torch.float32)
+            ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
         db2 = csum * gamma
         w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
         da = ops.linear_dgrad(dz, w2g, epilogue=(EPI_ROWSCALE if rs is not None else 0), row_scale=rs,
