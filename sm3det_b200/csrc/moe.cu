@@ -22,7 +22,7 @@ __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log
 __device__ __forceinline__ float normal_cdf(float v) { return 0.5f * (1.0f + erff(v * 0.70710678118654752440f)); }
 
 template <int PJ>  // padded projection width 32 * PJ >= a.P
-__global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int soft_load) {
+__global__ void __launch_bounds__(256, 2) moe_router_kernel(const RouterArgs a, int soft_load) {
   extern __shared__ float smem[];
   const int P = 32 * PJ, PR = a.P, E = a.E, C = a.C, k = a.k;   // PR = real width; padding columns are zero
   float* s_p = smem;                         // [RT][P+1]   projected tokens
@@ -48,18 +48,45 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const RouterArgs a, int
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < PJ; ++j) acc2[i][j] = 0ull;
+  // Staging is software-pipelined: the global loads of k-chunk i+1 (8 KB of tokens + P x 128 B of Wp per block) are in
+  // flight in registers while chunk i is multiplied -- the un-pipelined version spent most of its time in `long
+  // scoreboard` at the staging stores (profiles/r01_ncu_router_before.txt).
+  constexpr int NLD = 2 + PJ;                      // float4 per thread per chunk: (RT + 32*PJ) rows x 8 float4 / 256 threads
+  float4 pre[NLD];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int idx = tid + 256 * q, row = idx >> 3, c4 = (idx & 7) * 4;
+      float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < RT) {
+        const long long t = t0 + row;
+        if (t < a.T) v4 = ldg_f4(a.v + t * C + k0 + c4);
+      } else if (row - RT < PR) {
+        v4 = ldg_f4(a.wp + (long long)(row - RT) * C + k0 + c4);
+      }
+      pre[q] = v4;
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int idx = tid + 256 * q, row = idx >> 3, c4 = (idx & 7) * 4;
+      const float e4[4] = {pre[q].x, pre[q].y, pre[q].z, pre[q].w};
+      if (row < RT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_a[(c4 + e) * (RT + 2) + row] = e4[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_b[(c4 + e) * (P + 1) + row - RT] = e4[e];
+      }
+    }
+  };
+  gload(0);
   for (int k0 = 0; k0 < C; k0 += R_KC) {
+    __syncthreads();                                // previous chunk fully consumed
+    sstore();
     __syncthreads();
-    for (int idx = tid; idx < RT * R_KC; idx += 256) {
-      const int tt = idx / R_KC, kk = idx % R_KC;
-      const long long t = t0 + tt;
-      s_a[kk * (RT + 2) + tt] = (t < a.T) ? __ldg(a.v + t * C + k0 + kk) : 0.f;    // [kk][token]: token pairs are adjacent
-    }
-    for (int idx = tid; idx < P * R_KC; idx += 256) {
-      const int p = idx / R_KC, kk = idx % R_KC;
-      s_b[kk * (P + 1) + p] = (p < PR) ? __ldg(a.wp + (long long)p * C + k0 + kk) : 0.f;
-    }
-    __syncthreads();
+    if (k0 + R_KC < C) gload(k0 + R_KC);
     // FFMA2 (fma.rn.f32x2 = two IEEE fp32 FMAs per lane per issue, bit-identical to fmaf): accumulators are token pairs
 #pragma unroll 4
     for (int kk = 0; kk < R_KC; ++kk) {
