@@ -5,7 +5,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall
 SRC := sm3det_b200/csrc
 OBJ := build/obj
 LIB := sm3det_b200/lib/libsm3det_b200.so
-SRCS := common.cu gemm_tc.cu norm.cu stencil.cu moe.cu reduce.cu act.cu lsk.cu capi.cu
+SRCS := common.cu gemm_tc.cu norm.cu stencil.cu moe.cu reduce.cu act.cu lsk.cu neck.cu capi.cu
 OBJS := $(SRCS:%.cu=$(OBJ)/%.o)
 
 all: $(LIB)

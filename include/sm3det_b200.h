@@ -261,6 +261,16 @@ int sm3_im2col(const float* x, float* col, int32_t N, int32_t H, int32_t W, int3
 int sm3_col2im(const float* dcol, float* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
                int32_t pad, int32_t Kp, int32_t nchw, void* stream);
 
+/* ---- MultitaskFPN (the consumer of the 4-tuple; mmrotate/models/necks/Multitask_FPN.py:108-162) -----------------
+ * Lateral 1x1 / output 3x3 convolutions = sm3_im2col + sm3_gemm.  sm3_upsample_add: laterals[i-1] +
+ * F.interpolate(laterals[i], size=prev_shape, mode='nearest') :123-134 (NHWC) and its backward into the coarse level.
+ * sm3_transpose_batched: out[b,c,r] = in[b,r,c] -- NHWC <-> NCHW conversion of the returned levels. */
+int sm3_upsample_add(const float* a, const float* b, float* out, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w,
+                     int32_t C, void* stream);
+int sm3_upsample_add_bwd(const float* d, float* db, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, int32_t C,
+                         void* stream);
+int sm3_transpose_batched(const float* in, float* out, int32_t B, int32_t R, int32_t Cc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

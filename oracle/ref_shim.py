@@ -116,33 +116,49 @@ def _install_shims():
     _mod("timm.models.layers", DropPath=_DropPath, trunc_normal_=nn.init.trunc_normal_,
          to_2tuple=to_2tuple)
     _mod("mmengine"); _mod("mmengine.runner")
-    _mod("mmengine.model", ModuleList=nn.ModuleList, Sequential=nn.Sequential)
+    _mod("mmengine.model", ModuleList=nn.ModuleList, Sequential=nn.Sequential, BaseModule=_BaseModule)
     _mod("mmengine.logging", MMLogger=type("MMLogger", (), {
         "get_current_instance": staticmethod(lambda: None)}))
     _mod("mmengine.runner.checkpoint", CheckpointLoader=type("CheckpointLoader", (), {}))
+    class ConvModule(nn.Module):
+        """mmcv.cnn.ConvModule with norm_cfg = act_cfg = None (what MultitaskFPN builds in every SM3Det config)."""
+
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, conv_cfg=None, norm_cfg=None,
+                     act_cfg=None, inplace=False):
+            super().__init__()
+            assert conv_cfg is None and norm_cfg is None and act_cfg is None
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding)
+
+        def forward(self, x):
+            return self.conv(x)
+
+    def auto_fp16(*a, **k):
+        return lambda f: f
+
     _mod("mmcv")
-    _mod("mmcv.cnn", build_activation_layer=build_activation_layer,
+    _mod("mmcv.cnn", ConvModule=ConvModule, build_activation_layer=build_activation_layer,
          build_norm_layer=build_norm_layer, constant_init=constant_init,
          trunc_normal_init=trunc_normal_init, normal_init=normal_init)
     _mod("mmcv.cnn.utils")
     _mod("mmcv.cnn.utils.weight_init", constant_init=constant_init, normal_init=normal_init,
          trunc_normal_init=trunc_normal_init)
-    _mod("mmcv.runner", BaseModule=_BaseModule, _load_checkpoint=None, load_state_dict=None)
+    _mod("mmcv.runner", BaseModule=_BaseModule, _load_checkpoint=None, load_state_dict=None, auto_fp16=auto_fp16)
     _mod("mmcv.utils", to_2tuple=to_2tuple)
     _mod("mmrotate"); _mod("mmrotate.models"); _mod("mmrotate.models.backbones")
-    _mod("mmrotate.models.builder", ROTATED_BACKBONES=_REGISTRY)
+    _mod("mmrotate.models.necks")
+    _mod("mmrotate.models.builder", ROTATED_BACKBONES=_REGISTRY, ROTATED_NECKS=_REGISTRY)
     _mod("mmrotate.utils", get_root_logger=lambda *a, **k: None)
 
 
-def load_reference_module(name="convnext_moe"):
-    """Execute ``<reference>/mmrotate/models/backbones/<name>.py`` in place and return the module."""
+def load_reference_module(name="convnext_moe", package="backbones"):
+    """Execute ``<reference>/mmrotate/models/<package>/<name>.py`` in place and return the module."""
     if not reference_available():
         raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
-    full = f"mmrotate.models.backbones.{name}"
+    full = f"mmrotate.models.{package}.{name}"
     if full in sys.modules and getattr(sys.modules[full], "__file__", None):
         return sys.modules[full]
     _install_shims()
-    path = os.path.join(REFERENCE_ROOT, "mmrotate/models/backbones", name + ".py")
+    path = os.path.join(REFERENCE_ROOT, "mmrotate/models", package, name + ".py")
     spec = importlib.util.spec_from_file_location(full, path)
     mod = importlib.util.module_from_spec(spec)
     sys.modules[full] = mod

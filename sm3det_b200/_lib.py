@@ -86,6 +86,9 @@ SIGNATURES = {
     'sm3_scale_rows': [_P, _P, _P, _P, _I64, _I32, _P],
     'sm3_moe_router_bwd': [_P, _P],
     'sm3_gather_rows_peer': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    'sm3_upsample_add': [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    'sm3_upsample_add_bwd': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    'sm3_transpose_batched': [_P, _P, _I32, _I32, _I32, _P],
     # LSKNet-MoE
     'sm3_dwconv_fwd': [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     'sm3_dwconv_wgrad': [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],

@@ -204,4 +204,16 @@ int sm3_col2im(const float* dcol, float* dx, int32_t N, int32_t H, int32_t W, in
   return col2im(dcol, dx, N, H, W, Cin, ks, stride, pad, Kp, nchw, S(stream));
 }
 
+int sm3_upsample_add(const float* a, const float* b, float* out, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w,
+                     int32_t C, void* stream) {
+  return upsample_add(a, b, out, N, H, W, h, w, C, S(stream));
+}
+int sm3_upsample_add_bwd(const float* d, float* db, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w, int32_t C,
+                         void* stream) {
+  return upsample_add_bwd(d, db, N, H, W, h, w, C, S(stream));
+}
+int sm3_transpose_batched(const float* in, float* out, int32_t B, int32_t R, int32_t Cc, void* stream) {
+  return transpose_batched(in, out, B, R, Cc, S(stream));
+}
+
 }  // extern "C"

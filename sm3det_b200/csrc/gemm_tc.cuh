@@ -345,9 +345,21 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
       const Tile tl = decode_tile(p, t);
       if (tl.nkb() == 0) continue;
       if (cs_smem && tl.group != cs_group) { if (cs_group >= 0) cs_flush(cs_group); cs_group = tl.group; }
+      const int row0 = tl.m0 + quarter * 32;
+      // residual (shortcut) rows are prefetched one chunk ahead -- and for the first chunk before the accumulator is even
+      // ready -- so the epilogue no longer stalls a full HBM round trip per 32x16 block (profiles/r01_ncu_gemm_ffn2_stage0_specialised.txt)
+      float4 rr[4], rn[4];
+      auto load_resid = [&](int c_, float4 (&dst)[4]) {
+        const int n_ = tl.n0 + c_ * EPI_CW + c4;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = row0 + it * 8 + rl;
+          dst[it] = (row < p.M) ? ldg_f4(p.resid + (long long)row * p.ld_resid + n_) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if ((EPI & EPI_RESID) && cgrp < nchunks) load_resid(cgrp, rr);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row0 = tl.m0 + quarter * 32;
       float* dbase = p.D + (long long)tl.group * p.d_group_stride;
       const float* bias = p.bias ? p.bias + (long long)tl.group * p.bias_group_stride : nullptr;
       bool arrived = false;
@@ -368,7 +380,10 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
                        ::"r"(stage_base + (uint32_t)(lane * EPI_STAGE_ROW_FLOATS + 4 * j) * 4u),
                          "r"(vr[4 * j]), "r"(vr[4 * j + 1]), "r"(vr[4 * j + 2]), "r"(vr[4 * j + 3]) : "memory");
-        if (c + ncgrp < nchunks) tc_ld16_issue(tbase + (uint32_t)((c + ncgrp) * EPI_CW), vr);   // in flight while this chunk is written out
+        if (c + ncgrp < nchunks) {
+          tc_ld16_issue(tbase + (uint32_t)((c + ncgrp) * EPI_CW), vr);   // in flight while this chunk is written out
+          if (EPI & EPI_RESID) load_resid(c + ncgrp, rn);
+        }
         __syncwarp();
         const int n = tl.n0 + c * EPI_CW + c4;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), sv = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -394,10 +409,7 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           }
           x.x *= sv.x; x.y *= sv.y; x.z *= sv.z; x.w *= sv.w;
           if (EPI & EPI_ROWSCALE) { const float rs = __ldg(p.row_scale + row); x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs; }
-          if (EPI & EPI_RESID) {
-            const float4 rr = ldg_f4(p.resid + (long long)row * p.ld_resid + n);
-            x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-          }
+          if (EPI & EPI_RESID) { x.x += rr[it].x; x.y += rr[it].y; x.z += rr[it].z; x.w += rr[it].w; }
           cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
           float* dst = dbase + (long long)row * p.ldd + n;
           if (EPI & EPI_ATOMIC) {
@@ -405,6 +417,10 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
           } else {
             *reinterpret_cast<float4*>(dst) = x;
           }
+        }
+        if (EPI & EPI_RESID) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) rr[it] = rn[it];
         }
         if (EPI & EPI_COLSUM) {
           // lanes with the same (lane & 3) hold partial sums of the same 4 columns

@@ -152,4 +152,9 @@ int im2col(const float* x, float* col, int N, int H, int W, int Cin, int ks, int
 int col2im(const float* dcol, float* dx, int N, int H, int W, int Cin, int ks, int stride, int pad, int Kp, int nchw,
            cudaStream_t stream);
 
+// neck.cu (MultitaskFPN) ---------------------------------------------------------------------
+int upsample_add(const float* a, const float* b, float* out, int N, int H, int W, int h, int w, int C, cudaStream_t stream);
+int upsample_add_bwd(const float* d, float* db, int N, int H, int W, int h, int w, int C, cudaStream_t stream);
+int transpose_batched(const float* in, float* out, int B, int R, int Cc, cudaStream_t stream);
+
 }  // namespace sm3

@@ -520,3 +520,29 @@ def gather_rows_peer(bases, src_rank, src_row, *, rows, Cc, token_lists=None, sc
                                         _pi(src_rank), _pi(src_row), _p(scale), _p(out), rows, Cc, _stream()),
                'sm3_gather_rows_peer')
     return out
+
+
+# ---- MultitaskFPN ------------------------------------------------------------------------------------------------
+def upsample_add(a, b):
+    """a[N,H,W,C] + nearest-upsampled b[N,h,w,C]."""
+    lib = _lib.load()
+    N, H, W, Cc = a.shape
+    out = torch.empty_like(a)
+    _lib.check(lib.sm3_upsample_add(_p(a), _p(b), _p(out), N, H, W, b.shape[1], b.shape[2], Cc, _stream()), 'sm3_upsample_add')
+    return out
+
+
+def upsample_add_bwd(d, h, w):
+    lib = _lib.load()
+    N, H, W, Cc = d.shape
+    db = torch.empty((N, h, w, Cc), device=d.device, dtype=torch.float32)
+    _lib.check(lib.sm3_upsample_add_bwd(_p(d), _p(db), N, H, W, h, w, Cc, _stream()), 'sm3_upsample_add_bwd')
+    return db
+
+
+def transpose_batched(x, B, R, Cc, out_shape):
+    """out[b,c,r] = x[b,r,c] (x viewed as [B,R,Cc])."""
+    lib = _lib.load()
+    out = torch.empty(out_shape, device=x.device, dtype=torch.float32)
+    _lib.check(lib.sm3_transpose_batched(_p(x), _p(out), B, R, Cc, _stream()), 'sm3_transpose_batched')
+    return out
