@@ -116,101 +116,52 @@ __device__ __forceinline__ float2 unpack2(f32x2_t v) {
   return make_float2(__uint_as_float((uint32_t)v), __uint_as_float((uint32_t)(v >> 32)));
 }
 
-// Persistent, double-buffered forward / dgrad kernel: one 512-thread CTA per SM loops over (32 rows x 16 cols x 32 channels)
-// work items; the cp.async loads of item i+1 (38x22x32 halo tile, zero-filled outside the image) are in flight while item i
-// is computed, so the FMA pipe no longer idles during tile loads (the single-buffered version sat at 37 % FMA utilisation
-// with 3 CTAs/SM taking turns loading, profiles/r01_ncu_dwconv7_ffma2.txt).  lane = (row selector l/16, channel pair l%16):
-// a half-warp owns one output row and two channels per lane, so every LDS.64 / FFMA2 does the work of two scalar ones.
-constexpr int PT_H = 32;                 // output rows per item (16 warps x 2 half-warps)
-constexpr int PTI_H = PT_H + 6;          // input rows
-constexpr int P_THREADS = 512;
-
-__device__ __forceinline__ void dwp_issue_load(float* xs, const float* __restrict__ x, int n, int h0, int w0, int c0, int H,
-                                               int W, int C) {
-  for (int idx = threadIdx.x; idx < PTI_H * DTI * 8; idx += P_THREADS) {
-    const int q = idx & 7, pix = idx >> 3;
-    const int py = pix / DTI, px = pix - py * DTI;
-    const int hi = h0 + py - 3, wi = w0 + px - 3;
-    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(xs + pix * DCC + q * 4));
-    if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
-      const float* src = x + (((long long)n * H + hi) * W + wi) * C + c0 + q * 4;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    } else {
-      asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(P_THREADS, 1) dwconv7_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt,
-                                                                   const float* __restrict__ bias, const float* __restrict__ resid,
-                                                                   float* __restrict__ y, int N, int H, int W, int C, int tiles_w,
-                                                                   int tiles_h, int items) {
-  extern __shared__ float smem_dw[];                      // 2 x [PTI_H][DTI][DCC]
-  constexpr int BUF = PTI_H * DTI * DCC;
+// lane = (row selector l/16, channel pair l%16): a half-warp owns one output row of the 16x16 tile and two channels per
+// lane, so every LDS.64 / FFMA2 does the work of two of the scalar version's instructions.
+__global__ void __launch_bounds__(256) dwconv7_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                          const float* __restrict__ bias, const float* __restrict__ resid,
+                                                          float* __restrict__ y, int H, int W, int C, int tiles_w,
+                                                          int tiles_h) {
+  extern __shared__ float xs[];                           // [DTI][DTI][DCC]
+  const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
   const int cchunks = C / DCC;
+  const int n = blockIdx.y / cchunks, c0 = (blockIdx.y % cchunks) * DCC;
+  const int h0 = th * DT, w0 = tw * DT;
+  dw_load_tile(xs, x, n, h0, w0, c0, H, W, C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cp = lane & 15, r = warp * 2 + (lane >> 4);
-  auto decode = [&](int it, int& n, int& h0, int& w0, int& c0) {
-    const int tile = it % (tiles_w * tiles_h), rest = it / (tiles_w * tiles_h);
-    w0 = (tile % tiles_w) * DT; h0 = (tile / tiles_w) * PT_H;
-    c0 = (rest % cchunks) * DCC; n = rest / cchunks;
-  };
-  int buf = 0;
-  {
-    int n, h0, w0, c0;
-    if ((int)blockIdx.x < items) { decode(blockIdx.x, n, h0, w0, c0); dwp_issue_load(smem_dw, x, n, h0, w0, c0, H, W, C); }
-  }
-  for (int it = blockIdx.x; it < items; it += gridDim.x) {
-    int n, h0, w0, c0;
-    decode(it, n, h0, w0, c0);
-    const int nxt = it + gridDim.x;
-    if (nxt < items) {
-      int n2, h2, w2, c2;
-      decode(nxt, n2, h2, w2, c2);
-      dwp_issue_load(smem_dw + (buf ^ 1) * BUF, x, n2, h2, w2, c2, H, W, C);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();                                      // item `it` is resident in buffer `buf`
-    const float* xs = smem_dw + buf * BUF;
-    const int c = c0 + 2 * cp;
-    const int h = h0 + r;
-    if (h < H) {
-      const f32x2_t b2 = bias ? __ldg(reinterpret_cast<const f32x2_t*>(bias + c)) : 0ull;
-      f32x2_t acc[DT];
+  const int c = c0 + 2 * cp;
+  const int h = h0 + r;
+  if (h >= H) return;
+  const f32x2_t b2 = bias ? __ldg(reinterpret_cast<const f32x2_t*>(bias + c)) : 0ull;
+  f32x2_t acc[DT];
 #pragma unroll
-      for (int o = 0; o < DT; ++o) acc[o] = b2;
+  for (int o = 0; o < DT; ++o) acc[o] = b2;
 #pragma unroll 1
-      for (int i = 0; i < 7; ++i) {
-        f32x2_t wv[7];
+  for (int i = 0; i < 7; ++i) {
+    f32x2_t wv[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) wv[j] = __ldg(reinterpret_cast<const f32x2_t*>(wt + (i * 7 + j) * C + c));
-        const f32x2_t* xr = reinterpret_cast<const f32x2_t*>(xs + ((r + i) * DTI) * DCC) + cp;
+    for (int j = 0; j < 7; ++j) wv[j] = __ldg(reinterpret_cast<const f32x2_t*>(wt + (i * 7 + j) * C + c));
+    const f32x2_t* xr = reinterpret_cast<const f32x2_t*>(xs + ((r + i) * DTI) * DCC) + cp;
 #pragma unroll
-        for (int cc = 0; cc < DTI; ++cc) {
-          const f32x2_t v = xr[cc * (DCC / 2)];
+    for (int cc = 0; cc < DTI; ++cc) {
+      const f32x2_t v = xr[cc * (DCC / 2)];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            const int o = cc - j;
-            if (o >= 0 && o < DT) acc[o] = ffma2(v, wv[j], acc[o]);
-          }
-        }
-      }
-      const long long rowoff = (((long long)n * H + h) * W) * C + c;
-#pragma unroll
-      for (int o = 0; o < DT; ++o) {
-        const int w = w0 + o;
-        if (w < W) {
-          float2 v = unpack2(acc[o]);
-          if (resid) { const float2 rr = __ldg(reinterpret_cast<const float2*>(resid + rowoff + (long long)w * C)); v.x += rr.x; v.y += rr.y; }
-          *reinterpret_cast<float2*>(y + rowoff + (long long)w * C) = v;
-        }
+      for (int j = 0; j < 7; ++j) {
+        const int o = cc - j;
+        if (o >= 0 && o < DT) acc[o] = ffma2(v, wv[j], acc[o]);
       }
     }
-    __syncthreads();                                      // buffer `buf` may be overwritten by the load issued next iteration
-    buf ^= 1;
+  }
+  const long long rowoff = (((long long)n * H + h) * W) * C + c;
+#pragma unroll
+  for (int o = 0; o < DT; ++o) {
+    const int w = w0 + o;
+    if (w < W) {
+      float2 v = unpack2(acc[o]);
+      if (resid) { const float2 rr = __ldg(reinterpret_cast<const float2*>(resid + rowoff + (long long)w * C)); v.x += rr.x; v.y += rr.y; }
+      *reinterpret_cast<float2*>(y + rowoff + (long long)w * C) = v;
+    }
   }
 }
 
@@ -219,15 +170,13 @@ int dwconv7_fwd(const float* x, const float* wt, const float* bias, const float*
   SM3_REQUIRE(x && wt && y, SM3_ERR_INVALID_ARG, "dwconv7_fwd: null argument");
   SM3_REQUIRE(C % 4 == 0 && N > 0 && H > 0 && W > 0, SM3_ERR_UNSUPPORTED_SHAPE, "dwconv7_fwd: C=%d must be a multiple of 4", C);
   if (C % DCC == 0) {
-    const int tiles_w = (W + DT - 1) / DT, tiles_h = (H + PT_H - 1) / PT_H;
-    const size_t smem = (size_t)2 * PTI_H * DTI * DCC * sizeof(float);
+    const int tiles_w = (W + DT - 1) / DT, tiles_h = (H + DT - 1) / DT;
+    const size_t smem = (size_t)DTI * DTI * DCC * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(dwconv7_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    const long long items = (long long)tiles_w * tiles_h * N * (C / DCC);
-    SM3_REQUIRE(items < (1LL << 31), SM3_ERR_UNSUPPORTED_SHAPE, "dwconv7_fwd: tensor too large");
-    int grid = num_sms();
-    if (grid > items) grid = (int)items;
-    dwconv7_tile_kernel<<<grid, P_THREADS, smem, stream>>>(x, wt, bias, resid, y, N, H, W, C, tiles_w, tiles_h, (int)items);
+    SM3_REQUIRE((long long)N * (C / DCC) < 65536, SM3_ERR_UNSUPPORTED_SHAPE, "dwconv7_fwd: N*C/32 too large for grid.y");
+    dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(N * (C / DCC)));
+    dwconv7_tile_kernel<<<grid, 256, smem, stream>>>(x, wt, bias, resid, y, H, W, C, tiles_w, tiles_h);
     return check_launch("dwconv7_tile_kernel");
   }
   const int strips = (W + DW_WS - 1) / DW_WS;
