@@ -38,6 +38,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step')
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--expert-parallel', action='store_true',
+                    help='N > 1 only, not the headline config: shard the experts over the ranks (NVLink peer-memory dispatch)')
     ap.add_argument('--cpu-images', type=int, default=1, help='images in the bounded CPU sample')
     return ap.parse_args()
 
@@ -47,7 +49,7 @@ def workload_config(args, world):
                         f'{args.size}x{args.size}x3 synthetic SAR/RGB/IR 2:1:1, fp32, noisy_gating=False, drop_path=0',
             'arch': 'ConvNeXt-T', 'num_experts': 8, 'top_k': 2, 'moe_blocks': MODEL_KW['MoE_Block_inds'],
             'per_gpu_batch': args.batch, 'global_batch': args.batch * world, 'image': args.size,
-            'parallelism': f'dp{world}', 'l2': 'inputs and activations exceed L2 (>=100 MB per tensor); no flush needed'}
+            'parallelism': f'dp{world}' + ('+ep' if getattr(args, 'expert_parallel', False) and world > 1 else ''), 'l2': 'inputs and activations exceed L2 (>=100 MB per tensor); no flush needed'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -258,6 +260,9 @@ def run_ours(args):
     net.load_state_dict(sd, strict=True)
     net = net.cuda().train()
     model = net
+    if world > 1 and args.expert_parallel:
+        from sm3det_b200.expert_parallel import enable_expert_parallel
+        enable_expert_parallel(net, dist.new_group(list(range(world))))
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=False,
                                                           gradient_as_bucket_view=True)
@@ -339,15 +344,18 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        roof = gemm_roofline(net, dev_x, peaks)
-        net.zero_grad(set_to_none=True)
-        try:   # measured DRAM traffic of the GEMM launches of one step (ncu dram__bytes_read+write, profiles/)
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
-            roof['traffic'] = tr['bytes_per_launch']
-            roof['traffic_note'] = tr['note']
-        except Exception:
-            pass
-        roof_moe = moe_roofline(net, dev_x, peaks)
+        ep_mode = world > 1 and args.expert_parallel
+        roof = roof_moe = None
+        if not ep_mode:        # the instrumented extra passes are rank-0 only; expert parallelism needs every rank in each layer
+            roof = gemm_roofline(net, dev_x, peaks)
+            net.zero_grad(set_to_none=True)
+            try:   # measured DRAM traffic of the GEMM launches of one step (ncu dram__bytes_read+write, profiles/)
+                tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
+                roof['traffic'] = tr['bytes_per_launch']
+                roof['traffic_note'] = tr['note']
+            except Exception:
+                pass
+            roof_moe = moe_roofline(net, dev_x, peaks)
         line = {'metric': METRIC, 'value': B * world / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32 (bf16 hi+lo split operands on tcgen05, fp32 accumulate; SIMT fp32 elsewhere)',

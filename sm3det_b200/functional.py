@@ -294,7 +294,7 @@ class MoEBlockFn(Function):
         ops.colsum(d_o, db2s, rows=R, Cc=C, segs=segs, groups=E)
         dw1s = torch.zeros((E, 4 * C, C), device=dev, dtype=torch.float32)
         ops.linear_wgrad(None, v, dw1s, rows=R, x_row_index=pair_token, segs=segs, num_groups=E, dy_packed=dh_mn)
-        dxp = torch.zeros((R, C), device=dev, dtype=torch.float32)
+        dxp = torch.empty((R, C), device=dev, dtype=torch.float32)   # every row gather_sum reads (live slots) is written by the GEMM
         ops.linear_dgrad(None, w1, rows=R, a_packed=dh_k, out=dxp, grouped=grouped, w_group_stride=4 * C * C,
                          packed=ctx.packs.get('w1_t'))
         # router
