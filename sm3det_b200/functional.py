@@ -162,27 +162,20 @@ class DenseBlockFn(Function):
         u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
         # GEMM1 stores the pre-activation only; GELU runs in the HBM-bound act_pack kernel, which emits the result
         # directly as GEMM2's pre-split A operand (fp32 `a` never exists)
-        v_mn = None
-        if train and packs.get('w1') is not None and ops._pack_a_pays(4 * C, C):
-            # one pass over v emits both operand images: K-major for GEMM1 now, MN-major for wgrad1 in the backward
-            v_k, v_mn, _ = ops.act_pack(v, rows=T, width=C, mode=ops.ACT_COPY, want_k=True, mn_tile=ops._pick_bn(C))
-            h = ops.linear_fwd(None, w1, b1, rows=T, a_packed=v_k, packed=packs.get('w1'))
-            del v_k
-        else:
-            h = ops.linear_fwd(v, w1, b1, packed=packs.get('w1'))
+        h = ops.linear_fwd(v, w1, b1, packed=packs.get('w1'))
         a_k, _, _ = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_GELU, want_k=True)
         y2 = torch.empty((T, C), device=x.device, dtype=torch.float32) if train else None
         epi = EPI_COLSCALE | EPI_RESID | (EPI_ROWSCALE if row_scale is not None else 0) | (EPI_AUXSTORE if train else 0)
         out = ops.linear_fwd(None, w2, b2, rows=T, a_packed=a_k, epilogue=epi, aux_out=y2, col_scale=gamma,
                              row_scale=row_scale, resid=x.view(T, C), packed=packs.get('w2'))
         if train:
-            ctx.save_for_backward(x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, row_scale, v_mn)
+            ctx.save_for_backward(x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, row_scale)
             ctx.packs = packs
         return out.view(N, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, rs, v_mn = ctx.saved_tensors
+        x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, rs = ctx.saved_tensors
         N, H, W, C = x.shape
         T = N * H * W
         dout = dout.contiguous()
@@ -197,15 +190,8 @@ class DenseBlockFn(Function):
             ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
         db2 = csum * gamma
         w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
-        dz_mn = None
-        if rs is None and ops._pack_a_pays(4 * C, C):
-            # one pass over dz emits dgrad2's K-major and wgrad2's MN-major operand images
-            dz_k, dz_mn, _ = ops.act_pack(dz, rows=T, width=C, mode=ops.ACT_COPY, want_k=True, mn_tile=128)
-            da = ops.linear_dgrad(None, w2g, rows=T, a_packed=dz_k, packed=ops.pack_weight(w2g, transposed=True))
-            del dz_k
-        else:
-            da = ops.linear_dgrad(dz, w2g, epilogue=(EPI_ROWSCALE if rs is not None else 0), row_scale=rs,
-                                  packed=ops.pack_weight(w2g, transposed=True))
+        da = ops.linear_dgrad(dz, w2g, epilogue=(EPI_ROWSCALE if rs is not None else 0), row_scale=rs,
+                              packed=ops.pack_weight(w2g, transposed=True))
         # dh = da * gelu'(h) goes straight into the two operand images (dgrad1's A, wgrad1's A) + db1 column sums
         db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
         # one pass over h: dh = da * gelu'(h) as dgrad1's / wgrad1's operands (+ db1) and a = gelu(h) as wgrad2's operand
@@ -214,10 +200,10 @@ class DenseBlockFn(Function):
         del da
         dzs = dz if rs is None else ops.scale_rows(dz, row_scale=rs)
         dw2 = torch.zeros_like(w2)
-        ops.linear_wgrad(dzs, None, dw2, rows=T, row_scale=gamma, x_packed=a_mn, dy_packed=dz_mn)
-        del a_mn, dz_mn
+        ops.linear_wgrad(dzs, None, dw2, rows=T, row_scale=gamma, x_packed=a_mn)
+        del a_mn
         dw1 = torch.zeros_like(w1)
-        ops.linear_wgrad(None, v, dw1, rows=T, dy_packed=dh_mn, x_packed=v_mn)
+        ops.linear_wgrad(None, v, dw1, rows=T, dy_packed=dh_mn)
         dv = ops.linear_dgrad(None, w1, rows=T, a_packed=dh_k, packed=ctx.packs.get('w1_t'))
         dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
         return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
