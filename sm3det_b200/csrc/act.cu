@@ -30,12 +30,14 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// grid: (column-chunk groups of 32, row bands); block 256 = 32 chunk lanes x 8 row lanes
-template <int MODE, bool CS>
+// grid: (column-chunk groups of CLW, row bands); block 256 = CLW chunk lanes x 256/CLW row lanes.  CLW = 16 when the row has
+// an odd number of 16-chunk groups (W = 384: 48 chunks would leave half of the second 32-lane column idle).
+template <int MODE, bool CS, int CLW>
 __global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, int rows_per_band) {
-  __shared__ float s_cs[8][32 * 8 + 8];
-  const int cl = threadIdx.x & 31, rlane = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * 32 + cl;            // 8-column chunk index
+  constexpr int RL = 256 / CLW;                      // row lanes
+  __shared__ float s_cs[RL][CLW * 8 + 8];
+  const int cl = threadIdx.x & (CLW - 1), rlane = threadIdx.x / CLW;
+  const int chunk = blockIdx.x * CLW + cl;           // 8-column chunk index
   const int col = chunk * 8;
   const bool col_ok = col < a.W;
   const long long R_pad = (a.R + 31) / 32 * 32;      // images are padded to whole 32-row k-blocks
@@ -60,13 +62,13 @@ __global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, i
     }
   };
   load_row(r_begin + rlane);
-  for (long long r = r_begin + rlane; r < r_end; r += 8) {
+  for (long long r = r_begin + rlane; r < r_end; r += RL) {
     float y[8], y2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { y[e] = 0.f; y2[e] = 0.f; }
     const bool row_ok = row_live(r);
     const float4 h0 = nh0, h1 = nh1, d0 = nd0, d1 = nd1;
-    load_row(r + 8);
+    load_row(r + RL);
     if (row_ok) {
       const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
       if (MODE == 0) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256, 3) act_pack_kernel(const ActPackArgs a, i
         for (int e = 0; e < 8; ++e) {
           float t = 0.f;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) t += s_cs[w][cl * 8 + e];
+          for (int w = 0; w < RL; ++w) t += s_cs[w][cl * 8 + e];
           atomicAdd(a.colsum + col + e, t);
         }
       }
@@ -175,7 +177,9 @@ int act_pack(const ActPackArgs& a, cudaStream_t stream) {
   SM3_REQUIRE(!a.pack_mn || (a.mn_tile >= 32 && a.mn_tile <= 256 && a.mn_tile % 32 == 0), SM3_ERR_INVALID_ARG, "act_pack: mn_tile");
   SM3_REQUIRE(a.pack_k || a.pack_mn || a.out_f32 || a.colsum, SM3_ERR_INVALID_ARG, "act_pack: no output requested");
   const long long R_pad = (a.R + 31) / 32 * 32;
-  const int gx = (a.W / 8 + 31) / 32;
+  const int chunks_w = a.W / 8;
+  const int clw = (chunks_w % 32 != 0 && chunks_w % 16 == 0) ? 16 : 32;
+  const int gx = (chunks_w + clw - 1) / clw;
   long long bands = (long long)num_sms() * 8 / gx;
   if (bands < 1) bands = 1;
   long long rpb = (R_pad + bands - 1) / bands;
@@ -183,15 +187,17 @@ int act_pack(const ActPackArgs& a, cudaStream_t stream) {
   bands = (R_pad + rpb - 1) / rpb;
   dim3 grid((unsigned)gx, (unsigned)bands);
   const bool cs = a.colsum != nullptr;
+#define SM3_ACT_LAUNCH2(M, C_, W_) act_pack_kernel<M, C_, W_><<<grid, 256, 0, stream>>>(a, (int)rpb)
 #define SM3_ACT_LAUNCH(M)                                                          \
   do {                                                                             \
-    if (cs) act_pack_kernel<M, true><<<grid, 256, 0, stream>>>(a, (int)rpb);       \
-    else act_pack_kernel<M, false><<<grid, 256, 0, stream>>>(a, (int)rpb);         \
+    if (clw == 16) { if (cs) SM3_ACT_LAUNCH2(M, true, 16); else SM3_ACT_LAUNCH2(M, false, 16); }   \
+    else { if (cs) SM3_ACT_LAUNCH2(M, true, 32); else SM3_ACT_LAUNCH2(M, false, 32); }             \
   } while (0)
   if (a.mode == 0) SM3_ACT_LAUNCH(0);
   else if (a.mode == 1) SM3_ACT_LAUNCH(1);
   else if (a.mode == 3) SM3_ACT_LAUNCH(3);
   else SM3_ACT_LAUNCH(2);
+#undef SM3_ACT_LAUNCH2
 #undef SM3_ACT_LAUNCH
   return check_launch("act_pack_kernel");
 }
