@@ -43,11 +43,13 @@ __device__ __forceinline__ void dwg_load_tile(float* xs, const float* __restrict
   __syncthreads();
 }
 
+// lane = (row selector l/16, channel pair l%16); FFMA2 (fma.rn.f32x2) on channel pairs, as in stencil.cu's 7x7 kernel
 template <int KS, int DIL>
 __global__ void __launch_bounds__(256) dwconv_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, const float* __restrict__ resid,
                                                          float* __restrict__ y, int H, int W, int C, int tiles_w) {
   constexpr int R = DwGeom<KS, DIL>::R, TI = DwGeom<KS, DIL>::TI;
+  typedef unsigned long long f2;
   extern __shared__ float xs[];                           // [TI][TI][GCC]
   const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
   const int cchunks = C / GCC;
@@ -55,41 +57,38 @@ __global__ void __launch_bounds__(256) dwconv_tile_kernel(const float* __restric
   const int h0 = th * GT, w0 = tw * GT;
   dwg_load_tile<R, TI>(xs, x, n, h0, w0, c0, H, W, C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = c0 + lane;
-  const float b = bias ? __ldg(bias + c) : 0.f;
+  const int cp = lane & 15, r = warp * 2 + (lane >> 4);
+  const int c = c0 + 2 * cp;
+  const int h = h0 + r;
+  if (h >= H) return;
+  const f2 b2 = bias ? __ldg(reinterpret_cast<const f2*>(bias + c)) : 0ull;
+  f2 acc[GT];
+#pragma unroll
+  for (int o = 0; o < GT; ++o) acc[o] = b2;
 #pragma unroll 1
-  for (int rr = 0; rr < 2; ++rr) {
-    const int r = warp * 2 + rr;
-    const int h = h0 + r;
-    if (h >= H) break;
-    float acc[GT];
+  for (int i = 0; i < KS; ++i) {
+    f2 wv[KS];
 #pragma unroll
-    for (int o = 0; o < GT; ++o) acc[o] = b;
-#pragma unroll 1
-    for (int i = 0; i < KS; ++i) {
-      float wv[KS];
+    for (int j = 0; j < KS; ++j) wv[j] = __ldg(reinterpret_cast<const f2*>(wt + (i * KS + j) * C + c));
+    const f2* xr = reinterpret_cast<const f2*>(xs + ((r + i * DIL) * TI) * GCC) + cp;
 #pragma unroll
-      for (int j = 0; j < KS; ++j) wv[j] = __ldg(wt + (i * KS + j) * C + c);
-      const float* xr = xs + ((r + i * DIL) * TI) * GCC + lane;
+    for (int cc = 0; cc < TI; ++cc) {
+      const f2 v = xr[cc * (GCC / 2)];
 #pragma unroll
-      for (int cc = 0; cc < TI; ++cc) {
-        const float v = xr[cc * GCC];
-#pragma unroll
-        for (int j = 0; j < KS; ++j) {
-          const int o = cc - j * DIL;
-          if (o >= 0 && o < GT) acc[o] = fmaf(v, wv[j], acc[o]);
-        }
+      for (int j = 0; j < KS; ++j) {
+        const int o = cc - j * DIL;
+        if (o >= 0 && o < GT) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o]) : "l"(v), "l"(wv[j]));
       }
     }
-    const long long rowoff = (((long long)n * H + h) * W) * C + c;
+  }
+  const long long rowoff = (((long long)n * H + h) * W) * C + c;
 #pragma unroll
-    for (int o = 0; o < GT; ++o) {
-      const int w = w0 + o;
-      if (w < W) {
-        float v = acc[o];
-        if (resid) v += __ldg(resid + rowoff + (long long)w * C);
-        y[rowoff + (long long)w * C] = v;
-      }
+  for (int o = 0; o < GT; ++o) {
+    const int w = w0 + o;
+    if (w < W) {
+      float2 v = make_float2(__uint_as_float((uint32_t)acc[o]), __uint_as_float((uint32_t)(acc[o] >> 32)));
+      if (resid) { const float2 rr = __ldg(reinterpret_cast<const float2*>(resid + rowoff + (long long)w * C)); v.x += rr.x; v.y += rr.y; }
+      *reinterpret_cast<float2*>(y + rowoff + (long long)w * C) = v;
     }
   }
 }

@@ -99,7 +99,8 @@ class LinearFn(Function):
         w2 = w.view(w.shape[0], K)
         train = any(ctx.needs_input_grad)
         h = torch.empty((x2.shape[0], w2.shape[0]), device=x.device, dtype=torch.float32) if (gelu and train) else None
-        y = ops.linear_fwd(x2, w2, b, epilogue=EPI_GELU if gelu else 0, aux_out=h)
+        # weights are split per call (a few us; 1x1 conv weights are small) so both operands take the bulk-copy main loop
+        y = ops.linear_fwd(x2, w2, b, epilogue=EPI_GELU if gelu else 0, aux_out=h, packed=ops.pack_weight(w2, transposed=False))
         if train:
             ctx.save_for_backward(x2, w2, h)
             ctx.wshape, ctx.gelu, ctx.has_b = tuple(w.shape), gelu, b is not None
@@ -118,7 +119,7 @@ class LinearFn(Function):
             ops.colsum(dy2, db, rows=T, Cc=N)
         dw = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
         ops.linear_wgrad(dy2, x2, dw)
-        dx = ops.linear_dgrad(dy2, w2) if ctx.needs_input_grad[0] else None
+        dx = ops.linear_dgrad(dy2, w2, packed=ops.pack_weight(w2, transposed=True)) if ctx.needs_input_grad[0] else None
         return (None if dx is None else dx.view(*dy.shape[:-1], K)), dw.view(ctx.wshape), db, None
 
 
@@ -250,7 +251,7 @@ class PatchEmbedFn(Function):
         col, Ho, Wo = ops.im2col(x, N=N, H=H, W=W, Cin=Ci, ks=ks, stride=stride, pad=ks // 2, Kp=Kp, nchw=nchw)
         w2 = torch.zeros((Co, Kp), device=w.device, dtype=torch.float32)
         w2[:, :K] = w.permute(0, 2, 3, 1).reshape(Co, K)
-        y = ops.linear_fwd(col, w2, b)
+        y = ops.linear_fwd(col, w2, b, packed=ops.pack_weight(w2, transposed=False))
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(x, w2)
             ctx.geom = (N, H, W, Ci, Co, ks, stride, K, Kp, nchw, Ho, Wo)
@@ -270,7 +271,7 @@ class PatchEmbedFn(Function):
         ops.colsum(dy2, db, rows=T, Cc=Co)
         dx = None
         if ctx.needs_input_grad[0]:
-            dcol = ops.linear_dgrad(dy2, w2)
+            dcol = ops.linear_dgrad(dy2, w2, packed=ops.pack_weight(w2, transposed=True))
             dx = ops.col2im(dcol, N=N, H=H, W=W, Cin=Ci, ks=ks, stride=stride, pad=ks // 2, Kp=Kp, nchw=nchw)
         dw = dw2[:, :K].reshape(Co, ks, ks, Ci).permute(0, 3, 1, 2).contiguous()
         return dx, dw, db, None, None
