@@ -33,6 +33,19 @@ def _sync_active(sync):
     return bool(sync) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+def bn_batch_stats(s1, s2, n, running_mean, sync, group=None):
+    """(mean, biased var, n) of a (Sync)BatchNorm from the per-rank shifted sums s1 = sum(x - running_mean),
+    s2 = sum((x - running_mean)^2) over n local rows.  With ``sync`` the three are all-reduced first: the shift is the
+    running mean, identical on every rank, so the sums simply add.  Pure [C]-sized host-side glue (CPU-testable, gloo)."""
+    C = s1.numel()
+    if _sync_active(sync):
+        st = torch.cat([s1, s2, s1.new_tensor([float(n)])])
+        dist.all_reduce(st, group=group)
+        s1, s2, n = st[:C], st[C:2 * C], float(st[2 * C].item())
+    d = s1 / n
+    return running_mean + d, (s2 / n - d * d).clamp_min_(0.0), float(n)
+
+
 class BatchNormFn(Function):
     """y = BN(x) over all tokens (and all ranks when ``sync``); updates the running buffers in training mode."""
 
@@ -44,14 +57,7 @@ class BatchNormFn(Function):
         if train:
             # one pass, data shifted by the running mean (identical on every rank): s1 = sum(x-rm), s2 = sum (x-rm)^2
             s1, s2 = ops.colstat(x, rows=rows, Cc=C, sh1=running_mean)
-            n = float(rows)
-            if _sync_active(sync):
-                st = torch.cat([s1, s2, s1.new_tensor([n])])
-                dist.all_reduce(st)
-                s1, s2, n = st[:C], st[C:2 * C], float(st[2 * C].item())
-            d = s1 / n
-            mean = running_mean + d
-            var = (s2 / n - d * d).clamp_min_(0.0)
+            mean, var, n = bn_batch_stats(s1, s2, float(rows), running_mean, sync)
             rstd = torch.rsqrt(var + eps)
             with torch.no_grad():
                 running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)

@@ -15,3 +15,13 @@ def test_ep_exchange_plan_world2_gloo():
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count('ep plan ok') == 2, r.stdout[-2000:]
+
+
+def test_syncbn_stat_combination_world2_gloo():
+    """LSKNet SyncBN (BASELINE config 5): shifted-sum statistics all-reduced over 2 gloo ranks == full-batch BatchNorm."""
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29545',
+                        os.path.join(ROOT, 'tests', 'dist', 'syncbn_worker.py'), ROOT],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, MASTER_ADDR='127.0.0.1'))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count('syncbn stats ok') == 2, r.stdout[-2000:]
