@@ -80,6 +80,8 @@ typedef struct sm3_gemm_args {
   const float* col_scale; const float* row_scale;
   const float* resid; int64_t ld_resid;
   float* colsum; int64_t colsum_group_stride;
+  int32_t mma_passes;              /* 0 or 3: hi*hi + hi*lo + lo*hi (fp32-accurate, default); 1: hi*hi only = plain bf16
+                                      operands with fp32 accumulation (the mixed-precision recipe) */
 } sm3_gemm_args;
 int sm3_gemm(const sm3_gemm_args* args, void* stream);
 /* Weights are constant across the tokens of a step: split them into bf16 hi/lo ONCE per optimizer step, already

@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ('col_scale', c_f32p), ('row_scale', c_f32p),
         ('resid', c_f32p), ('ld_resid', C.c_int64),
         ('colsum', c_f32p), ('colsum_group_stride', C.c_int64),
+        ('mma_passes', C.c_int32),
     ]
 
 

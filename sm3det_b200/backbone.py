@@ -317,7 +317,15 @@ class ConvNeXt_moe(BaseModule):
 
     def forward(self, x, record=None):
         self._check_input(x)
+        self._select_precision()
         return self._trunk(self._stem(x), record)
+
+    def _select_precision(self):
+        """Mixed-precision recipe (configs train with fp16=dict(loss_scale='dynamic')): under torch.autocast, or with
+        ``self.amp = True``, the tensor-core GEMMs of this forward AND its backward run single-pass bf16 (fp32
+        accumulation); router, LayerNorm, depthwise conv and combine stay fp32 like the reference's autocast policy."""
+        from . import ops
+        ops.set_gemm_precision('bf16' if (getattr(self, 'amp', False) or torch.is_autocast_enabled()) else 'fp32')
 
     @staticmethod
     def _check_input(x):
@@ -435,4 +443,5 @@ class ConvNeXt_moe_MultiInput(ConvNeXt_moe):
             x = [x]
         x = torch.cat(list(x), dim=0)          # one shared stem for every modality (:798-801)
         self._check_input(x)
+        self._select_precision()
         return self._trunk(self._stem(x), record)

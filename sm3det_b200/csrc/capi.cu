@@ -38,6 +38,7 @@ int sm3_gemm(const sm3_gemm_args* a, void* stream) {
   p.col_scale = a->col_scale; p.row_scale = a->row_scale;
   p.resid = a->resid; p.ld_resid = a->ld_resid;
   p.colsum = a->colsum; p.colsum_group_stride = a->colsum_group_stride;
+  p.passes = (a->mma_passes == 1) ? 1 : 3;
   return gemm::launch(p, S(stream));
 }
 

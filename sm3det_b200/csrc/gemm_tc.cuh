@@ -84,6 +84,7 @@ struct Params {
   const float* col_scale; const float* row_scale;
   const float* resid; long long ld_resid;
   float* colsum; long long colsum_group_stride;
+  int passes;   // 3 (default) or 1 (bf16 operands: only the hi*hi product)
   int nstages; unsigned stage_bytes;   // filled by launch(): smem ring depth / stride (4 x 48 KB unless fully packed)
   int debug;   // perf experiments only: bit0 skip A loads+stores, bit1 skip the packed-B bulk copy, bit2 skip MMAs
 };
@@ -477,9 +478,14 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
             const uint64_t bhi = make_smem_desc(sb + OFF_B_HI + j * b_kstep, B_MN);
             const uint64_t blo = make_smem_desc(sb + b_lo_off + j * b_kstep, B_MN);
             if (!(p.debug & 4)) {
-              tc_mma(tmem_d, alo, bhi, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-              tc_mma(tmem_d, ahi, blo, idesc, 1u);
-              tc_mma(tmem_d, ahi, bhi, idesc, 1u);
+              const uint32_t accum = (kb > 0 || j > 0) ? 1u : 0u;
+              if (p.passes == 1) {
+                tc_mma(tmem_d, ahi, bhi, idesc, accum);
+              } else {
+                tc_mma(tmem_d, alo, bhi, idesc, accum);
+                tc_mma(tmem_d, ahi, blo, idesc, 1u);
+                tc_mma(tmem_d, ahi, bhi, idesc, 1u);
+              }
             }
           }
           tc_commit(empty_bar(stage));

@@ -172,8 +172,8 @@ int dwconv7_fwd(const float* x, const float* wt, const float* bias, const float*
   if (C % DCC == 0) {
     const int tiles_w = (W + DT - 1) / DT, tiles_h = (H + DT - 1) / DT;
     const size_t smem = (size_t)DTI * DTI * DCC * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(dwconv7_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    // per call: function attributes are per device, and the library may be driven from several devices of one process
+    cudaFuncSetAttribute(dwconv7_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SM3_REQUIRE((long long)N * (C / DCC) < 65536, SM3_ERR_UNSUPPORTED_SHAPE, "dwconv7_fwd: N*C/32 too large for grid.y");
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(N * (C / DCC)));
     dwconv7_tile_kernel<<<grid, 256, smem, stream>>>(x, wt, bias, resid, y, H, W, C, tiles_w, tiles_h);
@@ -329,8 +329,7 @@ int dwconv7_wgrad(const float* x, const float* dy, float* dwt, float* dbias, int
     if (bpc < 1) bpc = 1;
     size_t smem = (size_t)(DTI * DTI + DT * DT) * DCC * sizeof(float);
     if (smem < (size_t)16 * 50 * 32 * sizeof(float)) smem = (size_t)16 * 50 * 32 * sizeof(float);   // final reduction buffer
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)bpc, (unsigned)chunks);
     dwconv7_wgrad_tile_kernel<<<grid, 256, smem, stream>>>(x, dy, dwt, dbias, N, H, W, C, tiles_w, tiles_h, bpc);
     return check_launch("dwconv7_wgrad_tile_kernel");

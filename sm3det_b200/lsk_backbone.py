@@ -344,8 +344,13 @@ class LSKNet_moe(BaseModule):
             return tuple(outs), sum(gate_losses) / len(gate_losses)
         return tuple(outs)
 
+    def _select_precision(self):
+        from . import ops
+        ops.set_gemm_precision('bf16' if (getattr(self, 'amp', False) or torch.is_autocast_enabled()) else 'fp32')
+
     def forward(self, x, record=None):
         self._check_input(x)
+        self._select_precision()
         return self.forward_features(x, record)
 
 
@@ -390,6 +395,7 @@ class LSKNet_moe_MultiInput(LSKNet_moe):
             x = [x]
         x = torch.cat(list(x), dim=0)                                   # one shared stem (:751-754)
         self._check_input(x)
+        self._select_precision()
         stem = self.dataset_stems['single']
         x = LF.PatchEmbedFn.apply(x, stem.weight, stem.bias, stem.stride[0], True)
         return self.forward_features(x, record)

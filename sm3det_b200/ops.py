@@ -16,6 +16,19 @@ EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_COLSCALE, EPI_ROWSCALE, EPI_RESID, EPI_ATOMIC
 LN_NHWC, LN_PATCH2, LN_NCHW = 0, 1, 2
 
 
+# GEMM operand precision: 3 = split-bf16 hi*hi + hi*lo + lo*hi (fp32-accurate; what every parity test and bench.py use),
+# 1 = hi*hi only (plain bf16 operands, fp32 accumulate) -- the mixed-precision recipe; set through set_gemm_precision().
+MMA_PASSES = 3
+
+
+def set_gemm_precision(mode: str):
+    """'fp32' (default, 3-pass split-bf16) or 'bf16' (single pass; ~3x the tensor-core rate, ~3 significant digits)."""
+    global MMA_PASSES
+    if mode not in ('fp32', 'bf16'):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    MMA_PASSES = 3 if mode == 'fp32' else 1
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -70,6 +83,7 @@ def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a
     a.col_scale = _p(col_scale); a.row_scale = _p(row_scale)
     a.resid = _p(resid); a.ld_resid = ld_resid
     a.colsum = _p(colsum); a.colsum_group_stride = colsum_group_stride
+    a.mma_passes = MMA_PASSES
     _lib.check(lib.sm3_gemm(C.byref(a), _stream()), 'sm3_gemm')
     return D
 

@@ -200,3 +200,28 @@ def test_train_noisy_forward():
         assert abs(loss.item() - gold['gate_loss'].item()) <= 1e-4 * abs(gold['gate_loss'].item())
         for r, g in zip(rec, gold['moe']):
             assert rel(r['load'], g['load']) < 1e-4
+
+
+def test_mixed_precision_mode():
+    """AMP recipe: under torch.autocast the GEMMs run single-pass bf16; the result stays within bf16
+    accuracy of the fp32 oracle, differs from the fp32-accurate mode, and the next plain forward is fp32-accurate again."""
+    spec = CASES['mini_moe_e4k2_train_clean']
+    cfg, sd, net = build(spec['kw'])
+    net.train()
+    n, h, w = spec['img']
+    x = make_images(n, h, w, seed=1234).cuda()
+    with torch.no_grad():
+        ref, _ = backbone_forward(sd, cfg, x.cpu(), train=True)
+    o32, l32 = net(x)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        o16, l16 = net(x)
+    (sum(o.float().square().mean() for o in o16) + l16).backward()
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
+    e32 = max(rel(a, b) for a, b in zip(o32, ref))
+    l2 = lambda a, b: ((a.detach().float().cpu() - b).norm() / b.norm()).item()     # a routing flip moves single tokens a lot
+    e16 = max(l2(a, b) for a, b in zip(o16, ref))
+    print('fp32-mode err', e32, 'bf16-mode rel-L2 err', e16)
+    assert e32 < TOL
+    assert 1e-4 < e16 < 5e-2
+    o32b, _ = net(x)
+    assert max(rel(a, b) for a, b in zip(o32b, ref)) < TOL
