@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step')
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--amp', action='store_true', help='NOT the headline: run the mixed-precision recipe (single-pass bf16 GEMMs)')
     ap.add_argument('--expert-parallel', action='store_true',
                     help='N > 1 only, not the headline config: shard the experts over the ranks (NVLink peer-memory dispatch)')
     ap.add_argument('--cpu-images', type=int, default=1, help='images in the bounded CPU sample')
@@ -271,8 +272,9 @@ def run_ours(args):
     dev_x = host_x.cuda()
 
     def step(x):
-        outs, loss = model(x)
-        tot = sum(o.mean() for o in outs) + loss
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.amp):
+            outs, loss = model(x)
+        tot = sum(o.float().mean() for o in outs) + loss
         tot.backward()
         return tot
 
@@ -346,7 +348,7 @@ def run_ours(args):
             pass
         ep_mode = world > 1 and args.expert_parallel
         roof = roof_moe = None
-        if not ep_mode:        # the instrumented extra passes are rank-0 only; expert parallelism needs every rank in each layer
+        if not ep_mode and not args.amp:        # the instrumented extra passes are rank-0 only; expert parallelism needs every rank in each layer
             roof = gemm_roofline(net, dev_x, peaks)
             net.zero_grad(set_to_none=True)
             try:   # measured DRAM traffic of the GEMM launches of one step (ncu dram__bytes_read+write, profiles/)
@@ -358,7 +360,8 @@ def run_ours(args):
             roof_moe = moe_roofline(net, dev_x, peaks)
         line = {'metric': METRIC, 'value': B * world / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32 (bf16 hi+lo split operands on tcgen05, fp32 accumulate; SIMT fp32 elsewhere)',
+                'dtype': ('bf16 GEMM operands (single pass), fp32 accumulate and fp32 elsewhere -- optional AMP recipe, not the headline'
+                          if args.amp else 'f32 (bf16 hi+lo split operands on tcgen05, fp32 accumulate; SIMT fp32 elsewhere)'),
                 'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks,
                 'e2e': {'value': B * world / (ms_e2e * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
