@@ -72,6 +72,18 @@ LSK_CASES = {
 }
 
 
+VAN_MINI = dict(embed_dims=[32, 64, 96, 128], depths=[1, 1, 2, 1], mlp_ratios=[4, 4, 2, 2])
+LSK_CASES.update({
+    # VAN-MoE (van_moe.py = lsk_moe.py with the LKA gating unit); fixtures are named van_*.pt
+    'van_mini_moe_e4k2_eval': dict(kw=dict(**VAN_MINI, MoE_Block_inds_fc1=[[], [0], [0, 1], [0]],
+                                           MoE_Block_inds_fc2=[[0], [0], [1], [0]], num_experts=4, top_k=2),
+                               img=(2, 64, 64), mode='eval', unit='lka'),
+    'van_mini_moe_e4k2_train_noisy': dict(kw=dict(**VAN_MINI, MoE_Block_inds_fc1=[[], [0], [0, 1], [0]],
+                                                  MoE_Block_inds_fc2=[[0], [0], [1], []], num_experts=4, top_k=2),
+                                      img=(2, 64, 64), mode='train_noisy', unit='lka'),
+})
+
+
 def lsk_plan(cfg, n, h, w):
     """Per MoE layer (in forward order) its token count, and per dropout call its tensor shape [N,C,H,W]."""
     tokens, drops = [], []

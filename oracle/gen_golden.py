@@ -106,10 +106,12 @@ def run_lsk_case(name, spec):
     from oracle.cases import lsk_plan, make_drop_masks
     from oracle.lsk_moe_oracle import LskConfig, lsk_backbone_forward, lsk_param_shapes
     kw = dict(spec['kw'])
-    cfg = LskConfig(**kw)
-    mod = ref_shim.load_reference_module('lsk_moe')
+    unit = spec.get('unit', 'lsk')
+    cfg = LskConfig(spatial_unit=unit, **kw)
+    mod = ref_shim.load_reference_module('lsk_moe' if unit == 'lsk' else 'van_moe')
     torch.manual_seed(0)
-    net = mod.LSKNet_moe_MultiInput(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
+    cls = mod.LSKNet_moe_MultiInput if unit == 'lsk' else mod.VAN_moe_MultiInput
+    net = cls(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
     shapes = lsk_param_shapes(cfg)
     rsd = net.state_dict()
     assert set(shapes) == set(rsd), set(shapes) ^ set(rsd)
@@ -120,7 +122,7 @@ def run_lsk_case(name, spec):
     n, h, w = spec['img']
     x = make_images(n, h, w, seed=1234)
     mode = spec['mode']
-    gold = dict(name=name, kw=kw, img=spec['img'], mode=mode, weights='trained', family='lsk',
+    gold = dict(name=name, kw=kw, img=spec['img'], mode=mode, weights='trained', family='lsk', unit=unit,
                 sd_checksum=state_dict_checksum({k: v.float() for k, v in sd.items()}), x_checksum=float(x.double().abs().sum()))
     record, bn_state = [], {}
     no_grad_keys = ('running_', 'num_batches', '.mean', '.std')

@@ -51,6 +51,7 @@ class LskConfig:
     ln_eps: float = 1e-6          # norm_layer=partial(nn.LayerNorm, eps=1e-6) :606
     layer_scale_init_value: float = 1e-2   # :381
     multi_input: bool = True
+    spatial_unit: str = 'lsk'     # 'lka' = VAN_moe (van_moe.py: same file with LKA :319-333 as the gating unit)
 
     def moe_fc1(self, stage):
         return [q for q in self.MoE_Block_inds_fc1[stage] if q < self.depths[stage]]   # :451
@@ -110,10 +111,13 @@ def lsk_param_shapes(cfg: LskConfig) -> Dict[str, tuple]:
             g = a + 'spatial_gating_unit.'
             sh[g + 'conv0.weight'] = (c, 1, 5, 5); sh[g + 'conv0.bias'] = (c,)
             sh[g + 'conv_spatial.weight'] = (c, 1, 7, 7); sh[g + 'conv_spatial.bias'] = (c,)
-            sh[g + 'conv1.weight'] = (c // 2, c, 1, 1); sh[g + 'conv1.bias'] = (c // 2,)
-            sh[g + 'conv2.weight'] = (c // 2, c, 1, 1); sh[g + 'conv2.bias'] = (c // 2,)
-            sh[g + 'conv_squeeze.weight'] = (2, 2, 7, 7); sh[g + 'conv_squeeze.bias'] = (2,)
-            sh[g + 'conv.weight'] = (c, c // 2, 1, 1); sh[g + 'conv.bias'] = (c,)
+            if cfg.spatial_unit == 'lka':
+                sh[g + 'conv1.weight'] = (c, c, 1, 1); sh[g + 'conv1.bias'] = (c,)
+            else:
+                sh[g + 'conv1.weight'] = (c // 2, c, 1, 1); sh[g + 'conv1.bias'] = (c // 2,)
+                sh[g + 'conv2.weight'] = (c // 2, c, 1, 1); sh[g + 'conv2.bias'] = (c // 2,)
+                sh[g + 'conv_squeeze.weight'] = (2, 2, 7, 7); sh[g + 'conv_squeeze.bias'] = (2,)
+                sh[g + 'conv.weight'] = (c, c // 2, 1, 1); sh[g + 'conv.bias'] = (c,)
             sh[a + 'proj_2.weight'] = (c, c, 1, 1); sh[a + 'proj_2.bias'] = (c,)
             m = p + 'mlp.'
             if j in cfg.moe_fc1(i):
@@ -257,12 +261,22 @@ def lsk_block(x, sd, p):
     return x * attn
 
 
-def attention(x, sd, p):
+def lka(x, sd, p):
+    """LKA.forward van_moe.py:327-333."""
+    c = x.shape[1]
+    u = x.clone()
+    attn = F.conv2d(x, sd[p + 'conv0.weight'], sd[p + 'conv0.bias'], padding=2, groups=c)
+    attn = F.conv2d(attn, sd[p + 'conv_spatial.weight'], sd[p + 'conv_spatial.bias'], padding=9, groups=c, dilation=3)
+    attn = F.conv2d(attn, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'])
+    return u * attn
+
+
+def attention(x, sd, p, unit='lsk'):
     """Attention.forward :355-363."""
     shortcut = x.clone()
     x = F.conv2d(x, sd[p + 'proj_1.weight'], sd[p + 'proj_1.bias'])
     x = F.gelu(x)
-    x = lsk_block(x, sd, p + 'spatial_gating_unit.')
+    x = lsk_block(x, sd, p + 'spatial_gating_unit.') if unit == 'lsk' else lka(x, sd, p + 'spatial_gating_unit.')
     x = F.conv2d(x, sd[p + 'proj_2.weight'], sd[p + 'proj_2.bias'])
     return x + shortcut
 
@@ -282,7 +296,7 @@ def block(x, sd, p, cfg: LskConfig, moe1, moe2, dpr, train, bn_state, noise_it, 
     """Block.forward :387-396."""
     ls1 = sd[p + 'layer_scale_1'].unsqueeze(-1).unsqueeze(-1)
     ls2 = sd[p + 'layer_scale_2'].unsqueeze(-1).unsqueeze(-1)
-    x = x + drop_path(ls1 * attention(batch_norm(x, sd, p + 'norm1.', cfg, train, bn_state), sd, p + 'attn.'),
+    x = x + drop_path(ls1 * attention(batch_norm(x, sd, p + 'norm1.', cfg, train, bn_state), sd, p + 'attn.', cfg.spatial_unit),
                       dpr, train, dp_mask)
     y, loss = mlp(batch_norm(x, sd, p + 'norm2.', cfg, train, bn_state), sd, p + 'mlp.', cfg, moe1, moe2, train,
                   noise_it, drop_it, record)

@@ -183,12 +183,30 @@ class LSKblock(nn.Module):
         return LF.MulFn.apply(x, attn)
 
 
+class LKA(nn.Module):
+    """VAN large-kernel attention (van_moe.py:319-333): x * conv1(conv_spatial(conv0(x)))."""
+
+    def __init__(self, dim):
+        super().__init__()
+        if dim % 32:
+            raise NotImplementedError(f'sm3det_b200: VAN width {dim} unsupported (multiple of 32)')
+        self.conv0 = nn.Conv2d(dim, dim, 5, padding=2, groups=dim)
+        self.conv_spatial = nn.Conv2d(dim, dim, 7, stride=1, padding=9, groups=dim, dilation=3)
+        self.conv1 = nn.Conv2d(dim, dim, 1)
+
+    def forward(self, x):
+        attn = LF.DWConvFn.apply(x, self.conv0.weight, self.conv0.bias, 5, 1)
+        attn = LF.DWConvFn.apply(attn, self.conv_spatial.weight, self.conv_spatial.bias, 7, 3)
+        attn = _conv1x1(self.conv1, attn)
+        return LF.MulFn.apply(x, attn)
+
+
 class Attention(nn.Module):
-    def __init__(self, d_model):
+    def __init__(self, d_model, unit='lsk'):
         super().__init__()
         self.proj_1 = nn.Conv2d(d_model, d_model, 1)
         self.activation = nn.GELU()
-        self.spatial_gating_unit = LSKblock(d_model)
+        self.spatial_gating_unit = LSKblock(d_model) if unit == 'lsk' else LKA(d_model)
         self.proj_2 = nn.Conv2d(d_model, d_model, 1)
 
     def forward(self, x):
@@ -201,11 +219,11 @@ class Attention(nn.Module):
 
 class Block(nn.Module):
     def __init__(self, dim, mlp_ratio=4., drop=0., drop_path=0., act_layer=nn.GELU, norm_cfg=None, MoE_cfg1=None,
-                 MoE_cfg2=None):
+                 MoE_cfg2=None, unit='lsk'):
         super().__init__()
         self.norm1 = _build_bn(norm_cfg, dim)
         self.norm2 = _build_bn(norm_cfg, dim)
-        self.attn = Attention(dim)
+        self.attn = Attention(dim, unit)
         self.drop_path_rate = float(drop_path)
         self.drop_path = nn.Identity()
         self.MoE_cfg1, self.MoE_cfg2 = MoE_cfg1, MoE_cfg2
@@ -250,6 +268,8 @@ class OverlapPatchEmbed(nn.Module):
 
 @ROTATED_BACKBONES.register_module()
 class LSKNet_moe(BaseModule):
+    _spatial_unit = 'lsk'          # 'lka' in the VAN subclasses (the only difference between lsk_moe.py and van_moe.py)
+
     def __init__(self, MoE_Block_inds_fc1=[[], [], [], []], MoE_Block_inds_fc2=[[], [], [], []], num_experts=2, top_k=2,
                  img_size=224, noisy_gating=False, gate='cosine', in_chans=3, embed_dims=[32, 64, 160, 256],
                  mlp_ratios=[8, 8, 4, 4], drop_rate=0., drop_path_rate=0., norm_layer=partial(nn.LayerNorm, eps=1e-6),
@@ -280,7 +300,7 @@ class LSKNet_moe(BaseModule):
             mk = lambda on: ({'noisy_gating': noisy_gating, 'num_experts': num_experts, 'top_k': top_k, 'gating': gate}
                              if on else None)
             block = nn.ModuleList([Block(dim=embed_dims[i], mlp_ratio=mlp_ratios[i], drop=drop_rate, drop_path=dpr[cur + j],
-                                         norm_cfg=norm_cfg, MoE_cfg1=mk(j in ind1), MoE_cfg2=mk(j in ind2))
+                                         norm_cfg=norm_cfg, MoE_cfg1=mk(j in ind1), MoE_cfg2=mk(j in ind2), unit=self._spatial_unit)
                                    for j in range(depths[i])])
             norm = norm_layer(embed_dims[i])
             cur += depths[i]
@@ -399,3 +419,15 @@ class LSKNet_moe_MultiInput(LSKNet_moe):
         stem = self.dataset_stems['single']
         x = LF.PatchEmbedFn.apply(x, stem.weight, stem.bias, stem.stride[0], True)
         return self.forward_features(x, record)
+
+
+@ROTATED_BACKBONES.register_module()
+class VAN_moe(LSKNet_moe):
+    """van_moe.py:410-588: identical to LSKNet_moe except the spatial gating unit (LKA, :319-333)."""
+    _spatial_unit = 'lka'
+
+
+@ROTATED_BACKBONES.register_module()
+class VAN_moe_MultiInput(LSKNet_moe_MultiInput):
+    """van_moe.py:590-814."""
+    _spatial_unit = 'lka'

@@ -148,11 +148,11 @@ def test_linear_gelu_mul_axpy(ops):
 
 
 # ------------------------------------------------------------------------------------------------
-def build(kw, seed=0):
-    from sm3det_b200 import LSKNet_moe_MultiInput
-    cfg = LskConfig(**kw)
+def build(kw, seed=0, unit='lsk'):
+    from sm3det_b200 import LSKNet_moe_MultiInput, VAN_moe_MultiInput
+    cfg = LskConfig(spatial_unit=unit, **kw)
     sd = make_state_dict(lsk_param_shapes(cfg), seed, True)
-    net = LSKNet_moe_MultiInput(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
+    net = (LSKNet_moe_MultiInput if unit == 'lsk' else VAN_moe_MultiInput)(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
     net.load_state_dict(sd, strict=True)
     return cfg, sd, net.cuda()
 
@@ -170,10 +170,10 @@ def inject(net, cfg, noise, drops):
                 blk.mlp._injected_drop_masks = [m1.permute(0, 2, 3, 1).contiguous(), m2.permute(0, 2, 3, 1).contiguous()]
 
 
-@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'lsk_*.pt'))), ids=lambda p: os.path.basename(p)[:-3])
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'lsk_*.pt')) + glob.glob(os.path.join(GOLD, 'van_*.pt'))), ids=lambda p: os.path.basename(p)[:-3])
 def test_lsk_backbone_matches_reference_golden(path):
     gold = torch.load(path, weights_only=False)
-    cfg, sd, net = build(gold['kw'])
+    cfg, sd, net = build(gold['kw'], unit=gold.get('unit', 'lsk'))
     n, h, w = gold['img']
     x = make_images(n, h, w, seed=1234).cuda()
     train = gold['mode'] != 'eval'

@@ -16,13 +16,13 @@ GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
 
 def _inputs(gold):
-    cfg = LskConfig(**gold['kw'])
+    cfg = LskConfig(spatial_unit=gold.get('unit', 'lsk'), **gold['kw'])
     sd = make_state_dict(lsk_param_shapes(cfg), 0, True)
     n, h, w = gold['img']
     return cfg, sd, make_images(n, h, w, seed=1234)
 
 
-@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'lsk_*.pt'))), ids=lambda p: os.path.basename(p)[:-3])
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'lsk_*.pt')) + glob.glob(os.path.join(GOLD, 'van_*.pt'))), ids=lambda p: os.path.basename(p)[:-3])
 def test_oracle_reproduces_reference_golden(path):
     gold = torch.load(path, weights_only=False)
     cfg, sd, x = _inputs(gold)
@@ -98,3 +98,17 @@ def test_lsk_upcycle_dense_checkpoint():
     for e in range(3):
         assert torch.equal(moe.block2[0].mlp.fc1.experts[e].weight, dense.block2[0].mlp.fc1.weight)
         assert torch.equal(moe.block1[0].mlp.fc2.experts[e].bias, dense.block1[0].mlp.fc2.bias)
+
+
+def test_van_contract():
+    """VAN_moe(_MultiInput): same contract as LSKNet with the LKA gating unit (van_moe.py:319-333, :410, :590)."""
+    from sm3det_b200 import build_backbone
+    kw = dict(MoE_Block_inds_fc1=[[], [0], [0], []], MoE_Block_inds_fc2=[[], [0], [0], []], num_experts=2, top_k=1,
+              embed_dims=[32, 64, 160, 256], depths=[1, 1, 2, 1])
+    net = build_backbone(dict(type='VAN_moe_MultiInput', **kw))
+    shapes = lsk_param_shapes(LskConfig(spatial_unit='lka', **kw))
+    sd = net.state_dict()
+    assert set(shapes) == set(sd) and all(tuple(sd[k].shape) == tuple(v) for k, v in shapes.items())
+    if ref_shim.reference_available():
+        ref = ref_shim.load_reference_module('van_moe').VAN_moe_MultiInput(**kw)
+        assert set(ref.state_dict()) == set(sd)
