@@ -209,3 +209,62 @@ def test_router_noisy_soft_load(ops):
     assert rel(plan['load'], load) < 1e-5
     loss = (cv_squared(gates.sum(0)) + cv_squared(load)) * 1e-2
     assert abs(plan['loss'].item() - loss.item()) <= 1e-5 * abs(loss.item())
+
+
+@pytest.mark.parametrize('R,W', [(256, 384), (1000, 128), (300, 1536)])
+def test_act_pack_images_feed_gemms(ops, R, W):
+    """act_pack's bf16 hi/lo tile images (modes 0 and 3) are consumed by the packed GEMMs exactly like torch's
+    gelu / gelu-backward followed by matmuls (forward GEMM2, dgrad1, wgrad1, wgrad2) -- incl. 16-lane column groups (W=384)."""
+    g = torch.Generator().manual_seed(R + W)
+    C = 64
+    h = torch.randn(R, W, generator=g)
+    da = torch.randn(R, W, generator=g)
+    w2 = torch.randn(C, W, generator=g) / W ** 0.5          # GEMM2 weight [C, 4C]
+    w1 = torch.randn(W, C, generator=g) / C ** 0.5          # GEMM1 weight [4C, C]
+    v = torch.randn(R, C, generator=g)
+    dz = torch.randn(R, C, generator=g)
+    hd, dad = h.cuda(), da.cuda()
+    a_ref = F.gelu(h)
+    hr = h.clone().requires_grad_(True)
+    F.gelu(hr).backward(da)
+    dh_ref = hr.grad
+    # mode 0: K-major image -> forward GEMM2
+    a_k, _, a_f32 = ops.act_pack(hd, rows=R, width=W, mode=ops.ACT_GELU, want_k=True, want_f32=True)
+    assert rel(a_f32, a_ref) < 2e-6
+    y = ops.linear_fwd(None, w2.cuda(), None, rows=R, a_packed=a_k, packed=ops.pack_weight(w2.cuda(), transposed=False))
+    assert rel(y, a_ref @ w2.t()) < 5e-5
+    # mode 3: one pass -> dgrad1 (K-major dh), wgrad1 (MN-major dh), wgrad2 (MN-major gelu(h)), db1
+    db1 = torch.zeros(W, device='cuda')
+    dh_k, dh_mn, a_mn = ops.act_pack(hd, rows=R, width=W, mode=ops.ACT_BWD, da=dad, want_k=True, mn_tile=128,
+                                     mn_tile2=ops._pick_bn(W), colsum=db1)
+    assert rel(db1, dh_ref.sum(0)) < 5e-5
+    dv = ops.linear_dgrad(None, w1.cuda(), rows=R, a_packed=dh_k, packed=ops.pack_weight(w1.cuda(), transposed=True))
+    assert rel(dv, dh_ref @ w1) < 5e-5
+    dw1 = torch.zeros(W, C, device='cuda')
+    ops.linear_wgrad(None, v.cuda(), dw1, rows=R, dy_packed=dh_mn)
+    assert rel(dw1, dh_ref.t() @ v) < 5e-5
+    dw2 = torch.zeros(C, W, device='cuda')
+    ops.linear_wgrad(dz.cuda(), None, dw2, rows=R, x_packed=a_mn)
+    assert rel(dw2, dz.t() @ a_ref) < 5e-5
+
+
+def test_gather_rows_peer_single_device(ops):
+    """sm3_gather_rows_peer with a one-entry pointer table (the expert-parallel row gather, world size 1): direct rows,
+    rows through a token list, per-row scale, and -1 -> zero rows."""
+    g = torch.Generator().manual_seed(5)
+    T, C, R = 200, 96, 333
+    x = torch.randn(T, C, generator=g).cuda()
+    toks = torch.randint(0, T, (400,), generator=g, dtype=torch.int32).cuda()
+    src_rank = torch.zeros(R, dtype=torch.int32); src_rank[::7] = -1
+    src_slot = torch.randint(0, 400, (R,), generator=g, dtype=torch.int32)
+    scale = torch.rand(R, generator=g)
+    bases = torch.tensor([x.data_ptr()], dtype=torch.int64, device='cuda')
+    lists = torch.tensor([toks.data_ptr()], dtype=torch.int64, device='cuda')
+    out = ops.gather_rows_peer(bases, src_rank.cuda(), src_slot.cuda(), rows=R, Cc=C, token_lists=lists, scale=scale.cuda())
+    want = x.cpu()[toks.cpu().long()[src_slot.long()]] * scale[:, None]
+    want[src_rank < 0] = 0
+    assert torch.equal(out.cpu(), want)
+    direct = ops.gather_rows_peer(bases, src_rank.cuda(), (src_slot % T).cuda(), rows=R, Cc=C)
+    want2 = x.cpu()[(src_slot % T).long()]
+    want2[src_rank < 0] = 0
+    assert torch.equal(direct.cpu(), want2)
