@@ -45,7 +45,7 @@ def routing_flips(rec_gpu, rec_cpu):
     return flips, ok
 
 
-@pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, '*.pt')) if not os.path.basename(p).startswith('lsk_')), ids=lambda p: os.path.basename(p)[:-3])
+@pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, '*.pt')) if not os.path.basename(p).startswith(('lsk_', 'van_'))), ids=lambda p: os.path.basename(p)[:-3])
 def test_forward_matches_reference_golden(path):
     gold = torch.load(path, weights_only=False)
     if gold['mode'] == 'train_noisy':

@@ -32,7 +32,7 @@ def _run_oracle(gold, record):
     return cfg, sdg, backbone_forward(sdg, cfg, x, train=True, noise=noise, record=record)
 
 
-@pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, '*.pt')) if not os.path.basename(p).startswith('lsk_')), ids=lambda p: os.path.basename(p)[:-3])
+@pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, '*.pt')) if not os.path.basename(p).startswith(('lsk_', 'van_'))), ids=lambda p: os.path.basename(p)[:-3])
 def test_oracle_matches_reference_golden(path):
     gold = torch.load(path, weights_only=False)
     record = []
