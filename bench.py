@@ -244,7 +244,6 @@ def run_ours(args):
     import torch.distributed as dist
     from sm3det_b200 import ConvNeXt_moe_MultiInput, _lib
     from sm3det_b200.synth import make_images, make_state_dict
-    from oracle.convnext_moe_oracle import OracleConfig, param_shapes   # shapes only (weight generation)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -255,9 +254,9 @@ def run_ours(args):
     lib = _lib.load()
     assert lib.sm3_device_supported() == 1, 'bench.py needs an sm_100 (B200) device'
 
-    cfg = OracleConfig(**MODEL_KW)
-    sd = make_state_dict(param_shapes(cfg), 0, True)
     net = ConvNeXt_moe_MultiInput(**MODEL_KW)
+    # seeded "trained-like" weights keyed by state_dict name (the product leg never touches oracle/)
+    sd = make_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 0, True)
     net.load_state_dict(sd, strict=True)
     net = net.cuda().train()
     model = net
