@@ -175,6 +175,9 @@ int sm3_affine(const float* x1, const float* a1, const float* x2, const float* a
 int sm3_mul(const float* a, const float* b, const float* add, float* out, int64_t n, void* stream) {
   return mul(a, b, add, out, n, S(stream));
 }
+int sm3_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream) {
+  return dropout(x, out, n, p, seed, S(stream));
+}
 int sm3_lsk_agg(const float* a1, const float* a2, float* agg, int32_t* amax, int64_t T, int32_t Ch, void* stream) {
   return lsk_agg(a1, a2, agg, amax, T, Ch, S(stream));
 }

@@ -318,6 +318,36 @@ int mul(const float* a, const float* b, const float* add, float* out, long long 
   return check_launch("mul_kernel");
 }
 
+// Dropout with a counter-based mask (nn.Dropout of Mlp, lsk_moe.py:300,311,316): keep = hash(seed, element index) >= p,
+// out = x * keep / (1 - p).  The same call with dy as input is the backward (the mask is recomputed, never stored), so
+// dropout costs one read + one write instead of torch's rand / compare / scale / multiply passes and a saved mask.
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {      // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4,
+                                                     uint32_t thresh, float scale, uint64_t seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = ldg_f4(x + i * 4);
+  const uint64_t base = seed ^ ((uint64_t)i * 4ull * 0xD1342543DE82EF95ull);
+  float4 o;
+  o.x = mix32(base) >= thresh ? v.x * scale : 0.f;
+  o.y = mix32(base + 0x632BE59BD9B4E019ull) >= thresh ? v.y * scale : 0.f;
+  o.z = mix32(base + 2ull * 0x632BE59BD9B4E019ull) >= thresh ? v.z * scale : 0.f;
+  o.w = mix32(base + 3ull * 0x632BE59BD9B4E019ull) >= thresh ? v.w * scale : 0.f;
+  *reinterpret_cast<float4*>(out + i * 4) = o;
+}
+
+int dropout(const float* x, float* out, long long n, float p, unsigned long long seed, cudaStream_t stream) {
+  SM3_REQUIRE(x && out && n % 4 == 0 && p >= 0.f && p < 1.f, SM3_ERR_INVALID_ARG, "dropout: bad argument");
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  dropout_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(x, out, n / 4, thresh, 1.0f / (1.0f - p), seed);
+  return check_launch("dropout_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------
 // LSK spatial selection (LSKblock.forward :336-341).  a1, a2: [T, Ch].
 // agg[t] = (mean, max) over the 2*Ch channels of cat(a1, a2); amax[t] = argmax channel (first on ties).

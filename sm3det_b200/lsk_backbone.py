@@ -128,11 +128,11 @@ class Mlp(nn.Module):
         if p == 0.0 or not self.training:
             return x
         masks = getattr(self, '_injected_drop_masks', None)
-        if masks:
+        if masks:                                   # tests inject the reference's masks
             m = masks.pop(0).to(x.device, torch.float32).reshape(x.shape).contiguous()
-        else:
-            m = (torch.rand(x.shape, device=x.device) >= p).float() / (1.0 - p)
-        return LF.MulFn.apply(x, m)
+            return LF.MulFn.apply(x, m)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # host RNG (torch.manual_seed reproducible), no device sync
+        return LF.DropoutFn.apply(x, p, seed)
 
     def forward(self, x, ls, resid, row_scale, record=None):
         """x: NHWC BN output.  Returns (resid + row_scale * ls * mlp(x), loss or None)  (Block.forward :390-395)."""

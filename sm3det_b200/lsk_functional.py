@@ -217,6 +217,19 @@ class MulFn(Function):
         return da, db
 
 
+class DropoutFn(Function):
+    """nn.Dropout with a counter-based mask: forward and backward are the same kernel with the same seed."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout(x.contiguous(), p, seed)
+
+    @staticmethod
+    def backward(ctx, d):
+        return ops.dropout(d.contiguous(), ctx.p, ctx.seed), None, None
+
+
 class AxpyFn(Function):
     """out = a[c] * y * row_scale[t] + x   (a = layer scale or None, row_scale = drop-path mask or None)."""
 

@@ -467,6 +467,13 @@ def mul(a, b, add=None, out=None):
     return out
 
 
+def dropout(x, p, seed):
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    _lib.check(lib.sm3_dropout(_p(x), _p(out), x.numel(), float(p), int(seed), _stream()), 'sm3_dropout')
+    return out
+
+
 def lsk_agg(a1, a2, *, T, Ch, want_idx=True):
     lib = _lib.load()
     agg = torch.empty((T, 2), device=a1.device, dtype=torch.float32)

@@ -237,3 +237,18 @@ def test_lsk_eval_list_input_and_plain_class():
     assert all(torch.equal(a, b) for a, b in zip(o1, o2))
     assert max(rel(a, b) for a, b in zip(o1, ref)) < TOL and abs(l1.item() - rl.item()) < 1e-4 * abs(rl.item())
     assert all(o.is_contiguous() and o.shape[0] == 2 for o in o1)
+
+
+def test_fused_dropout(ops):
+    """sm3_dropout: keep-rate ~ 1-p, survivors scaled by 1/(1-p), the backward reuses the identical mask, seeds differ."""
+    from sm3det_b200.lsk_functional import DropoutFn
+    x = torch.randn(1 << 20, device='cuda').requires_grad_(True)
+    y = DropoutFn.apply(x, 0.1, 1234)
+    keep = (y != 0)
+    assert abs(keep.float().mean().item() - 0.9) < 3e-3
+    assert torch.allclose(y[keep], x.detach()[keep] / 0.9)
+    y.backward(torch.ones_like(y))
+    assert torch.equal(x.grad != 0, keep) and torch.allclose(x.grad[keep], torch.full_like(x.grad[keep], 1 / 0.9))
+    y2 = ops.dropout(x.detach(), 0.1, 1235)
+    assert (y2 != 0).ne(keep).float().mean().item() > 0.1            # a different seed gives a different mask
+    assert torch.equal(ops.dropout(x.detach(), 0.0, 7), x.detach())
