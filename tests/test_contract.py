@@ -126,3 +126,47 @@ def test_reference_arm_two_processes_gloo_style_launch():
     line = json.loads(outs[0].splitlines()[-1])
     assert line['impl'] == 'reference' and line['cpu_baseline']['kind'] == 'port' and line['value'] > 0
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['unit'] == 'img/s'
+
+
+def test_pack_cache_invalidation(monkeypatch):
+    """PackCache re-splits a weight image exactly when a parameter changed in place (optimizer step / load_state_dict) or
+    moved (stack_expert_params re-pointing .data) -- host logic, checked with a stub in place of the CUDA pack kernel."""
+    import torch
+    from sm3det_b200 import ops
+    from sm3det_b200.backbone import PackCache
+    calls = []
+
+    def fake_pack(w, *, transposed, groups=1, out=None):
+        calls.append((w.data_ptr(), transposed, groups))
+        return (out if out is not None else torch.zeros(4, dtype=torch.int16)), 4
+
+    monkeypatch.setattr(ops, 'pack_weight', fake_pack)
+    pc = PackCache()
+    p = torch.nn.Parameter(torch.randn(8, 8))
+    a = pc.get('w1', [p], False)
+    assert pc.get('w1', [p], False) is a and len(calls) == 1            # hit
+    pc.get('w1', [p], True)
+    assert len(calls) == 2                                               # the transposed image is a separate entry
+    with torch.no_grad():
+        p.add_(1.0)                                                      # what an optimizer step does
+    pc.get('w1', [p], False)
+    assert len(calls) == 3
+    p.data = p.data.clone()                                              # storage moved
+    pc.get('w1', [p], False)
+    assert len(calls) == 4
+    opt = torch.optim.SGD([p], lr=0.1)
+    p.grad = torch.ones_like(p)
+    opt.step()
+    pc.get('w1', [p], False)
+    assert len(calls) == 5
+
+
+def test_ep_expert_layout_host_plan():
+    """expert_parallel._expert_layout: 128-row aligned expert segments per owner, source-major offsets, tile map."""
+    from sm3det_b200.expert_parallel import _expert_layout
+    cnt = [[5, 0, 130, 1], [0, 0, 127, 300]]          # cnt[source][expert], W = 2, E = 4 (2 experts per rank)
+    seg, off, rows, tiles = _expert_layout(cnt, 2, 4)
+    assert seg == [[0, 128], [0, 384]]                  # rank 0: e0 (5 rows -> 1 tile), e1 (0 rows -> 0 tiles at 128); rank 1: e2 257 rows -> 3 tiles, e3
+    assert off[0] == [0, 5] and off[2] == [0, 130] and off[3] == [0, 1]
+    assert rows == [128, 384 + 384]                     # e3: 301 rows -> 3 tiles
+    assert tiles[0] == [0] and tiles[1] == [0, 0, 0, 1, 1, 1]
