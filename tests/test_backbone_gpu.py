@@ -212,10 +212,14 @@ def test_mixed_precision_mode():
     x = make_images(n, h, w, seed=1234).cuda()
     with torch.no_grad():
         ref, _ = backbone_forward(sd, cfg, x.cpu(), train=True)
-    o32, l32 = net(x)
-    with torch.autocast('cuda', dtype=torch.bfloat16):
-        o16, l16 = net(x)
-    (sum(o.float().square().mean() for o in o16) + l16).backward()
+    from sm3det_b200 import ops
+    try:
+        o32, l32 = net(x)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            o16, l16 = net(x)
+        (sum(o.float().square().mean() for o in o16) + l16).backward()
+    finally:
+        ops.set_gemm_precision('fp32')            # never leak the bf16 mode into the other tests of this process
     assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
     e32 = max(rel(a, b) for a, b in zip(o32, ref))
     l2 = lambda a, b: ((a.detach().float().cpu() - b).norm() / b.norm()).item()     # a routing flip moves single tokens a lot
