@@ -1,16 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the SM3Det ConvNeXt-MoE backbone hot path (BASELINE.json metric: backbone images/s @1024^2).
+"""Benchmark of the SM3Det sparse-MoE backbone hot path (BASELINE.json metric: backbone images/s @1024^2, bs = 32).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--config t_e8|b_e16|lsk_s] [--global-batch G | --batch B] [--expert-parallel]
 
-One "step" = forward + backward of the backbone over one synthetic batch (BASELINE configs[1]:
-ConvNeXt-T, E=8 top-2, MoE in the last two stages every other block, 8 x 3 x 1024 x 1024 per GPU,
-fp32).  N > 1 runs one process per GPU (torchrun), DistributedDataParallel over NCCL, per-GPU batch
-fixed (weak scaling); the timed region is bracketed by barrier + synchronize and the max over ranks
-is reported.  `--impl reference` times the reference's own CPU implementation of the same path (the
-oracle port: identical torch CPU ops in the reference's order) on the box's host cores.
+One "step" = forward + backward of the backbone over the GLOBAL batch of synthetic 1024^2 tiles:
+  t_e8  (default) BASELINE configs[1]/[2]: ConvNeXt-T, E = 8 top-2, MoE in the last two stages every other block.
+        Global batch 32 at every N (the batch the metric is quoted on) -> strong scaling: 32 / 16 / 8 / 4 images per GPU at
+        N = 1 / 2 / 4 / 8, processed as micro-batches of <= 8 images with gradient accumulation (configs[1]'s bs = 8 is the
+        micro-batch; `--global-batch 8` is configs[1] literally).  N > 1: one process per GPU (torchrun),
+        DistributedDataParallel over NCCL, one gradient all-reduce per step.
+  b_e16 BASELINE configs[3]: ConvNeXt-B, E = 16, all 36 blocks MoE; experts sharded over the ranks when N > 1.
+  lsk_s BASELINE configs[4]: LSKNet-S MoE, SyncBN, global batch 16 (4 GPUs -> 4 per GPU).
+The timed region is bracketed by barrier + synchronize and the max over ranks is reported.  `--impl reference` times the
+reference's own CPU implementation of the same path (the oracle port: identical torch CPU ops in the reference's order)
+on the box's host cores.
 """
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -24,33 +31,73 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MODEL_KW = dict(arch='tiny', MoE_Block_inds=[[], [], [0, 2, 4, 6, 8], [0, 2]], num_experts=8, top_k=2,
-                noisy_gating=False, drop_path_rate=0.0)
 METRIC = 'backbone images/sec @1024^2 (fwd+bwd)'
+CONFIGS = {
+    't_e8': dict(family='convnext', global_batch=32, micro=8,
+                 kw=dict(arch='tiny', MoE_Block_inds=[[], [], [0, 2, 4, 6, 8], [0, 2]], num_experts=8, top_k=2,
+                         noisy_gating=False, drop_path_rate=0.0),
+                 name='SM3Det ConvNeXt-T e8t2 last-2-blocks MoE backbone (BASELINE configs[1]/[2])'),
+    'b_e16': dict(family='convnext', global_batch=8, micro=2,
+                  kw=dict(arch='base', MoE_Block_inds=[[0, 1, 2], [0, 1, 2], list(range(27)), [0, 1, 2]], num_experts=16,
+                          top_k=2, noisy_gating=False, drop_path_rate=0.0),
+                  name='SM3Det ConvNeXt-B e16t2 all-blocks MoE backbone (BASELINE configs[3])'),
+    'lsk_s': dict(family='lsk', global_batch=16, micro=4,
+                  kw=dict(MoE_Block_inds_fc1=[[], [0], [0, 2], [0]], MoE_Block_inds_fc2=[[], [0], [0, 2], [0]], num_experts=4,
+                          top_k=2, embed_dims=[64, 128, 320, 512], depths=[2, 2, 4, 2], drop_rate=0.1, drop_path_rate=0.,
+                          norm_cfg=dict(type='SyncBN', requires_grad=True)),
+                  name='SM3Det LSKNet-S MoE backbone, SyncBN, noisy gating + dropout as configured (BASELINE configs[4])'),
+}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=6)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=8, help='images per GPU per step')
+    ap.add_argument('--config', default='t_e8', choices=sorted(CONFIGS))
+    ap.add_argument('--global-batch', type=int, default=None, help='images per step over all GPUs (strong scaling)')
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU per step (weak scaling; overrides --global-batch)')
+    ap.add_argument('--micro-batch', type=int, default=None, help='images per forward/backward pass (gradient accumulation)')
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-eager', action='store_true')
     ap.add_argument('--amp', action='store_true', help='NOT the headline: run the mixed-precision recipe (single-pass bf16 GEMMs)')
     ap.add_argument('--expert-parallel', action='store_true',
-                    help='N > 1 only, not the headline config: shard the experts over the ranks (NVLink peer-memory dispatch)')
+                    help='N > 1: shard the experts over the ranks (NVLink peer-memory dispatch); default for --config b_e16')
+    ap.add_argument('--no-expert-parallel', action='store_true')
     ap.add_argument('--cpu-images', type=int, default=1, help='images in the bounded CPU sample')
-    return ap.parse_args()
+    a = ap.parse_args()
+    return a
+
+
+def resolve(args, world):
+    """-> (cfg entry, per-GPU batch, micro-batch, scaling)."""
+    c = CONFIGS[args.config]
+    if args.batch is not None:
+        per, scaling = args.batch, 'weak'
+    else:
+        g = args.global_batch if args.global_batch is not None else c['global_batch']
+        if g % world:
+            raise SystemExit(f'global batch {g} is not divisible by {world} GPUs')
+        per, scaling = g // world, 'strong'
+    micro = min(per, args.micro_batch or c['micro'])
+    while per % micro:
+        micro -= 1
+    ep = world > 1 and c['family'] == 'convnext' and not args.no_expert_parallel and \
+        (args.expert_parallel or args.config == 'b_e16') and c['kw']['num_experts'] % world == 0
+    return c, per, micro, scaling, ep
 
 
 def workload_config(args, world):
-    return {'workload': f'SM3Det ConvNeXt-T e8t2 last-2-blocks MoE backbone, fwd+bwd, bs={args.batch}/GPU x {world} GPU, '
-                        f'{args.size}x{args.size}x3 synthetic SAR/RGB/IR 2:1:1, fp32, noisy_gating=False, drop_path=0',
-            'arch': 'ConvNeXt-T', 'num_experts': 8, 'top_k': 2, 'moe_blocks': MODEL_KW['MoE_Block_inds'],
-            'per_gpu_batch': args.batch, 'global_batch': args.batch * world, 'image': args.size,
-            'parallelism': f'dp{world}' + ('+ep' if getattr(args, 'expert_parallel', False) and world > 1 else ''), 'l2': 'inputs and activations exceed L2 (>=100 MB per tensor); no flush needed'}
+    c, per, micro, scaling, ep = resolve(args, world)
+    kw = c['kw']
+    return {'workload': f'{c["name"]}, fwd+bwd, global batch {per * world} = {per}/GPU x {world} GPU in micro-batches of '
+                        f'{micro}, {args.size}x{args.size}x3 synthetic SAR/RGB/IR 2:1:1, fp32',
+            'config': args.config, 'num_experts': kw['num_experts'], 'top_k': kw['top_k'],
+            'per_gpu_batch': per, 'micro_batch': micro, 'global_batch': per * world, 'image': args.size,
+            'parallelism': f'dp{world}' + ('+ep' if ep else ''),
+            'l2': 'inputs and activations exceed L2 (>= 100 MB per tensor); no flush needed'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -85,32 +132,64 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def cpu_reference_step(sd, cfg, x):
-    """fwd+bwd of the oracle port on the host cores (train mode, clean gating) -- test infrastructure."""
-    from oracle.convnext_moe_oracle import backbone_forward
-    sdg = {k: (v.clone().requires_grad_(True) if 'ffn.mean' not in k and 'ffn.std' not in k else v) for k, v in sd.items()}
-    outs, loss = backbone_forward(sdg, cfg, x, train=True)
+# ---- the reference's own implementation (oracle port): CPU baseline, --impl reference, GPU-eager comparator ----------
+def oracle_model(config):
+    """(forward(x, train) -> (outs, loss), state_dict on CPU) of the oracle port for a bench config -- test infrastructure,
+    used only as a *baseline that is timed*, never on the product path."""
+    from sm3det_b200.synth import make_state_dict
+    c = CONFIGS[config]
+    if c['family'] == 'convnext':
+        from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes
+        kw = dict(c['kw'])
+        cfg = OracleConfig(**kw)
+        sd = make_state_dict(param_shapes(cfg), 0, True)
+        return (lambda s, x, train: backbone_forward(s, cfg, x, train=train)), sd
+    from oracle.lsk_moe_oracle import LskConfig, lsk_backbone_forward, lsk_param_shapes
+    kw = {k: v for k, v in c['kw'].items() if k != 'norm_cfg'}
+    cfg = LskConfig(**kw)
+    sd = make_state_dict(lsk_param_shapes(cfg), 0, True)
+    return (lambda s, x, train: lsk_backbone_forward(s, cfg, x, train=train, bn_state={})), sd
+
+
+def _grad_sd(sd):
+    skip = ('ffn.mean', 'ffn.std', 'running_', 'num_batches', '.mean', '.std')
+    return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not any(t in k for t in skip) else v) for k, v in sd.items()}
+
+
+def oracle_step(fwd, sd, x):
+    outs, loss = fwd(_grad_sd(sd), x, True)
     (sum(o.mean() for o in outs) + loss).backward()
 
 
 def time_cpu_reference(args, images, steps, warmup):
-    from oracle.convnext_moe_oracle import OracleConfig, param_shapes
-    from sm3det_b200.synth import make_images, make_state_dict
+    """fwd+bwd (the bench metric) and eval forward (what north_star names as the CPU baseline) of the oracle port."""
+    from sm3det_b200.synth import make_images
     # torch's CPU kernels stop scaling (and then collapse: 143 s/img at 128 threads vs 1.5 s at 16 on the 128-thread
     # B200 host, profiles/r01_cpu_threads.txt) long before the box runs out of cores: use the best-performing count.
     threads = int(os.environ.get('SM3_CPU_THREADS', min(16, os.cpu_count() or 1)))
     torch.set_num_threads(threads)
-    cfg = OracleConfig(**MODEL_KW)
-    sd = make_state_dict(param_shapes(cfg), 0, True)
+    fwd, sd = oracle_model(args.config)
     x = make_images(images, args.size, args.size, seed=1234)
-    cpu_reference_step(sd, cfg, make_images(1, 128, 128, seed=1))     # thread-pool / allocator warm-up, not timed
+    oracle_step(fwd, sd, make_images(1, 128, 128, seed=1))     # thread-pool / allocator warm-up, not timed
     for _ in range(warmup):
-        cpu_reference_step(sd, cfg, x)
+        oracle_step(fwd, sd, x)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(sd, cfg, x)
+        oracle_step(fwd, sd, x)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return images / dt, dt, threads
+    with torch.no_grad():
+        t1 = time.perf_counter()
+        fwd(sd, x, False)
+        dt_fwd = time.perf_counter() - t1
+    return images / dt, dt, threads, images / dt_fwd
+
+
+def cpu_baseline_entry(args, ips, dt, threads, fwd_ips):
+    return {'value': ips, 'unit': 'img/s', 'cores': threads, 'kind': 'port', 'host_cpus': os.cpu_count(),
+            'eval_forward_img_s': fwd_ips,
+            'sample': f'fwd+bwd of {args.cpu_images} workload image(s) per step (oracle port = the reference\'s torch CPU fp32 '
+                      f'ops in its order), {threads} of {os.cpu_count()} host threads (torch CPU stops scaling beyond, '
+                      f'profiles/r01_cpu_threads.txt), {dt:.1f} s/step; eval_forward_img_s = one eval forward of the same images'}
 
 
 def run_reference(args):
@@ -118,61 +197,98 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    ips, dt, threads = time_cpu_reference(args, args.cpu_images, steps, warmup)
-    cfg = workload_config(args, args.gpus)
+    ips, dt, threads, fwd_ips = time_cpu_reference(args, args.cpu_images, steps, warmup)
+    _, _, _, scaling, _ = resolve(args, args.gpus)
     line = {'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'img/s', 'n_gpus': args.gpus, 'steps': steps,
-            'warmup': warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-            'cpu_baseline': {'value': ips, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
-                             'sample': f'{args.cpu_images} images of the workload per step (fwd+bwd, torch CPU fp32, '
-                                       f'{threads} threads); reference python executes the same ops'},
+            'warmup': warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, args.gpus),
+            'cpu_baseline': cpu_baseline_entry(args, ips, dt, threads, fwd_ips),
             'e2e': {'value': ips, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
 
+def time_gpu_eager(args, micro):
+    """The GPU-side comparator: the reference's own module graph -- here its oracle port, the same
+    torch ops -- run in eager PyTorch on this B200 (cuBLAS / cuDNN / ATen kernels), fp32 and with TF32 allowed, timed with
+    CUDA events like tools/analysis_tools/benchmark.py:118-146.  Not the product: the number our kernels have to beat."""
+    from sm3det_b200.synth import make_images
+    fwd, sd = oracle_model(args.config)
+    sd = {k: v.cuda() for k, v in sd.items()}
+    x = make_images(micro, args.size, args.size, seed=1234).cuda()
+    out = {'kind': 'oracle port (the reference\'s torch ops) in eager PyTorch on cuda:0', 'micro_batch': micro, 'unit': 'img/s'}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for name, tf32 in (('fp32', False), ('tf32', True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                oracle_step(fwd, sd, x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            e0.record()
+            for _ in range(n):
+                oracle_step(fwd, sd, x)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = micro * n / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out['peak_mem_gb'] = torch.cuda.max_memory_allocated() / 2 ** 30
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
-def gemm_roofline(net, x, peaks):
-    """Instrumented pass: CUDA-event time of every tensor-core GEMM launch in one fwd+bwd step and its
-    algorithmic FLOPs (2*M*N*K; grouped launches count live rows only via the plan's token count)."""
+TENSOR_OPS = ('gemm', 'ffn_fused_fwd', 'ffn_fused_bwd')     # ops.* entry points that launch tcgen05 kernels
+
+
+def gemm_roofline(step_fn, peaks):
+    """Instrumented pass: CUDA-event time of every tensor-core launch in one fwd+bwd micro-batch and its algorithmic FLOPs
+    (2*M*N*K per GEMM; the fused FFN kernels report the FLOPs of the GEMMs the algorithm needs, not their recomputation)."""
     from sm3det_b200 import ops
     rec = []
-    orig = ops.gemm
+    orig = {n: getattr(ops, n) for n in TENSOR_OPS if hasattr(ops, n)}
 
-    def timed(**kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig(**kw)
-        e1.record()
-        rows = kw['M']
-        if kw.get('sched', 0) == ops.SCHED_GROUPED:
-            rows = kw.get('_live_rows', rows)
-        flops = 2.0 * rows * kw['N'] * kw['K']
-        rec.append((e0, e1, flops, kw['M'], kw['N'], kw['K'], kw.get('sched', 0), 4.0 * (rows * kw['K'] + kw['N'] * kw['K'] + rows * kw['N'])))
-        return r
+    def wrap(name, fn):
+        def timed(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            if name == 'gemm':
+                rows = kw['M']
+                flops = 2.0 * rows * kw['N'] * kw['K']
+                byts = 4.0 * (rows * kw['K'] + kw['N'] * kw['K'] + rows * kw['N'])
+                shape = (kw['M'], kw['N'], kw['K'], kw.get('sched', 0))
+            else:
+                flops, byts, shape = ops.fused_cost(name, *a, **kw)
+            rec.append((e0, e1, flops, byts, name, shape))
+            return r
+        return timed
 
-    ops.gemm = timed
+    for n, f in orig.items():
+        setattr(ops, n, wrap(n, f))
     try:
-        outs, loss = net(x)
-        (sum(o.mean() for o in outs) + loss).backward()
+        step_fn()
         torch.cuda.synchronize()
     finally:
-        ops.gemm = orig
+        for n, f in orig.items():
+            setattr(ops, n, f)
     tot_ms = sum(a.elapsed_time(b) for a, b, *_ in rec)
     if os.environ.get('SM3_GEMM_TABLE'):
         with open(os.environ['SM3_GEMM_TABLE'], 'w') as f:
-            for a, b, fl, M, N, K, sched, _ in rec:
+            for a, b, fl, _, name, shape in rec:
                 ms = a.elapsed_time(b)
-                f.write(f'M={M} N={N} K={K} sched={sched} ms={ms:.4f} tflops={fl / ms * 1e-9:.1f}\n')
-    # grouped / split-K launches: M (or K) is the padded pair space; close enough for the aggregate (pad <= 1.5 %)
+                f.write(f'{name} shape={shape} ms={ms:.4f} tflops={fl / ms * 1e-9:.1f}\n')
     tot_flops = sum(r[2] for r in rec)
     peak = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0
     ach = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-    return {'bound': 'tensor', 'kernel': 'gemm_bf16x3_kernel (all launches of one fwd+bwd step)', 'achieved': ach,
-            'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None, 'launches': len(rec),
-            'algorithmic_bytes_per_launch': sum(r[7] for r in rec) / max(len(rec), 1),
-            'gemm_ms_per_step': tot_ms,
+    return {'bound': 'tensor', 'kernel': 'tcgen05 kernels (gemm_bf16x3 + fused FFN), all launches of one fwd+bwd micro-batch',
+            'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None, 'launches': len(rec),
+            'algorithmic_bytes_per_launch': sum(r[3] for r in rec) / max(len(rec), 1),
+            'tensor_ms_per_micro_batch': tot_ms, 'algorithmic_tflop_per_micro_batch': tot_flops / 1e12,
             'note': 'algorithmic fp32 FLOPs; each costs 3 bf16 tensor-core MACs (hi*hi+hi*lo+lo*hi), so the tensor pipe '
-                    'runs at 3x this rate; peak = measured cuBLAS bf16 (sustained) from MEASURED_PEAKS.json'
+                    'runs at 3x this rate (ceiling of frac = 1/3); peak = measured cuBLAS bf16 (sustained) from MEASURED_PEAKS.json'
                     if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 'peak = fallback 1.59 PFLOP/s'}
 
 
@@ -232,7 +348,8 @@ def moe_roofline(net, x, peaks):
            'layers': len(seq), 'achieved': by / (ms * 1e-3) / 1e9 if ms else 0.0, 'peak': peak, 'unit': 'GB/s',
            'ms': ms, 'algorithmic_bytes': by, 'expert_tflops': fl / (ms * 1e-3) / 1e12 if ms else 0.0,
            'note': 'the expert GEMM pair is tensor-bound (16kTC^2 FLOP on 3-pass split-bf16), so the sequence cannot reach the '
-                   'HBM roofline; dispatch_only isolates the HBM-bound gather + scatter kernels'}
+                   'HBM roofline (the north-star 60 % target is NOT met on the sequence as written); dispatch_only isolates '
+                   'the HBM-bound gather + scatter kernels'}
     out['frac'] = out['achieved'] / peak
     if dms:
         out['dispatch_only'] = {'achieved': dby / (dms * 1e-3) / 1e9, 'frac': dby / (dms * 1e-3) / 1e9 / peak, 'ms': dms,
@@ -240,10 +357,36 @@ def moe_roofline(net, x, peaks):
     return out
 
 
+def build_model(args, world, ep):
+    import torch.distributed as dist
+    from sm3det_b200.synth import make_state_dict
+    c = CONFIGS[args.config]
+    if c['family'] == 'convnext':
+        from sm3det_b200 import ConvNeXt_moe_MultiInput
+        net = ConvNeXt_moe_MultiInput(**c['kw'])
+    else:
+        from sm3det_b200 import LSKNet_moe_MultiInput
+        net = LSKNet_moe_MultiInput(**c['kw'])
+    # seeded "trained-like" weights keyed by state_dict name (the product leg never touches oracle/)
+    sd = make_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 0, True)
+    net.load_state_dict(sd, strict=True)
+    del sd
+    net = net.cuda().train()
+    model = net
+    if ep:
+        from sm3det_b200.expert_parallel import enable_expert_parallel
+        enable_expert_parallel(net, dist.new_group(list(range(world))))
+    if world > 1:
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=False,
+                                                          gradient_as_bucket_view=True)
+    return net, model
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from sm3det_b200 import ConvNeXt_moe_MultiInput, _lib
-    from sm3det_b200.synth import make_images, make_state_dict
+    from sm3det_b200 import _lib
+    from sm3det_b200.synth import make_images
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -253,28 +396,29 @@ def run_ours(args):
         dist.init_process_group('nccl')
     lib = _lib.load()
     assert lib.sm3_device_supported() == 1, 'bench.py needs an sm_100 (B200) device'
-
-    net = ConvNeXt_moe_MultiInput(**MODEL_KW)
-    # seeded "trained-like" weights keyed by state_dict name (the product leg never touches oracle/)
-    sd = make_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 0, True)
-    net.load_state_dict(sd, strict=True)
-    net = net.cuda().train()
-    model = net
-    if world > 1 and args.expert_parallel:
-        from sm3det_b200.expert_parallel import enable_expert_parallel
-        enable_expert_parallel(net, dist.new_group(list(range(world))))
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=False,
-                                                          gradient_as_bucket_view=True)
-    B, S = args.batch, args.size
+    c, B, MB, scaling, ep = resolve(args, world)
+    net, model = build_model(args, world, ep)
+    S = args.size
+    n_micro = B // MB
     host_x = make_images(B, S, S, seed=1234 + rank).pin_memory()
     dev_x = host_x.cuda()
 
-    def step(x):
+    def micro_step(x):
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.amp):
             outs, loss = model(x)
-        tot = sum(o.float().mean() for o in outs) + loss
+        tot = (sum(o.float().mean() for o in outs) + loss) / n_micro
         tot.backward()
+        return tot.detach()
+
+    def step(x):
+        """one optimizer step's worth of work: fwd+bwd over the per-GPU batch, gradients accumulated over the micro-batches,
+        all-reduced (DDP) once, during the last micro-batch's backward"""
+        tot = None
+        for i in range(n_micro):
+            sync_ctx = model.no_sync() if (world > 1 and i + 1 < n_micro) else contextlib.nullcontext()
+            with sync_ctx:
+                t = micro_step(x[i * MB:(i + 1) * MB])
+            tot = t if tot is None else tot + t
         return tot
 
     def sync():
@@ -333,7 +477,7 @@ def run_ours(args):
         main.wait_event(ready[cur])
         tot = step(bufs[cur])
         freed[cur].record(main)
-        host_res[cur].copy_(tot.detach(), non_blocking=True)      # D2H read of the step result (4 bytes)
+        host_res[cur].copy_(tot, non_blocking=True)      # D2H read of the step result (4 bytes)
         res_ready[cur].record(main)
         if i > 0:
             res_ready[cur ^ 1].synchronize()
@@ -345,43 +489,58 @@ def run_ours(args):
     sync()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     t = torch.tensor([ms, ms_e2e], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
+    del bufs
     if rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        ep_mode = world > 1 and args.expert_parallel
         roof = roof_moe = None
-        if not ep_mode and not args.amp:        # the instrumented extra passes are rank-0 only; expert parallelism needs every rank in each layer
-            roof = gemm_roofline(net, dev_x, peaks)
+        if not ep and not args.amp:        # the instrumented extra passes are rank-0 only; expert parallelism needs every rank in each layer
+            xm = dev_x[:MB]
+
+            def one():
+                outs, loss = net(xm)
+                (sum(o.mean() for o in outs) + loss).backward()
+            roof = gemm_roofline(one, peaks)
             net.zero_grad(set_to_none=True)
-            try:   # measured DRAM traffic of the GEMM launches of one step (ncu dram__bytes_read+write, profiles/)
-                tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
+            try:   # measured DRAM traffic of the tensor-core launches of one micro-batch (ncu dram__bytes_read+write, profiles/)
+                tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_gemm_traffic.json')))
                 roof['traffic'] = tr['bytes_per_launch']
                 roof['traffic_note'] = tr['note']
             except Exception:
                 pass
-            roof_moe = moe_roofline(net, dev_x, peaks)
+            if c['family'] == 'convnext':
+                roof_moe = moe_roofline(net, xm, peaks)
         line = {'metric': METRIC, 'value': B * world / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
                 'dtype': ('bf16 GEMM operands (single pass), fp32 accumulate and fp32 elsewhere -- optional AMP recipe, not the headline'
                           if args.amp else 'f32 (bf16 hi+lo split operands on tcgen05, fp32 accumulate; SIMT fp32 elsewhere)'),
                 'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks,
                 'e2e': {'value': B * world / (ms_e2e * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
-                'gpu_launches': launches, 'roofline': roof, 'roofline_moe': roof_moe}
+                'gpu_launches': launches, 'peak_mem_gb': peak_mem, 'roofline': roof, 'roofline_moe': roof_moe}
+        if world == 1 and not args.no_gpu_eager:
+            del model, net
+            torch.cuda.empty_cache()
+            try:
+                line['gpu_eager'] = time_gpu_eager(args, MB)
+                line['gpu_eager']['ours_over_eager_fp32'] = line['value'] / line['gpu_eager']['fp32']
+                line['gpu_eager']['ours_over_eager_tf32'] = line['value'] / line['gpu_eager']['tf32']
+            except Exception as e:                      # a comparator failure must not lose the bench line
+                line['gpu_eager'] = {'error': f'{type(e).__name__}: {e}'[:300]}
         if world == 1 and not args.no_cpu_baseline:
-            ips, dt, threads = time_cpu_reference(args, args.cpu_images, 1, 0)
-            line['cpu_baseline'] = {'value': ips, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'one fwd+bwd of {args.cpu_images} workload images (oracle port = the '
-                                              f'reference\'s torch CPU ops), {threads} threads, {dt:.1f} s'}
+            ips, dt, threads, fwd_ips = time_cpu_reference(args, args.cpu_images, 1, 0)
+            line['cpu_baseline'] = cpu_baseline_entry(args, ips, dt, threads, fwd_ips)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

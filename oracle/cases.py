@@ -28,6 +28,28 @@ CASES = {
                                        img=(2, 128, 128), mode='train', weights='trained', stride=2),
 }
 
+# ---- full-size cases: the shapes bench.py times (BASELINE configs 2/3, the shipped k=3 recipe, config 4's widths) -----
+# One 1024^2 (or 512^2) image each; fixtures keep strided output samples, compact routing (int8 indices + the oracle's own
+# (k)-vs-(k+1) logit gap per token, which is what decides whether a routing flip is a numerical tie) and gradient digests.
+CFG2_KW = dict(arch='tiny', MoE_Block_inds=[[], [], [0, 2, 4, 6, 8], [0, 2]], num_experts=8, top_k=2)
+CFG4_KW = dict(arch='base', MoE_Block_inds=[[0, 1, 2], [0, 1, 2], list(range(27)), [0, 1, 2]], num_experts=16, top_k=2)
+FULL_CASES = {
+    'cfg2_t_e8k2_1024_eval': dict(kw=dict(CFG2_KW), img=(1, 1024, 1024), mode='eval', weights='trained', stride=8),
+    'cfg2_t_e8k2_1024_train_clean': dict(kw=dict(CFG2_KW, noisy_gating=False), img=(1, 1024, 1024), mode='train',
+                                         weights='trained', stride=8),
+    'cfg2_t_e8k2_1024_train_noisy': dict(kw=dict(CFG2_KW), img=(1, 1024, 1024), mode='train_noisy', weights='trained',
+                                         stride=8),
+    # configs/SM3Det/SM3Det_convnext_t.py:15-19 (shipped recipe: top_k = 3)
+    'ship_t_e8k3_512_train_noisy': dict(kw=dict(CFG2_KW, top_k=3), img=(2, 512, 512), mode='train_noisy', weights='trained',
+                                        stride=4),
+    # BASELINE config 4: ConvNeXt-B, E = 16, all 36 blocks MoE (C = 128 / 256 / 512 / 1024)
+    'cfg4_b_e16k2_512_train_clean': dict(kw=dict(CFG4_KW, noisy_gating=False), img=(1, 512, 512), mode='train',
+                                         weights='trained', stride=4),
+}
+for _v in FULL_CASES.values():
+    _v['full'] = True
+CASES.update(FULL_CASES)
+
 
 def upstream_grads(outs, seed=99):
     """Seeded upstream gradients for the 4 outputs: randn / sqrt(numel)."""
@@ -46,11 +68,11 @@ def make_noise(cfg, n_tokens_per_layer, seed=7):
     return out
 
 
-def summarize_grad(g: torch.Tensor):
+def summarize_grad(g: torch.Tensor, full_below=4096, samples=256):
     g = g.detach().float().reshape(-1)
-    if g.numel() <= 4096:
+    if g.numel() <= full_below:
         return dict(full=g.clone())
-    idx = torch.linspace(0, g.numel() - 1, 256).long()
+    idx = torch.linspace(0, g.numel() - 1, samples).long()
     return dict(sample=g[idx].clone(), idx=idx, l2=g.double().norm().item(), s=g.double().sum().item())
 
 
@@ -71,6 +93,14 @@ LSK_CASES = {
                                            img=(3, 64, 64), mode='train_noisy'),
 }
 
+# BASELINE config 5 at its real widths (configs/SM3Det/SM3Det_lsk_s.py:14-25), one 1024^2 image
+LSK_S_KW = dict(embed_dims=[64, 128, 320, 512], depths=[2, 2, 4, 2], MoE_Block_inds_fc1=[[], [0], [0, 2], [0]],
+                MoE_Block_inds_fc2=[[], [0], [0, 2], [0]], num_experts=4, top_k=2)
+LSK_CASES.update({
+    'lsk_s_cfg5_1024_eval': dict(kw=dict(LSK_S_KW), img=(1, 1024, 1024), mode='eval', full=True, stride=8),
+    'lsk_s_cfg5_1024_train_noisy_drop': dict(kw=dict(LSK_S_KW, drop_rate=0.1), img=(1, 1024, 1024), mode='train_noisy',
+                                             full=True, stride=8),
+})
 
 VAN_MINI = dict(embed_dims=[32, 64, 96, 128], depths=[1, 1, 2, 1], mlp_ratios=[4, 4, 2, 2])
 LSK_CASES.update({

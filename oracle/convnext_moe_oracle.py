@@ -181,7 +181,7 @@ def prob_in_top_k(clean, noisy, stddev, noisy_top_values, k):
     batch = clean.size(0)
     m = noisy_top_values.size(1)
     flat = noisy_top_values.flatten()
-    pos_in = torch.arange(batch) * m + k
+    pos_in = (torch.arange(batch) * m + k).to(flat.device)                    # .to(device): :157
     thr_in = torch.unsqueeze(torch.gather(flat, 0, pos_in), 1)
     is_in = torch.gt(noisy, thr_in)
     thr_out = torch.unsqueeze(torch.gather(flat, 0, pos_in - 1), 1)
@@ -190,8 +190,12 @@ def prob_in_top_k(clean, noisy, stddev, noisy_top_values, k):
     return torch.where(is_in, prob_in, prob_out)
 
 
+_FORCE = None   # iterator of forced top-k index tensors (set by *_forward(forced_idx=...)); test-only
+
+
 def noisy_top_k_gating(x, sd, p, cfg: OracleConfig, train: bool, noise=None, noise_epsilon=1e-2):
     """MoE_layer.noisy_top_k_gating :194-223.  ``noise`` (optional [T,E]) replaces randn_like :203."""
+    global _FORCE
     E, k = cfg.num_experts, cfg.top_k
     if cfg.gate == 'linear':
         clean = x @ sd[p + 'w_gate']
@@ -210,6 +214,11 @@ def noisy_top_k_gating(x, sd, p, cfg: OracleConfig, train: bool, noise=None, noi
     top_logits, top_idx = logits.topk(min(k + 1, E), dim=-1)
     top_k_logits = top_logits[:, :k]
     top_k_idx = top_idx[:, :k]
+    if _FORCE is not None:
+        # TEST-ONLY teacher forcing (no reference counterpart): route with the supplied top-k indices so the CUDA
+        # path and this oracle can be compared element-wise on tokens whose (k)-vs-(k+1) logits are a numerical tie
+        top_k_idx = next(_FORCE).long()
+        top_k_logits = logits.gather(1, top_k_idx)
     top_k_gates = torch.softmax(top_k_logits, -1)
     zeros = torch.zeros_like(logits, requires_grad=True)
     gates = zeros.scatter(-1, top_k_idx, top_k_gates)
@@ -242,7 +251,7 @@ def moe_layer(x, sd, p, cfg: OracleConfig, train: bool, noise=None, loss_coef=1e
             for e in range(cfg.num_experts)]
     # combine :269-284
     stitched = torch.cat(outs, 0).mul(nonzero_gates)
-    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True)
+    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True, device=stitched.device)   # :277
     y = zeros.index_add(0, batch_index, stitched.float())
     if record is not None:
         record.append(dict(prefix=p, x=x.detach(), top_idx=info['top_idx'].detach(),
@@ -290,12 +299,25 @@ def convnext_block(x, sd, p, cfg: OracleConfig, is_moe: bool, dpr: float, train:
 def backbone_forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, x, train: bool = False,
                      noise: Optional[List[torch.Tensor]] = None,
                      dp_masks: Optional[List[torch.Tensor]] = None,
-                     record: Optional[list] = None, pre_gamma: Optional[list] = None):
+                     record: Optional[list] = None, pre_gamma: Optional[list] = None,
+                     forced_idx: Optional[List[torch.Tensor]] = None):
     """ConvNeXt_moe.forward :582-600 / ConvNeXt_moe_MultiInput.forward :794-820.
+
+    ``forced_idx`` (test-only): per MoE layer, in forward order, a [T,k] index tensor that replaces the layer's own
+    top-k choice (see noisy_top_k_gating).
 
     ``x``: Tensor [N,3,H,W] or list of such (concatenated on N, :798-800).
     Returns ``tuple(outs)`` or ``(tuple(outs), gate_loss)`` when at least one MoE block ran.
     """
+    global _FORCE
+    _FORCE = None if forced_idx is None else iter(forced_idx)
+    try:
+        return _backbone_forward(sd, cfg, x, train, noise, dp_masks, record, pre_gamma)
+    finally:
+        _FORCE = None
+
+
+def _backbone_forward(sd, cfg, x, train, noise, dp_masks, record, pre_gamma):
     if isinstance(x, (list, tuple)):
         x = torch.cat(list(x), dim=0)
     C, depths = cfg.channels, cfg.depths

@@ -27,6 +27,21 @@ def moe_token_counts(cfg, n, h, w):
     return counts
 
 
+def moe_digest(r, full):
+    """What a fixture keeps of one MoE layer.  Full-size cases: int8 indices + the (k)-vs-(k+1) logit gap per token (the
+    margin a routing flip is judged against) instead of the gate values."""
+    d = dict(prefix=r['prefix'], importance=r['importance'], load=r['load'], loss=r['loss'])
+    if not full:
+        d.update(top_idx=r['top_idx'].to(torch.int16), top_gates=r['top_gates'])
+        return d
+    k = r['top_idx'].shape[1]
+    lg = r['logits']
+    top = lg.topk(min(k + 1, lg.shape[1]), dim=-1).values
+    d.update(top_idx=r['top_idx'].to(torch.int8), logit_scale=float(lg.abs().max()),
+             gap=(top[:, k - 1] - top[:, k]).float() if top.shape[1] > k else torch.full((lg.shape[0],), float('inf')))
+    return d
+
+
 def run_case(name, spec):
     kw = dict(spec['kw'])
     cfg = OracleConfig(**kw)
@@ -77,8 +92,7 @@ def run_case(name, spec):
     gold['outs'] = [o.detach()[:, :, ::st, ::st].clone() for o in r_outs]
     gold['out_l2'] = [o.detach().double().norm().item() for o in r_outs]
     gold['stride'] = st
-    gold['moe'] = [dict(prefix=r['prefix'], top_idx=r['top_idx'].to(torch.int16), top_gates=r['top_gates'],
-                        importance=r['importance'], load=r['load'], loss=r['loss']) for r in record]
+    gold['moe'] = [moe_digest(r, spec.get('full', False)) for r in record]
     if mode != 'eval':
         ups = upstream_grads(r_outs)
         (sum((o * g).sum() for o, g in zip(r_outs, ups)) + (r_loss if has_loss else 0.0)).backward()
@@ -90,8 +104,16 @@ def run_case(name, spec):
                 assert og is None or float(og.abs().max()) == 0.0, pname
                 continue
             assert og is not None, pname
-            assert torch.equal(p.grad, og), f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
-            grads[pname] = summarize_grad(p.grad)
+            if spec.get('full', False):
+                # multi-threaded CPU reductions over >= 10^5 tokens are not run-to-run bit-stable (the reference differs
+                # from ITSELF in the last bit between runs); forward outputs, loss and routing above stay bit-exact
+                assert float((p.grad - og).abs().max()) <= 1e-5 * float(og.abs().max()) + 1e-12, \
+                    f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
+            else:
+                assert torch.equal(p.grad, og), f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
+            # thousands of expert parameters (config 4): keep the digests small -- the GPU test compares full gradients
+            # against the live oracle anyway, the digests only pin oracle == reference
+            grads[pname] = summarize_grad(p.grad, 256, 24) if len(shapes) > 1500 else summarize_grad(p.grad)
         gold['grads'] = grads
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + '.pt')
@@ -159,10 +181,11 @@ def run_lsk_case(name, spec):
     if has_loss:
         assert torch.equal(r_loss, o_loss), (r_loss, o_loss)
         gold['gate_loss'] = r_loss.detach().clone()
-    gold['outs'] = [o.detach().clone() for o in r_outs]
-    gold['stride'] = 1
-    gold['moe'] = [dict(prefix=r['prefix'], top_idx=r['top_idx'].to(torch.int16), top_gates=r['top_gates'],
-                        importance=r['importance'], load=r['load'], loss=r['loss']) for r in record]
+    st = spec.get('stride', 1)
+    gold['outs'] = [o.detach()[:, :, ::st, ::st].clone() for o in r_outs]
+    gold['out_l2'] = [o.detach().double().norm().item() for o in r_outs]
+    gold['stride'] = st
+    gold['moe'] = [moe_digest(r, spec.get('full', False)) for r in record]
     if mode != 'eval':
         ups = upstream_grads(r_outs)
         (sum((o * g).sum() for o, g in zip(r_outs, ups)) + (r_loss if has_loss else 0.0)).backward()
@@ -174,7 +197,13 @@ def run_lsk_case(name, spec):
                 assert og is None or float(og.abs().max()) == 0.0, pname
                 continue
             assert og is not None, pname
-            assert torch.equal(p.grad, og), f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
+            if spec.get('full', False):
+                # multi-threaded CPU reductions over >= 10^5 tokens are not run-to-run bit-stable (the reference differs
+                # from ITSELF in the last bit between runs); forward outputs, loss and routing above stay bit-exact
+                assert float((p.grad - og).abs().max()) <= 1e-5 * float(og.abs().max()) + 1e-12, \
+                    f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
+            else:
+                assert torch.equal(p.grad, og), f'{name}: grad {pname} differs by {(p.grad - og).abs().max()}'
             grads[pname] = summarize_grad(p.grad)
         gold['grads'] = grads
         new_sd = net.state_dict()

@@ -150,8 +150,12 @@ def batch_norm(x, sd, p, cfg: LskConfig, train: bool, bn_state: Optional[dict]):
     return y
 
 
+_FORCE = None   # iterator of forced top-k index tensors (set by *_forward(forced_idx=...)); test-only
+
+
 def noisy_top_k_gating(x, sd, p, cfg: LskConfig, train: bool, noise=None, noise_epsilon=1e-2):
     """MoE_layer.noisy_top_k_gating lsk_moe.py:163-192."""
+    global _FORCE
     E, k = cfg.num_experts, cfg.top_k
     if cfg.gate == 'linear':
         clean = x @ sd[p + 'w_gate']
@@ -168,6 +172,11 @@ def noisy_top_k_gating(x, sd, p, cfg: LskConfig, train: bool, noise=None, noise_
         logits = clean
     top_logits, top_idx = logits.topk(min(k + 1, E), dim=-1)
     top_k_logits, top_k_idx = top_logits[:, :k], top_idx[:, :k]
+    if _FORCE is not None:
+        # TEST-ONLY teacher forcing (no reference counterpart): route with the supplied top-k indices so the CUDA
+        # path and this oracle can be compared element-wise on tokens whose (k)-vs-(k+1) logits are a numerical tie
+        top_k_idx = next(_FORCE).long()
+        top_k_logits = logits.gather(1, top_k_idx)
     top_k_gates = torch.softmax(top_k_logits, -1)
     zeros = torch.zeros_like(logits, requires_grad=True)
     gates = zeros.scatter(-1, top_k_idx, top_k_gates)
@@ -202,7 +211,7 @@ def moe_conv_layer(x, sd, p, cfg: LskConfig, train: bool, noise=None, loss_coef=
                          sd[p + f'experts.{e}.bias'])
             outs.append(o.reshape(expert_inputs[e].shape[0], -1))
     stitched = torch.cat(outs, 0).mul(nonzero_gates)
-    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True)
+    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True, device=stitched.device)
     y = zeros.index_add(0, batch_index, stitched)                              # :263 (no .float())
     if record is not None:
         record.append(dict(prefix=p, x=x.detach(), top_idx=info['top_idx'].detach(),
@@ -307,9 +316,18 @@ def block(x, sd, p, cfg: LskConfig, moe1, moe2, dpr, train, bn_state, noise_it, 
 def lsk_backbone_forward(sd: Dict[str, torch.Tensor], cfg: LskConfig, x, train: bool = False,
                          noise: Optional[List[torch.Tensor]] = None, drop_masks: Optional[List[torch.Tensor]] = None,
                          dp_masks: Optional[List[torch.Tensor]] = None, record: Optional[list] = None,
-                         bn_state: Optional[dict] = None):
+                         bn_state: Optional[dict] = None, forced_idx: Optional[List[torch.Tensor]] = None):
     """LSKNet_moe_MultiInput.forward :740-765 (datasets=None path) + forward_features :716-739,
     or LSKNet_moe.forward_features :541-559 when ``cfg.multi_input`` is False."""
+    global _FORCE
+    _FORCE = None if forced_idx is None else iter(forced_idx)
+    try:
+        return _lsk_backbone_forward(sd, cfg, x, train, noise, drop_masks, dp_masks, record, bn_state)
+    finally:
+        _FORCE = None
+
+
+def _lsk_backbone_forward(sd, cfg, x, train, noise, drop_masks, dp_masks, record, bn_state):
     if isinstance(x, (list, tuple)):
         x = torch.cat(list(x), dim=0)
     D, depths = list(cfg.embed_dims), list(cfg.depths)

@@ -106,21 +106,26 @@ class PackCache:
     """Per-module cache of the pre-split (bf16 hi/lo, tile-ordered) weight images the GEMM bulk-copies.
 
     An entry is rebuilt when any of its parameters changed in place (tensor version counters, which every
-    optimizer step / load_state_dict bumps) or moved (data_ptr); it lives and dies with the owning module.
+    optimizer step / load_state_dict bumps) or moved (data_ptr, device); it lives and dies with the owning module.
+    Writes that bypass the version counter (``p.data.copy_()``, EMA swaps through ``.data``) need an explicit
+    ``invalidate()`` -- ``ConvNeXtBlock._apply`` / ``load_state_dict`` hooks call it for the common cases.
     """
 
     def __init__(self):
         self._d = {}
 
+    def invalidate(self):
+        self._d.clear()
+
     def get(self, name, params, transposed):
         from . import ops
-        key = tuple(p._version for p in params) + (params[0].data_ptr(),)
+        key = tuple(p._version for p in params) + (params[0].data_ptr(), str(params[0].device))
         hit = self._d.get((name, transposed))
         if hit is not None and hit[0] == key:
             return hit[1]
-        with torch.no_grad():
-            packed = ops.pack_weight(params[0], transposed=transposed, groups=len(params),
-                                     out=None if hit is None else hit[1][0])
+        reuse = None if hit is None or hit[1][0].device != params[0].device else hit[1][0]   # never write into a buffer
+        with torch.no_grad():                                                                # left behind on another GPU
+            packed = ops.pack_weight(params[0], transposed=transposed, groups=len(params), out=reuse)
         self._d[(name, transposed)] = (key, packed)
         return packed
 
@@ -143,6 +148,14 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones((in_channels)), requires_grad=True)
         self.drop_path_rate = float(drop_path_rate)
         self._packs = PackCache()
+
+    def _apply(self, fn, recurse=True):      # .to() / .cuda() / .half(): cached images no longer describe the weights
+        self._packs.invalidate()
+        return super()._apply(fn, recurse)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._packs.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def _row_scale(self, x):
         """timm DropPath as a per-token scale (per-sample Bernoulli(keep) / keep), None when inactive."""
@@ -317,15 +330,16 @@ class ConvNeXt_moe(BaseModule):
 
     def forward(self, x, record=None):
         self._check_input(x)
-        self._select_precision()
-        return self._trunk(self._stem(x), record)
+        with self._precision():
+            return self._trunk(self._stem(x), record)
 
-    def _select_precision(self):
+    def _precision(self):
         """Mixed-precision recipe (configs train with fp16=dict(loss_scale='dynamic')): under torch.autocast, or with
-        ``self.amp = True``, the tensor-core GEMMs of this forward AND its backward run single-pass bf16 (fp32
-        accumulation); router, LayerNorm, depthwise conv and combine stay fp32 like the reference's autocast policy."""
+        ``self.amp = True``, the tensor-core GEMMs of this forward AND of its backward (ops.captures_precision) run
+        single-pass bf16 (fp32 accumulation); router, LayerNorm, depthwise conv and combine stay fp32 like the
+        reference's autocast policy.  The mode is scoped to this call, not a process global."""
         from . import ops
-        ops.set_gemm_precision('bf16' if (getattr(self, 'amp', False) or torch.is_autocast_enabled()) else 'fp32')
+        return ops.precision_scope(ops.autocast_passes(self))
 
     @staticmethod
     def _check_input(x):
@@ -443,5 +457,5 @@ class ConvNeXt_moe_MultiInput(ConvNeXt_moe):
             x = [x]
         x = torch.cat(list(x), dim=0)          # one shared stem for every modality (:798-801)
         self._check_input(x)
-        self._select_precision()
-        return self._trunk(self._stem(x), record)
+        with self._precision():
+            return self._trunk(self._stem(x), record)

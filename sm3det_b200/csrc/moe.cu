@@ -547,7 +547,8 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
   __shared__ float s_cimp[R_MAXE], s_cload[R_MAXE];
   __shared__ float s_dtau;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool soft = (a.noise != nullptr) && (k < E);
+  const bool noisy = a.noise != nullptr;
+  const bool soft = noisy && (k < E);
   for (int e = warp; e < E; e += 8) {
     float ss = 0.f;
     for (int p = lane; p < PR; p += 32) { const float s = __ldg(a.sim + p * E + e); ss += s * s; }
@@ -595,23 +596,30 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
     for (int j = 0; j < R_MAXK; ++j) if (j < k && idx[j] == lane) dnz += g[j] * (dG[j] - sdot);
     const float l_e = (lane < E) ? __ldg(a.logits + t * E + lane) : 0.f;
     float dl = 0.f, dr = 0.f;
-    if (soft) {
-      const int idx_k = __ldg(a.top_idx_m + t * m + k);           // the (k+1)-th expert
-      const float thr_in = __ldg(a.top_vals + t * m + k), thr_out = __ldg(a.top_vals + t * m + k - 1);
-      float dthr = 0.f, dsig = 0.f, sg = 1.f, ep = 0.f;
+    if (noisy) {
+      // the gates depend on the noise scale sigma = softplus(r) + 0.01 whenever noise was added (also for k == E, where
+      // the load falls back to the hard count, :219-222); the soft-load terms exist only for k < E
+      float dsig = 0.f, sg = 1.f, ep = 0.f;
       if (lane < E) {
         sg = __ldg(a.sigma + t * E + lane);
         ep = __ldg(a.noise + t * E + lane);
-        const float z = (l_e - (mine_in ? thr_in : thr_out)) / sg;
-        const float dz = s_cload[lane] * 0.3989422804014327f * __expf(-0.5f * z * z);
-        dl = dz / sg;
-        dthr = -dz / sg;
-        dsig = -dz * z / sg;
       }
-      const float sum_in = warp_sum(mine_in ? dthr : 0.f);
-      const float sum_out = warp_sum(mine_in ? 0.f : dthr);
-      if (lane == idx_k) dnz += sum_in;
-      if (lane == idx[k - 1]) dnz += sum_out;
+      if (soft) {
+        const int idx_k = __ldg(a.top_idx_m + t * m + k);           // the (k+1)-th expert
+        const float thr_in = __ldg(a.top_vals + t * m + k), thr_out = __ldg(a.top_vals + t * m + k - 1);
+        float dthr = 0.f;
+        if (lane < E) {
+          const float z = (l_e - (mine_in ? thr_in : thr_out)) / sg;
+          const float dz = s_cload[lane] * 0.3989422804014327f * __expf(-0.5f * z * z);
+          dl = dz / sg;
+          dthr = -dz / sg;
+          dsig = -dz * z / sg;
+        }
+        const float sum_in = warp_sum(mine_in ? dthr : 0.f);
+        const float sum_out = warp_sum(mine_in ? 0.f : dthr);
+        if (lane == idx_k) dnz += sum_in;
+        if (lane == idx[k - 1]) dnz += sum_out;
+      }
       if (lane < E) {
         dsig += ep * dnz;
         dr = dsig * (1.0f - __expf(-(sg - 1e-2f)));                // sigmoid(r) from softplus(r) = sigma - 0.01
@@ -653,9 +661,11 @@ __global__ void __launch_bounds__(256) moe_router_bwd_kernel(const RouterBwdArgs
 int moe_router_bwd(const RouterBwdArgs& a, cudaStream_t stream) {
   SM3_REQUIRE(a.p && a.sim && a.temperature && a.top_idx && a.top_gate && a.dgate && a.logits && a.importance && a.dp &&
               a.dsim_hat && a.dtemperature, SM3_ERR_INVALID_ARG, "moe_router_bwd: null argument");
+  if (a.noise)
+    SM3_REQUIRE(a.sigma && a.dr, SM3_ERR_INVALID_ARG, "moe_router_bwd: noisy gating needs sigma and dr");
   if (a.noise && a.k < a.E)
-    SM3_REQUIRE(a.sigma && a.top_vals && a.top_idx_m && a.load && a.dr, SM3_ERR_INVALID_ARG,
-                "moe_router_bwd: noisy gating needs sigma, top_vals, top_idx_m, load and dr");
+    SM3_REQUIRE(a.top_vals && a.top_idx_m && a.load, SM3_ERR_INVALID_ARG,
+                "moe_router_bwd: the soft load (noisy, k < E) needs top_vals, top_idx_m and load");
   SM3_REQUIRE(a.P % 4 == 0 && a.P <= 256 && a.E <= R_MAXE && a.k <= R_MAXK, SM3_ERR_UNSUPPORTED_SHAPE, "moe_router_bwd: shape");
   const int Ppad = (a.P + 31) / 32 * 32;
   const size_t smem = sizeof(float) * 2 * (size_t)a.E * (Ppad + 1);

@@ -138,6 +138,7 @@ def _build_plan(ctx, cnt_all, seg_all, tile_group_s, num_tiles_s, pair_token, E,
     return plan
 
 
+@ops.captures_precision
 class EPMoEBlockFn(Function):
     """ConvNeXt MoE block with expert-parallel experts: dwconv -> LN -> router (local) -> P2P dispatch -> owned experts ->
     P2P combine (+ gamma + shortcut).  Same math as functional.MoEBlockFn; experts[...] are ALL E experts' parameters."""
@@ -187,7 +188,7 @@ class EPMoEBlockFn(Function):
             record.append(dict(v=v.clone(), top_idx=r['top_idx'], top_gate=r['top_gate'], importance=plan['importance'],
                                load=plan['load'], loss=plan['loss'], y=y, counts=plan['counts']))
         if train:
-            ctx.noisy = noise is not None and k < E
+            ctx.noisy = noise is not None     # gates depend on w_noise whenever noise was added, also for k == E
             ctx.save_for_backward(x, u, stats, v.clone(), h, xr, o, dww, lnw, gamma, wp, sim, tau, row_scale, r['top_idx'],
                                   r['top_gate'], r['logits'], r['p'], slot_of, plan['importance'], w1s[own], w2s[own], noise,
                                   r['sigma'], r['top_vals'], r['top_idx_m'], plan['load'], w_noise)

@@ -31,6 +31,7 @@ def _taps_flipped(dww):    # correlation taps for dgrad
     return dww.flip(2, 3).reshape(dww.shape[0], 49).t().contiguous()
 
 
+@ops.captures_precision
 class StemFn(Function):
     @staticmethod
     def forward(ctx, x, w, b, lnw, lnb, eps, ps):
@@ -75,6 +76,7 @@ class StemFn(Function):
         return None, dw, db, dlnw, dlnb, None, None
 
 
+@ops.captures_precision
 class DownsampleFn(Function):
     @staticmethod
     def forward(ctx, x, lnw, lnb, w, b, eps):
@@ -111,6 +113,7 @@ class DownsampleFn(Function):
         return dx.view(N, H, W, C), dlnw, dlnb, dw, db, None
 
 
+@ops.captures_precision
 class OutNormFn(Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):
@@ -153,6 +156,7 @@ def _block_front_bwd(dv, dout, x, u, stats, dww, lnw):
     return dx, ddww, ddwb, dlnw, dlnb
 
 
+@ops.captures_precision
 class DenseBlockFn(Function):
     @staticmethod
     def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps, packs):
@@ -225,6 +229,7 @@ def stack_expert_params(params):
             p.data = flat[i]
 
 
+@ops.captures_precision
 class MoEBlockFn(Function):
     """x -> dwconv -> LN -> router/plan/assign -> grouped expert GEMMs -> combine (+gamma, +shortcut)."""
 
@@ -252,7 +257,7 @@ class MoEBlockFn(Function):
             record.append(dict(v=v, top_idx=r['top_idx'], top_gate=r['top_gate'], importance=plan['importance'],
                                load=plan['load'], loss=plan['loss'], y=y, counts=plan['counts']))
         if train:
-            ctx.noisy = noise is not None and k < E
+            ctx.noisy = noise is not None     # gates depend on w_noise whenever noise was added, also for k == E
             ctx.save_for_backward(x, u, stats, v, h, o, dww, lnw, gamma, wp, sim, tau, row_scale, r['top_idx'],
                                   r['top_gate'], r['logits'], r['p'], slot_of, pair_token, plan['importance'],
                                   plan['seg_begin'], plan['seg_end'], plan['tile_group'], plan['num_m_tiles'],

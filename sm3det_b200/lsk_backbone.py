@@ -10,6 +10,7 @@ all compute goes through sm3det_b200.lsk_functional (NHWC fp32 end-to-end, NCHW 
 returned feature maps).  ``norm_cfg=dict(type='SyncBN')`` all-reduces the batch statistics over the default process
 group (NCCL) when one is initialised; at world size 1 it is plain BatchNorm, as in the reference.
 """
+import math
 import warnings
 from functools import partial
 
@@ -329,7 +330,24 @@ class LSKNet_moe(BaseModule):
         return out
 
     def init_weights(self):
+        """lsk_moe.py:473-523 / :766-826: init_cfg=None -> from-scratch initialisation (Linear trunc-normal 0.02,
+        LayerNorm (1, 0), Conv2d fan-out normal); a Pretrained dict -> up-cycle the dense checkpoint."""
         cfg = self.init_cfg
+        if cfg is None:
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.trunc_normal_(m.weight, mean=0., std=.02, a=-2., b=2.)
+                    if m.bias is not None:
+                        nn.init.constant_(m.bias, 0.)
+                elif isinstance(m, nn.LayerNorm):
+                    nn.init.constant_(m.weight, 1.0)
+                    nn.init.constant_(m.bias, 0.)
+                elif isinstance(m, nn.Conv2d):
+                    fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+                    nn.init.normal_(m.weight, 0., math.sqrt(2.0 / fan_out))
+                    if m.bias is not None:
+                        nn.init.constant_(m.bias, 0.)
+            return
         if isinstance(cfg, dict) and cfg.get('type') == 'Pretrained' and cfg.get('checkpoint'):
             ckpt = torch.load(cfg['checkpoint'], map_location='cpu')
             sd = ckpt.get('state_dict', ckpt.get('model', ckpt))
@@ -364,14 +382,14 @@ class LSKNet_moe(BaseModule):
             return tuple(outs), sum(gate_losses) / len(gate_losses)
         return tuple(outs)
 
-    def _select_precision(self):
+    def _precision(self):
         from . import ops
-        ops.set_gemm_precision('bf16' if (getattr(self, 'amp', False) or torch.is_autocast_enabled()) else 'fp32')
+        return ops.precision_scope(ops.autocast_passes(self))     # scoped to this call (see ops.captures_precision)
 
     def forward(self, x, record=None):
         self._check_input(x)
-        self._select_precision()
-        return self.forward_features(x, record)
+        with self._precision():
+            return self.forward_features(x, record)
 
 
 @ROTATED_BACKBONES.register_module()
@@ -400,6 +418,21 @@ class LSKNet_moe_MultiInput(LSKNet_moe):
             self.dataset_stems[dataset] = self.patch_embed1.proj
         self.patch_embed1 = _build_bn(norm_cfg, embed_dims[0])          # patch_embed1 becomes the BN only (:692-695)
 
+    def upcycle_state_dict(self, src):
+        """lsk_moe.py:806-813: on top of the expert remap, the dense checkpoint's stem conv 'patch_embed1.proj.*' moves to
+        'dataset_stems.single.*' and its BatchNorm 'patch_embed1.norm.*' to 'patch_embed1.*' (patch_embed1 is the BN only)."""
+        out = {}
+        for k, v in super().upcycle_state_dict(src).items():
+            if k.startswith('patch_embed1'):
+                if 'norm' in k:
+                    out[k.replace('.norm.', '.')] = v
+                else:
+                    for d in self.datasets:
+                        out[k.replace('patch_embed1.proj', 'dataset_stems.' + str(d))] = v
+            else:
+                out[k] = v
+        return out
+
     def forward_features(self, x, record=None):
         outs, gate_losses = [], []
         for i in range(self.num_stages):
@@ -415,10 +448,10 @@ class LSKNet_moe_MultiInput(LSKNet_moe):
             x = [x]
         x = torch.cat(list(x), dim=0)                                   # one shared stem (:751-754)
         self._check_input(x)
-        self._select_precision()
-        stem = self.dataset_stems['single']
-        x = LF.PatchEmbedFn.apply(x, stem.weight, stem.bias, stem.stride[0], True)
-        return self.forward_features(x, record)
+        with self._precision():
+            stem = self.dataset_stems['single']
+            x = LF.PatchEmbedFn.apply(x, stem.weight, stem.bias, stem.stride[0], True)
+            return self.forward_features(x, record)
 
 
 @ROTATED_BACKBONES.register_module()

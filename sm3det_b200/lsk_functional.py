@@ -46,6 +46,7 @@ def bn_batch_stats(s1, s2, n, running_mean, sync, group=None):
     return running_mean + d, (s2 / n - d * d).clamp_min_(0.0), float(n)
 
 
+@ops.captures_precision
 class BatchNormFn(Function):
     """y = BN(x) over all tokens (and all ranks when ``sync``); updates the running buffers in training mode."""
 
@@ -94,6 +95,7 @@ class BatchNormFn(Function):
         return dx, dw, db, None, None, None, None, None, None
 
 
+@ops.captures_precision
 class LinearFn(Function):
     """y[T,N] = act(x[T,K] @ w[N,K]^T + b); w may be a 1x1 conv weight [N,K,1,1]."""
 
@@ -129,6 +131,7 @@ class LinearFn(Function):
         return (None if dx is None else dx.view(*dy.shape[:-1], K)), dw.view(ctx.wshape), db, None
 
 
+@ops.captures_precision
 class DWConvFn(Function):
     @staticmethod
     def forward(ctx, x, w, b, ks, dil):
@@ -151,6 +154,7 @@ class DWConvFn(Function):
         return dx, dwt.t().reshape(w.shape).contiguous(), db, None, None
 
 
+@ops.captures_precision
 class GeluFn(Function):
     @staticmethod
     def forward(ctx, h):
@@ -170,6 +174,7 @@ class GeluFn(Function):
         return dh.view(h.shape)
 
 
+@ops.captures_precision
 class LSKSelectFn(Function):
     """attn1*sig0 + attn2*sig1 with sig = sigmoid(conv_squeeze([mean_c, max_c] of cat(attn1, attn2)))."""
 
@@ -201,6 +206,7 @@ class LSKSelectFn(Function):
         return da1.view(a1.shape), da2.view(a2.shape), dw, db
 
 
+@ops.captures_precision
 class MulFn(Function):
     @staticmethod
     def forward(ctx, a, b):
@@ -217,6 +223,7 @@ class MulFn(Function):
         return da, db
 
 
+@ops.captures_precision
 class DropoutFn(Function):
     """nn.Dropout with a counter-based mask: forward and backward are the same kernel with the same seed."""
 
@@ -230,6 +237,7 @@ class DropoutFn(Function):
         return ops.dropout(d.contiguous(), ctx.p, ctx.seed), None, None
 
 
+@ops.captures_precision
 class AxpyFn(Function):
     """out = a[c] * y * row_scale[t] + x   (a = layer scale or None, row_scale = drop-path mask or None)."""
 
@@ -254,6 +262,7 @@ class AxpyFn(Function):
         return dy, d, da, None
 
 
+@ops.captures_precision
 class PatchEmbedFn(Function):
     """Conv2d(ks, stride, padding=ks//2) as im2col + tcgen05 GEMM.  x: NCHW (network input) or NHWC; out NHWC."""
 
@@ -296,6 +305,7 @@ class PatchEmbedFn(Function):
         return dx, dw, db, None, None
 
 
+@ops.captures_precision
 class MoELinearFn(Function):
     """LSKNet MoE layer: router -> plan -> grouped expert GEMM (single Conv2d(in,out,1) per expert, dispatch gather
     fused into the A-operand load) -> deterministic combine (x gamma + resid when given)."""
@@ -325,7 +335,7 @@ class MoELinearFn(Function):
             record.append(dict(x=x2, top_idx=r['top_idx'], top_gate=r['top_gate'], importance=plan['importance'],
                                load=plan['load'], loss=plan['loss'], y=y, counts=plan['counts']))
         if train:
-            ctx.noisy = noise is not None and k < E
+            ctx.noisy = noise is not None     # gates depend on w_noise whenever noise was added, also for k == E
             ctx.save_for_backward(x2, o, wp, sim, tau, gamma, row_scale, r['top_idx'], r['top_gate'], r['logits'], r['p'],
                                   slot_of, pair_token, plan['importance'], plan['seg_begin'], plan['seg_end'],
                                   plan['tile_group'], plan['num_m_tiles'], w0, noise, r['sigma'], r['top_vals'],

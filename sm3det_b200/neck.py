@@ -30,6 +30,7 @@ class ConvModule(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding)
 
 
+@ops.captures_precision
 class UpsampleAddFn(Function):
     @staticmethod
     def forward(ctx, a, b):
@@ -42,6 +43,7 @@ class UpsampleAddFn(Function):
         return d, ops.upsample_add_bwd(d, *ctx.hw)
 
 
+@ops.captures_precision
 class ToNCHWFn(Function):
     @staticmethod
     def forward(ctx, x):
@@ -112,6 +114,10 @@ class MultitaskFPN(BaseModule):
                 raise NotImplementedError(f'sm3det_b200 MultitaskFPN: channel count {c} unsupported (multiple of 32)')
 
     def forward(self, inputs, start_level=None, add_extra_convs=None):
+        with ops.precision_scope(ops.autocast_passes(self)):      # per-call GEMM precision (bf16 under autocast)
+            return self._forward(inputs, start_level, add_extra_convs)
+
+    def _forward(self, inputs, start_level=None, add_extra_convs=None):
         if start_level is None:
             start_level = self.start_level
         if add_extra_convs is None:

@@ -17,16 +17,54 @@ LN_NHWC, LN_PATCH2, LN_NCHW = 0, 1, 2
 
 
 # GEMM operand precision: 3 = split-bf16 hi*hi + hi*lo + lo*hi (fp32-accurate; what every parity test and bench.py use),
-# 1 = hi*hi only (plain bf16 operands, fp32 accumulate) -- the mixed-precision recipe; set through set_gemm_precision().
-MMA_PASSES = 3
+# 1 = hi*hi only (plain bf16 operands, fp32 accumulate) -- the mixed-precision recipe.  The precision is a per-call
+# property carried by a thread-local scope: a backbone forward opens `precision_scope(passes)` around its kernels, every
+# autograd Function decorated with `@captures_precision` remembers the scope it was RECORDED under and re-opens it for
+# its backward -- so an interleaved forward of another model (EMA / teacher / validation hook) can no longer change the
+# precision of a pending backward, and two Python threads do not see each other's mode.
+import contextlib
+import threading
+
+_tls = threading.local()
 
 
-def set_gemm_precision(mode: str):
-    """'fp32' (default, 3-pass split-bf16) or 'bf16' (single pass; ~3x the tensor-core rate, ~3 significant digits)."""
-    global MMA_PASSES
-    if mode not in ('fp32', 'bf16'):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
-    MMA_PASSES = 3 if mode == 'fp32' else 1
+def current_passes() -> int:
+    return getattr(_tls, 'passes', 3)
+
+
+@contextlib.contextmanager
+def precision_scope(passes: int):
+    if passes not in (1, 3):
+        raise ValueError('mma passes must be 3 (fp32-accurate split-bf16) or 1 (bf16 operands)')
+    prev = current_passes()
+    _tls.passes = passes
+    try:
+        yield
+    finally:
+        _tls.passes = prev
+
+
+def autocast_passes(module=None) -> int:
+    """1 under torch.autocast (or when `module.amp` is set), else 3."""
+    import torch as _t
+    return 1 if (getattr(module, 'amp', False) or _t.is_autocast_enabled()) else 3
+
+
+def captures_precision(cls):
+    """Class decorator for torch.autograd.Function subclasses: backward runs at the GEMM precision of its own forward."""
+    fwd, bwd = cls.forward, cls.backward
+
+    def forward(ctx, *args, **kwargs):
+        ctx._mma_passes = current_passes()
+        return fwd(ctx, *args, **kwargs)
+
+    def backward(ctx, *grads):
+        with precision_scope(ctx._mma_passes):
+            return bwd(ctx, *grads)
+
+    cls.forward = staticmethod(forward)
+    cls.backward = staticmethod(backward)
+    return cls
 
 
 def _stream():
@@ -83,7 +121,7 @@ def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a
     a.col_scale = _p(col_scale); a.row_scale = _p(row_scale)
     a.resid = _p(resid); a.ld_resid = ld_resid
     a.colsum = _p(colsum); a.colsum_group_stride = colsum_group_stride
-    a.mma_passes = MMA_PASSES
+    a.mma_passes = current_passes()
     _lib.check(lib.sm3_gemm(C.byref(a), _stream()), 'sm3_gemm')
     return D
 

@@ -58,7 +58,7 @@ def test_state_dict_layout_matches_reference(kw, multi):
     if ref_shim.reference_available() and kw['arch'] == 'tiny':
         ref = ref_shim.build_reference_backbone(name, **kw)      # the reference cannot be built on 'meta'
         assert mine == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
-        assert [n for n, _ in net.named_parameters()].sort() == [n for n, _ in ref.named_parameters()].sort()
+        assert sorted(n for n, _ in net.named_parameters()) == sorted(n for n, _ in ref.named_parameters())
 
 
 def test_registry_builds_literal_sm3det_config_dicts():

@@ -25,6 +25,8 @@ def _inputs(gold):
 @pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'lsk_*.pt')) + glob.glob(os.path.join(GOLD, 'van_*.pt'))), ids=lambda p: os.path.basename(p)[:-3])
 def test_oracle_reproduces_reference_golden(path):
     gold = torch.load(path, weights_only=False)
+    if gold['mode'] != 'eval' and gold['img'][1] >= 512 and not os.environ.get('SM3_SLOW_TESTS'):
+        pytest.skip('full-size training fixture: re-checked by oracle/gen_golden.py (set SM3_SLOW_TESTS=1 to run here)')
     cfg, sd, x = _inputs(gold)
     assert abs(float(x.double().abs().sum()) - gold['x_checksum']) < 1e-6 * gold['x_checksum']
     noise, drops = lsk_injections(cfg, gold)
@@ -32,12 +34,13 @@ def test_oracle_reproduces_reference_golden(path):
     with torch.no_grad():
         res = lsk_backbone_forward(sd, cfg, x, train=gold['mode'] != 'eval', noise=noise, drop_masks=drops, record=rec, bn_state=bn)
     outs, loss = res if 'gate_loss' in gold else (res, None)
+    st = gold.get('stride', 1)
     for o, g in zip(outs, gold['outs']):
-        assert torch.equal(o, g)
+        assert torch.equal(o[:, :, ::st, ::st], g)
     if loss is not None:
         assert torch.equal(loss, gold['gate_loss'])
     for r, g in zip(rec, gold['moe']):
-        assert torch.equal(r['top_idx'].to(torch.int16), g['top_idx'])
+        assert torch.equal(r['top_idx'].to(g['top_idx'].dtype), g['top_idx'])
     for k, v in gold.get('bn', {}).items():
         assert torch.equal(bn[k], v), k
 
@@ -98,6 +101,41 @@ def test_lsk_upcycle_dense_checkpoint():
     for e in range(3):
         assert torch.equal(moe.block2[0].mlp.fc1.experts[e].weight, dense.block2[0].mlp.fc1.weight)
         assert torch.equal(moe.block1[0].mlp.fc2.experts[e].bias, dense.block1[0].mlp.fc2.bias)
+
+
+def test_lsk_multi_input_upcycle_moves_the_stem():
+    """lsk_moe.py:806-813: a dense LSKNet checkpoint's 'patch_embed1.proj.*' must land in 'dataset_stems.single.*' and
+    'patch_embed1.norm.*' in 'patch_embed1.*' (round-1 advisor finding: they were silently dropped)."""
+    from sm3det_b200 import LSKNet_moe, LSKNet_moe_MultiInput
+    kw = dict(embed_dims=[64, 128], depths=[1, 1], num_stages=2, mlp_ratios=[4, 4])
+    dense = LSKNet_moe(**kw)
+    with torch.no_grad():
+        dense.patch_embed1.norm.running_mean.normal_()
+    moe = LSKNet_moe_MultiInput(num_experts=3, top_k=2, MoE_Block_inds_fc1=[[], [0]], MoE_Block_inds_fc2=[[0], []], **kw)
+    res = moe.load_state_dict(moe.upcycle_state_dict(dense.state_dict()), strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all('w_gate' in k or 'w_noise' in k or k.endswith(('.mean', '.std')) for k in res.missing_keys), res.missing_keys
+    assert torch.equal(moe.dataset_stems['single'].weight, dense.patch_embed1.proj.weight)
+    assert torch.equal(moe.dataset_stems['single'].bias, dense.patch_embed1.proj.bias)
+    assert torch.equal(moe.patch_embed1.weight, dense.patch_embed1.norm.weight)
+    assert torch.equal(moe.patch_embed1.running_mean, dense.patch_embed1.norm.running_mean)
+    for e in range(3):
+        assert torch.equal(moe.block2[0].mlp.fc1.experts[e].weight, dense.block2[0].mlp.fc1.weight)
+
+
+def test_lsk_init_weights_from_scratch():
+    """init_cfg=None branch of init_weights (lsk_moe.py:476-490): Conv2d ~ N(0, 2/fan_out), biases 0, LayerNorm (1, 0)."""
+    from sm3det_b200 import LSKNet_moe_MultiInput
+    net = LSKNet_moe_MultiInput(embed_dims=[64, 128], depths=[1, 1], num_stages=2, mlp_ratios=[4, 4], init_cfg=None)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.fill_(3.0)
+    net.init_weights()
+    conv = net.patch_embed2.proj
+    fan_out = conv.kernel_size[0] * conv.kernel_size[1] * conv.out_channels // conv.groups
+    assert abs(conv.weight.std().item() - (2.0 / fan_out) ** 0.5) < 0.2 * (2.0 / fan_out) ** 0.5
+    assert float(conv.bias.abs().max()) == 0.0
+    assert torch.equal(net.norm1.weight, torch.ones_like(net.norm1.weight)) and float(net.norm1.bias.abs().max()) == 0.0
 
 
 def test_van_contract():

@@ -35,6 +35,8 @@ def _run_oracle(gold, record):
 @pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, '*.pt')) if not os.path.basename(p).startswith(('lsk_', 'van_'))), ids=lambda p: os.path.basename(p)[:-3])
 def test_oracle_matches_reference_golden(path):
     gold = torch.load(path, weights_only=False)
+    if gold['mode'] != 'eval' and gold['img'][1] >= 512 and not os.environ.get('SM3_SLOW_TESTS'):
+        pytest.skip('full-size training fixture: re-checked by oracle/gen_golden.py (set SM3_SLOW_TESTS=1 to run here)')
     record = []
     cfg, sd, res = _run_oracle(gold, record)
     has_loss = 'gate_loss' in gold
@@ -49,8 +51,9 @@ def test_oracle_matches_reference_golden(path):
     assert len(record) == len(gold['moe'])
     for r, g in zip(record, gold['moe']):
         assert r['prefix'] == g['prefix']
-        assert torch.equal(r['top_idx'].to(torch.int16), g['top_idx']), 'router top-k indices must be bit-exact'
-        torch.testing.assert_close(r['top_gates'], g['top_gates'], rtol=1e-6, atol=1e-7)
+        assert torch.equal(r['top_idx'].to(g['top_idx'].dtype), g['top_idx']), 'router top-k indices must be bit-exact'
+        if 'top_gates' in g:
+            torch.testing.assert_close(r['top_gates'], g['top_gates'], rtol=1e-6, atol=1e-7)
         torch.testing.assert_close(r['load'], g['load'], rtol=1e-6, atol=1e-6)
     if 'grads' in gold:
         ups = upstream_grads(outs)
