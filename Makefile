@@ -5,7 +5,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall
 SRC := sm3det_b200/csrc
 OBJ := build/obj
 LIB := sm3det_b200/lib/libsm3det_b200.so
-SRCS := common.cu gemm_tc.cu norm.cu stencil.cu moe.cu reduce.cu act.cu lsk.cu neck.cu capi.cu
+SRCS := common.cu gemm_tc.cu ffn_fused.cu norm.cu stencil.cu moe.cu reduce.cu act.cu lsk.cu neck.cu capi.cu
 OBJS := $(SRCS:%.cu=$(OBJ)/%.o)
 
 all: $(LIB)
@@ -21,6 +21,10 @@ $(LIB): $(OBJS)
 build/gemm_test: tests/cuda/gemm_test.cu $(SRC)/gemm_tc.cu $(SRC)/common.cu $(SRC)/gemm_tc.cuh
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -I $(SRC) tests/cuda/gemm_test.cu $(SRC)/gemm_tc.cu $(SRC)/common.cu -o $@
+
+build/ffn_test: tests/cuda/ffn_test.cu $(SRC)/ffn_fused.cu $(SRC)/gemm_tc.cu $(SRC)/common.cu $(SRC)/gemm_tc.cuh $(SRC)/ffn_fused.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -I $(SRC) tests/cuda/ffn_test.cu $(SRC)/ffn_fused.cu $(SRC)/gemm_tc.cu $(SRC)/common.cu -o $@
 
 clean:
 	rm -rf build sm3det_b200/lib/*.so

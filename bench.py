@@ -239,7 +239,7 @@ def time_gpu_eager(args, micro):
 
 
 # ------------------------------------------------------------------------------------------------
-TENSOR_OPS = ('gemm', 'ffn_fused_fwd', 'ffn_fused_bwd')     # ops.* entry points that launch tcgen05 kernels
+TENSOR_OPS = ('gemm', 'ffn_fused_fwd', 'ffn_fused_bwd_all')     # ops.* entry points that launch tcgen05 kernels
 
 
 def gemm_roofline(step_fn, peaks):

@@ -18,6 +18,7 @@
 #ifndef SM3DET_B200_H_
 #define SM3DET_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -99,6 +100,42 @@ int64_t sm3_gemm_packed_act_elems(int64_t rows, int32_t cols, int32_t mn_major, 
 int sm3_gemm_pack_act(const float* X, int64_t ld, const int32_t* row_index, int64_t rows, int32_t cols,
                       int32_t mn_major, int32_t tile, uint16_t* out, void* stream);
 int32_t sm3_gemm_tile_n(int32_t N);   /* tile width the GEMM uses for an N-column output (0 if unsupported) */
+/* Same image with an explicit tile width (N % tile == 0): the fused FFN kernels stream weight chunks of their own width. */
+int sm3_gemm_pack_b_tile(const float* B, int64_t stride_mn, int64_t stride_k, int64_t group_stride, int32_t groups,
+                         int32_t N, int32_t K, int32_t tile, uint16_t* out, void* stream);
+/* Workspace contract: every op works on caller-owned buffers only.  sm3_gemm itself needs no scratch memory
+ * (operand images are explicit arguments sized by sm3_gemm_packed_elems / sm3_gemm_packed_act_elems), so this returns 0;
+ * it exists so that callers can size allocations uniformly through the C ABI. */
+size_t sm3_gemm_workspace_bytes(const sm3_gemm_args* args);
+
+/* ---- fused dense FFN for the narrow stages (C <= 192 forward, C <= 128 backward into dv, C <= 96 weight gradients) ------
+ * The [M, 4C] hidden tensor never leaves the SM (GEMM1 -> +b1 -> GELU -> bf16 hi/lo split -> shared memory -> GEMM2 with
+ * the accumulators in TMEM); the backward RECOMPUTES the hidden pre-activation instead of loading a saved copy.
+ * Replaces FFN.forward (convnext_moe.py:397-405) + layer scale / drop-path / shortcut (:367-370) and autograd's backward
+ * of them for dense ConvNeXt blocks.
+ *   mode 0 (forward)     out = resid + row_scale * col_scale * (gelu(A1 Wa1^T + b1) Wb^T + bias2);  aux_out = pre-scale value
+ *                        A1 = v, Wa1 = W1 [4C,C], Wb = W2 [C,4C]
+ *   mode 1 (backward dv) out = ((A2 Wa2^T) * gelu'(A1 Wa1^T + b1)) Wb^T
+ *                        A1 = v, A2 = dz, Wa1 = W1, Wa2 = (gamma W2)^T stored [4C,C], Wb = W1^T stored [C,4C]
+ *   mode 2 (weight grads) dw1 += dh^T v, dw2 += gamma * dz^T gelu(h), db1 += sum dh   (h, dh recomputed as in mode 1)
+ * a1 / a2: K-major images from sm3_gemm_pack_act(tile 128); wa1 / wa2: sm3_gemm_pack_b_tile(tile = chunk) of the [4C,C]
+ * matrices; wb: sm3_gemm_pack_b_tile(tile = C) of the [C,4C] matrix; chunk = sm3_ffn_fused_chunk(mode, C). */
+typedef struct sm3_ffn_args {
+  const uint16_t* a1; const uint16_t* a2;
+  const uint16_t* wa1; const uint16_t* wa2; const uint16_t* wb;
+  const float* bias1;              /* [4C] */
+  const float* bias2;              /* [C]  mode 0 */
+  const float* col_scale;          /* [C]  mode 0: gamma (optional); mode 2: gamma (required) */
+  const float* row_scale;          /* [M]  mode 0: drop-path scale (optional) */
+  const float* resid;              /* [M,C] mode 0: shortcut (optional) */
+  float* out;                      /* [M,C] modes 0, 1 */
+  float* aux_out;                  /* [M,C] mode 0, optional */
+  float* dw1; float* dw2; float* db1;   /* mode 2: [4C,C], [C,4C], [4C]; accumulated, pre-zeroed by the caller */
+  int32_t M, C, H4, chunk, mma_passes, mode;
+} sm3_ffn_args;
+int32_t sm3_ffn_fused_chunk(int32_t mode, int32_t C);   /* hidden chunk width for (mode, C); 0 = shape not supported */
+int sm3_ffn_fused(const sm3_ffn_args* args, void* stream);
+size_t sm3_ffn_fused_workspace_bytes(const sm3_ffn_args* args);   /* 0: accumulators live in TMEM, operands in smem */
 
 /* ---- LayerNorm over channels (F.layer_norm, eps inside rsqrt, biased variance) ---------------
  * Replaces LayerNorm2d.forward (convnext_moe.py:34-47) at :351 (block norm), :549-551 (downsample
@@ -153,6 +190,7 @@ typedef struct sm3_router_args {
 } sm3_router_args;
 int sm3_moe_router_blocks(int32_t T);
 int sm3_moe_router(const sm3_router_args* args, void* stream);
+size_t sm3_moe_router_workspace_bytes(const sm3_router_args* args);   /* bytes of `partials` for args->T, args->E */
 
 typedef struct sm3_plan_args {
   const float* partials; int32_t T, E, k, max_m_tiles;
@@ -161,6 +199,7 @@ typedef struct sm3_plan_args {
   int32_t* tile_group; int32_t* num_m_tiles;
 } sm3_plan_args;
 int sm3_moe_plan(const sm3_plan_args* args, void* stream);
+size_t sm3_moe_plan_workspace_bytes(const sm3_plan_args* args);       /* bytes of all plan outputs laid out back to back */
 int sm3_moe_assign(const int32_t* top_idx, int32_t T, int32_t k, int32_t E, const int32_t* seg_begin,
                    int32_t* cursor, int32_t* slot_of, int32_t* pair_token, void* stream);
 int sm3_moe_combine(const float* expert_out, const int32_t* slot_of, const int32_t* top_idx, const float* gate,

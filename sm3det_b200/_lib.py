@@ -57,6 +57,16 @@ class PlanArgs(C.Structure):
     ]
 
 
+class FfnArgs(C.Structure):
+    _fields_ = [
+        ('a1', C.c_void_p), ('a2', C.c_void_p), ('wa1', C.c_void_p), ('wa2', C.c_void_p), ('wb', C.c_void_p),
+        ('bias1', c_f32p), ('bias2', c_f32p), ('col_scale', c_f32p), ('row_scale', c_f32p), ('resid', c_f32p),
+        ('out', c_f32p), ('aux_out', c_f32p), ('dw1', c_f32p), ('dw2', c_f32p), ('db1', c_f32p),
+        ('M', C.c_int32), ('C', C.c_int32), ('H4', C.c_int32), ('chunk', C.c_int32), ('mma_passes', C.c_int32),
+        ('mode', C.c_int32),
+    ]
+
+
 # name -> argtypes (restype is always int unless listed in _RESTYPES); mirrors include/sm3det_b200.h
 _I32, _I64, _F32, _P = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 SIGNATURES = {
@@ -69,6 +79,13 @@ SIGNATURES = {
     'sm3_gemm_packed_act_elems': [_I64, _I32, _I32, _I32],
     'sm3_gemm_pack_act': [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P],
     'sm3_gemm_tile_n': [_I32],
+    'sm3_gemm_pack_b_tile': [_P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _P, _P],
+    'sm3_gemm_workspace_bytes': [C.POINTER(GemmArgs)],
+    'sm3_ffn_fused_chunk': [_I32, _I32],
+    'sm3_ffn_fused': [C.POINTER(FfnArgs), _P],
+    'sm3_ffn_fused_workspace_bytes': [C.POINTER(FfnArgs)],
+    'sm3_moe_router_workspace_bytes': [C.POINTER(RouterArgs)],
+    'sm3_moe_plan_workspace_bytes': [C.POINTER(PlanArgs)],
     'sm3_layernorm_fwd': [_P, _P, _P, _P, _P, _I64, _I32, _F32, _I32, _I32, _I32, _P],
     'sm3_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P],
     'sm3_stem_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _P],
@@ -106,7 +123,9 @@ SIGNATURES = {
     'sm3_im2col': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     'sm3_col2im': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
-_RESTYPES = {'sm3_last_error': C.c_char_p, 'sm3_gemm_packed_elems': C.c_int64, 'sm3_gemm_packed_act_elems': C.c_int64}
+_RESTYPES = {'sm3_last_error': C.c_char_p, 'sm3_gemm_packed_elems': C.c_int64, 'sm3_gemm_packed_act_elems': C.c_int64,
+             'sm3_gemm_workspace_bytes': C.c_size_t, 'sm3_ffn_fused_workspace_bytes': C.c_size_t,
+             'sm3_moe_router_workspace_bytes': C.c_size_t, 'sm3_moe_plan_workspace_bytes': C.c_size_t}
 
 
 class ActPackArgs(C.Structure):

@@ -117,15 +117,16 @@ class PackCache:
     def invalidate(self):
         self._d.clear()
 
-    def get(self, name, params, transposed):
+    def get(self, name, params, transposed, tile=0):
         from . import ops
         key = tuple(p._version for p in params) + (params[0].data_ptr(), str(params[0].device))
+        name = (name, tile)
         hit = self._d.get((name, transposed))
         if hit is not None and hit[0] == key:
             return hit[1]
         reuse = None if hit is None or hit[1][0].device != params[0].device else hit[1][0]   # never write into a buffer
         with torch.no_grad():                                                                # left behind on another GPU
-            packed = ops.pack_weight(params[0], transposed=transposed, groups=len(params), out=reuse)
+            packed = ops.pack_weight(params[0], transposed=transposed, groups=len(params), out=reuse, tile=tile)
         self._d[(name, transposed)] = (key, packed)
         return packed
 
@@ -177,12 +178,24 @@ class ConvNeXtBlock(nn.Module):
         dw = self.depthwise_conv
         grad = torch.is_grad_enabled()
         pc = self._packs
+        from . import ops
         if self.MoE_cfg is None:
             f = self.ffn
             w1, w2 = f.pointwise_conv1.weight, f.pointwise_conv2.weight
-            packs = {'w1': pc.get('w1', [w1], False), 'w2': pc.get('w2', [w2], False)}
-            if grad:
-                packs['w1_t'] = pc.get('w1', [w1], True)
+            C = w2.shape[0]
+            cf, cb, cw = ops.ffn_chunk(0, C), ops.ffn_chunk(1, C), ops.ffn_chunk(2, C)
+            train_ok = cb > 0 and cb == cw
+            if cf > 0 and (train_ok or not grad):
+                # fused FFN kernels: weight images in the chunk widths they stream (csrc/ffn_fused.cu)
+                packs = {'fused': dict(fwd=cf, bwd=cb, train=train_ok),
+                         'w1_c': pc.get('w1', [w1], False, tile=cf), 'w2_n': pc.get('w2', [w2], False, tile=C)}
+                if grad:
+                    packs['w1_cb'] = pc.get('w1', [w1], False, tile=cb)
+                    packs['w1_tn'] = pc.get('w1', [w1], True, tile=C)
+            else:
+                packs = {'w1': pc.get('w1', [w1], False), 'w2': pc.get('w2', [w2], False)}
+                if grad:
+                    packs['w1_t'] = pc.get('w1', [w1], True)
             out = Fn.DenseBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias,
                                         w1, f.pointwise_conv1.bias, w2, f.pointwise_conv2.bias, self.gamma, rs, eps, packs)
             return out, None

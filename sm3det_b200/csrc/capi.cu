@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.h"
+#include "ffn_fused.cuh"
 
 using namespace sm3;
 
@@ -56,6 +57,30 @@ int sm3_gemm_pack_act(const float* X, int64_t ld, const int32_t* row_index, int6
   return gemm::pack_act(X, ld, row_index, rows, cols, mn_major, tile, out, S(stream));
 }
 int32_t sm3_gemm_tile_n(int32_t N) { return gemm::pick_bn(N); }
+int sm3_gemm_pack_b_tile(const float* B, int64_t s_mn, int64_t s_k, int64_t group_stride, int32_t groups, int32_t N, int32_t K,
+                         int32_t tile, uint16_t* out, void* stream) {
+  return gemm::pack_b(B, s_mn, s_k, group_stride, groups, N, K, out, S(stream), tile);
+}
+size_t sm3_gemm_workspace_bytes(const sm3_gemm_args*) { return 0; }
+
+int32_t sm3_ffn_fused_chunk(int32_t mode, int32_t C) { return mode == 2 ? ffn::wgrad_chunk(C) : ffn::chain_chunk(mode, C); }
+size_t sm3_ffn_fused_workspace_bytes(const sm3_ffn_args*) { return 0; }
+int sm3_ffn_fused(const sm3_ffn_args* a, void* stream) {
+  if (!a) { set_last_error("sm3_ffn_fused: null args"); return SM3_ERR_INVALID_ARG; }
+  if (a->mode == 2) {
+    ffn::WgradParams p{};
+    p.a1 = a->a1; p.a2 = a->a2; p.wa1 = a->wa1; p.wa2 = a->wa2; p.bias1 = a->bias1; p.gamma = a->col_scale;
+    p.dw1 = a->dw1; p.dw2 = a->dw2; p.db1 = a->db1;
+    p.M = a->M; p.C = a->C; p.H4 = a->H4; p.HC = a->chunk; p.passes = a->mma_passes;
+    return ffn::wgrad(p, S(stream));
+  }
+  ffn::ChainParams p{};
+  p.a1 = a->a1; p.a2 = a->a2; p.wa1 = a->wa1; p.wa2 = a->wa2; p.wb = a->wb;
+  p.bias1 = a->bias1; p.bias2 = a->bias2; p.col_scale = a->col_scale; p.row_scale = a->row_scale; p.resid = a->resid;
+  p.out = a->out; p.aux_out = a->aux_out;
+  p.M = a->M; p.C = a->C; p.H4 = a->H4; p.HC = a->chunk; p.passes = a->mma_passes; p.mode = a->mode;
+  return ffn::chain(p, S(stream));
+}
 
 int sm3_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int64_t T, int32_t C,
                       float eps, int32_t out_mode, int32_t H, int32_t W, void* stream) {
@@ -94,6 +119,13 @@ int sm3_moe_router(const sm3_router_args* a, void* stream) {
   r.top_idx = a->top_idx; r.top_gate = a->top_gate; r.logits = a->logits; r.top_vals = a->top_vals; r.p_out = a->p_out; r.sigma = a->sigma; r.top_idx_m = a->top_idx_m;
   r.partials = a->partials; r.nblocks = router_blocks(a->T);
   return moe_router(r, S(stream));
+}
+size_t sm3_moe_router_workspace_bytes(const sm3_router_args* a) {
+  return a ? (size_t)router_blocks(a->T) * 3u * (size_t)a->E * sizeof(float) : 0;
+}
+size_t sm3_moe_plan_workspace_bytes(const sm3_plan_args* a) {
+  // importance[E] load[E] loss[1] floats + counts / seg_begin / seg_end / cursor [E] each + tile_group[max_m_tiles] + num_m_tiles[1] ints
+  return a ? (size_t)(2 * a->E + 1) * sizeof(float) + (size_t)(4 * a->E + a->max_m_tiles + 1) * sizeof(int32_t) : 0;
 }
 int sm3_moe_plan(const sm3_plan_args* a, void* stream) {
   if (!a) { set_last_error("sm3_moe_plan: null args"); return SM3_ERR_INVALID_ARG; }

@@ -58,10 +58,10 @@ __global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ B
 }
 
 int pack_b(const float* B, long long s_mn, long long s_k, long long group_stride, int groups, int N, int K,
-           uint16_t* out, cudaStream_t stream) {
+           uint16_t* out, cudaStream_t stream, int tile) {
   SM3_REQUIRE(B && out && N > 0 && K > 0 && groups >= 1, SM3_ERR_INVALID_ARG, "gemm pack: bad argument");
-  const int BN = pick_bn(N);
-  SM3_REQUIRE(BN > 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm pack: N=%d has no tile width", N);
+  const int BN = tile > 0 ? tile : pick_bn(N);
+  SM3_REQUIRE(BN > 0 && BN % 8 == 0 && BN <= 256 && N % BN == 0, SM3_ERR_UNSUPPORTED_SHAPE, "gemm pack: N=%d has no tile width (tile=%d)", N, tile);
   SM3_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, SM3_ERR_INVALID_ARG, "gemm pack: output must be 16B aligned");
   const long long kblocks = (K + BK - 1) / BK;
   const long long chunks = (long long)N * kblocks * 4;

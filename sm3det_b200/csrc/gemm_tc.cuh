@@ -736,8 +736,9 @@ __global__ void __maxnreg__(168) gemm_bf16x3_kernel(const __grid_constant__ Para
 // the tile-ordered bf16 image the kernel bulk-copies: [group][n_tile][k_block]{ hi[BN x 32] | lo[BN x 32] } with
 // each plane in the K-major SWIZZLE_64B canonical layout.  packed_elems(N, K) bf16 elements per group.
 long long packed_elems(int N, int K);
+// `tile` > 0 overrides the tile width (the fused FFN kernels stream weight chunks of their own width).
 int pack_b(const float* B, long long s_mn, long long s_k, long long group_stride, int groups, int N, int K,
-           uint16_t* out, cudaStream_t stream);
+           uint16_t* out, cudaStream_t stream, int tile = 0);
 // Pre-split an ACTIVATION operand.  mn_major = 0: X[rows, K] row-major (optional row gather, -1 = zero row) ->
 // K-major tiles of `tile` rows (128 for the A operand).  mn_major = 1: X[R, W] row-major where the ROW index is the
 // reduction index (wgrad operands; optional row gather) -> MN-major tiles of `tile` columns (128 for A, BN for B).

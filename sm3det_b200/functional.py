@@ -158,12 +158,28 @@ def _block_front_bwd(dv, dout, x, u, stats, dww, lnw):
 
 @ops.captures_precision
 class DenseBlockFn(Function):
+    """Dense ConvNeXt block.  Narrow stages (ops.ffn_chunk: C <= 96 for training, <= 192 for inference) run the FFN as the
+    fused tcgen05 kernels of csrc/ffn_fused.cu -- the [T,4C] hidden tensor is never written to HBM and the backward
+    recomputes it; wider stages keep the GEMM -> act_pack -> GEMM sequence."""
+
     @staticmethod
     def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps, packs):
         N, H, W, C = x.shape
         T = N * H * W
         train = any(ctx.needs_input_grad)
         u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
+        fused = packs.get('fused')
+        if fused is not None and (not train or fused['train']):
+            v_img = ops.pack_act(v, rows=T, cols=C, mn_major=False)
+            del v
+            out, y2 = ops.ffn_fused_fwd(v_img, packs['w1_c'][0], packs['w2_n'][0], b1, b2, T=T, C=C, chunk=fused['fwd'],
+                                        gamma=gamma, row_scale=row_scale, resid=x.view(T, C), want_aux=train)
+            if train:
+                ctx.fused = fused
+                ctx.save_for_backward(x, u, stats, v_img, y2, dww, lnw, w1, b1, w2, gamma, row_scale)
+                ctx.packs = packs
+            return out.view(N, H, W, C)
+        ctx.fused = None
         # GEMM1 stores the pre-activation only; GELU runs in the HBM-bound act_pack kernel, which emits the result
         # directly as GEMM2's pre-split A operand (fp32 `a` never exists)
         h = ops.linear_fwd(v, w1, b1, packed=packs.get('w1'))
@@ -179,6 +195,8 @@ class DenseBlockFn(Function):
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.fused is not None:
+            return DenseBlockFn._backward_fused(ctx, dout)
         x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, rs = ctx.saved_tensors
         N, H, W, C = x.shape
         T = N * H * W
@@ -209,6 +227,37 @@ class DenseBlockFn(Function):
         dw1 = torch.zeros_like(w1)
         ops.linear_wgrad(None, v, dw1, rows=T, dy_packed=dh_mn)
         dv = ops.linear_dgrad(None, w1, rows=T, a_packed=dh_k, packed=ctx.packs.get('w1_t'))
+        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
+        return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
+
+    @staticmethod
+    def _backward_fused(ctx, dout):
+        """Appendix F steps 1-3 with nothing hidden-sized in HBM: dz' = drop-path-scaled dout is split once into its
+        operand image; one fused kernel gives dv (dgrad2 -> gelu' -> dgrad1), a second one dW1, dW2, db1."""
+        x, u, stats, v_img, y2, dww, lnw, w1, b1, w2, gamma, rs = ctx.saved_tensors
+        N, H, W, C = x.shape
+        T = N * H * W
+        dout = dout.contiguous()
+        dz = dout.view(T, C)
+        dev = x.device
+        f = ctx.fused
+        if rs is None:
+            csum, dgamma = ops.colstat(dz, rows=T, Cc=C, y=y2)            # one pass: sum dz and sum dz * y2
+            dzs = dz
+        else:
+            dgamma = torch.zeros((C,), device=dev, dtype=torch.float32)
+            ops.colsum(dz, dgamma, rows=T, Cc=C, b=y2, row_scale=rs)
+            csum = torch.zeros((C,), device=dev, dtype=torch.float32)
+            ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
+            dzs = ops.scale_rows(dz, row_scale=rs)
+        db2 = csum * gamma
+        dz_img = ops.pack_act(dzs, rows=T, cols=C, mn_major=False)
+        w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
+        w2gt_img, _ = ops.pack_weight(w2g, transposed=True, tile=f['bwd'])
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
+        dv = ops.ffn_fused_bwd_all(v_img, dz_img, ctx.packs['w1_cb'][0], w2gt_img, ctx.packs['w1_tn'][0], b1, gamma, dw1, dw2, db1,
+                                   T=T, C=C, chunk=f['bwd'])
         dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
         return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
 

@@ -126,8 +126,9 @@ def gemm(*, A, a_smn, a_sk, B, b_smn, b_sk, M, N, K, D, ldd, b_group_stride=0, a
     return D
 
 
-def pack_weight(w, *, transposed: bool, groups: int = 1, out=None):
+def pack_weight(w, *, transposed: bool, groups: int = 1, out=None, tile: int = 0):
     """bf16 hi/lo tile image of a weight for the GEMM's B operand (sm3_gemm_pack_b) -> (buffer, elems_per_group).
+    tile > 0: explicit tile width (the fused FFN kernels stream weight chunks of their own width).
 
     w: [N,K] (or the first of `groups` adjacent [N,K] expert weights).  transposed=False packs B(n,k) = w[n,k]
     (forward);  transposed=True packs B(n=k', k=n') = w[n',k'] (dgrad).  Callers cache the result per parameter
@@ -142,7 +143,11 @@ def pack_weight(w, *, transposed: bool, groups: int = 1, out=None):
     per = lib.sm3_gemm_packed_elems(N, K)
     if out is None or out.numel() != groups * per:
         out = torch.empty((groups * per,), device=w.device, dtype=torch.int16)
-    _lib.check(lib.sm3_gemm_pack_b(_p(w), s_mn, s_k, n_ * k_, groups, N, K, out.data_ptr(), _stream()), 'sm3_gemm_pack_b')
+    if tile:
+        _lib.check(lib.sm3_gemm_pack_b_tile(_p(w), s_mn, s_k, n_ * k_, groups, N, K, tile, out.data_ptr(), _stream()),
+                   'sm3_gemm_pack_b_tile')
+    else:
+        _lib.check(lib.sm3_gemm_pack_b(_p(w), s_mn, s_k, n_ * k_, groups, N, K, out.data_ptr(), _stream()), 'sm3_gemm_pack_b')
     return out, per
 
 
@@ -158,6 +163,75 @@ def pack_act(x, *, rows, cols, mn_major, tile=128, row_index=None, ld=None):
 
 
 ACT_GELU, ACT_DGELU, ACT_COPY, ACT_BWD = 0, 1, 2, 3
+
+
+# ---- fused dense FFN (narrow stages): the [T,4C] hidden tensor never leaves the SM --------------------------------------
+FFN_FWD, FFN_BWD_DX, FFN_WGRAD = 0, 1, 2
+
+
+def ffn_chunk(mode: int, C: int) -> int:
+    """hidden chunk width of sm3_ffn_fused for (mode, C); 0 = not supported (use the GEMM -> act_pack -> GEMM path)."""
+    import os
+    if os.environ.get('SM3_FUSED_FFN', '1') == '0':
+        return 0
+    return int(_lib.load().sm3_ffn_fused_chunk(mode, C))
+
+
+def _ffn_args(*, T, C, chunk, mode, a1, wa1, b1, a2=None, wa2=None, wb=None):
+    a = _lib.FfnArgs()
+    a.a1 = _p(a1, torch.int16); a.a2 = None if a2 is None else _p(a2, torch.int16)
+    a.wa1 = _p(wa1, torch.int16); a.wa2 = None if wa2 is None else _p(wa2, torch.int16)
+    a.wb = None if wb is None else _p(wb, torch.int16)
+    a.bias1 = _p(b1)
+    a.M, a.C, a.H4, a.chunk, a.mma_passes, a.mode = T, C, 4 * C, chunk, current_passes(), mode
+    return a
+
+
+def ffn_fused_fwd(v_img, w1_img, w2_img, b1, b2, *, T, C, chunk, gamma=None, row_scale=None, resid=None, want_aux=False):
+    """out[T,C] = resid + row_scale * gamma * (gelu(v W1^T + b1) W2^T + b2); aux = the value before gamma (y2)."""
+    lib = _lib.load()
+    out = torch.empty((T, C), device=b1.device, dtype=torch.float32)
+    aux = torch.empty((T, C), device=b1.device, dtype=torch.float32) if want_aux else None
+    a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_FWD, a1=v_img, wa1=w1_img, b1=b1, wb=w2_img)
+    a.bias2 = _p(b2); a.col_scale = _p(gamma); a.row_scale = _p(row_scale); a.resid = _p(resid)
+    a.out = _p(out); a.aux_out = _p(aux)
+    _lib.check(lib.sm3_ffn_fused(C.byref(a), _stream()), 'sm3_ffn_fused(fwd)')
+    return out, aux
+
+
+def ffn_fused_bwd(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, *, T, C, chunk):
+    """dv[T,C] = ((dz (gamma W2)) * gelu'(v W1^T + b1)) W1   (hidden pre-activation recomputed from v)."""
+    lib = _lib.load()
+    out = torch.empty((T, C), device=b1.device, dtype=torch.float32)
+    a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_BWD_DX, a1=v_img, a2=dz_img, wa1=w1_img, wa2=w2gt_img, b1=b1, wb=w1t_img)
+    a.out = _p(out)
+    _lib.check(lib.sm3_ffn_fused(C.byref(a), _stream()), 'sm3_ffn_fused(bwd)')
+    return out
+
+
+def ffn_fused_wgrad(v_img, dz_img, w1_img, w2gt_img, b1, gamma, dw1, dw2, db1, *, T, C, chunk):
+    """dw1 += dh^T v, dw2 += gamma * dz^T gelu(h), db1 += colsum(dh)  (accumulating; h, dh recomputed on chip)."""
+    lib = _lib.load()
+    a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_WGRAD, a1=v_img, a2=dz_img, wa1=w1_img, wa2=w2gt_img, b1=b1)
+    a.col_scale = _p(gamma); a.dw1 = _p(dw1); a.dw2 = _p(dw2); a.db1 = _p(db1)
+    _lib.check(lib.sm3_ffn_fused(C.byref(a), _stream()), 'sm3_ffn_fused(wgrad)')
+
+
+def ffn_fused_bwd_all(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, gamma, dw1, dw2, db1, *, T, C, chunk):
+    dv = ffn_fused_bwd(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, T=T, C=C, chunk=chunk)
+    ffn_fused_wgrad(v_img, dz_img, w1_img, w2gt_img, b1, gamma, dw1, dw2, db1, T=T, C=C, chunk=chunk)
+    return dv
+
+
+def fused_cost(name, *a, **kw):
+    """(algorithmic FLOPs, algorithmic HBM bytes, shape) of a fused-FFN call, for bench.py's roofline (recomputation of the
+    hidden pre-activation is NOT counted: FLOPs are those of the GEMMs the algorithm needs)."""
+    T, Cc = kw['T'], kw['C']
+    unit = 2.0 * T * Cc * 4 * Cc
+    wbytes = 2 * 4.0 * 4 * Cc * Cc
+    if name == 'ffn_fused_fwd':
+        return 2 * unit, (3 + (1 if kw.get('want_aux') else 0)) * 4.0 * T * Cc + wbytes, (T, Cc, 'fwd')
+    return 4 * unit, 3 * 4.0 * T * Cc + 2 * wbytes, (T, Cc, 'bwd')
 
 
 def act_pack(h, *, rows, width, mode, da=None, want_k=False, mn_tile=0, want_f32=False, colsum=None, live_tiles=None,

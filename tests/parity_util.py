@@ -7,12 +7,16 @@ outputs that differ from the CPU oracle's in the last bits, so on a token whose 
 tie the two sides may pick different experts -- and that token (plus everything a 7x7 depthwise conv spreads it to) then
 legitimately differs by O(1).  Round 1 skipped the numeric assertions whenever that happened.  Now:
 
-  1. every flip must be a near-tie: the ORACLE's own (k)-vs-(k+1) logit gap on that token (stored in the full-size
-     fixtures, recomputed live for the small ones) must be below ``GAP_TOL x max|logit|``, and flips must be rare;
-  2. the oracle is then re-run *teacher-forced* to the CUDA path's routing (``forced_idx``, a test-only hook), and outputs,
-     pre-gamma MoE outputs, importance / load / gate loss and every parameter gradient are compared on ALL elements --
-     no masking, no early exit;
-  3. when there is no flip, the CUDA path is additionally compared with the reference-generated fixture directly.
+  1. the oracle is run *teacher-forced* to the CUDA path's routing (``forced_idx``, a test-only hook): at every MoE layer it
+     still computes its OWN logits and top-k from inputs that already contain the CUDA path's upstream decisions, so a
+     difference at layer L is that layer's own numerics, not the echo of an upstream flip (with 36 MoE layers in a row --
+     config 4 -- one legitimate tie flip otherwise cascades into real routing changes downstream);
+  2. every such per-layer flip must be a near-tie: the oracle's (k)-vs-(k+1) logit gap on that token must be below
+     ``GAP_TOL x max|logit|``, and flips must be rare;
+  3. outputs, pre-gamma MoE outputs, importance / load / gate loss and every parameter gradient of the forced oracle are
+     compared with the CUDA path on ALL elements -- no masking, no early exit;
+  4. when the routing also equals the reference's own (the fixture's indices) everywhere, the CUDA path is additionally
+     compared with the reference-generated fixture values directly.
 The oracle itself is pinned bit-for-bit to the unmodified reference by oracle/gen_golden.py / tests/test_oracle.py.
 """
 import torch
@@ -95,19 +99,7 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
     has_loss = isinstance(res_g, tuple) and len(res_g) == 2 and isinstance(res_g[0], tuple)
     og, lg = res_g if has_loss else (res_g, None)
 
-    # (1) routing vs the reference's own decisions
-    flips = 0
-    if rec_g:
-        if gold is not None and 'gap' in gold['moe'][0]:
-            ref_layers = gold['moe']
-        else:
-            ref_rec = []
-            with torch.no_grad():
-                backbone_forward(sd, cfg, x, train=train, noise=noise, record=ref_rec)
-            ref_layers = ref_rec
-        flips = assert_flips_are_near_ties(rec_g, ref_layers, what=str(gold['name'] if gold else kw.get('arch')))
-
-    # (2) teacher-forced oracle: everything, everywhere
+    # (1) the oracle, teacher-forced to the CUDA path's routing
     forced = [r['top_idx'].cpu().long() for r in rec_g] or None
     rec_c, pre_c = [], []
     if backward:
@@ -117,7 +109,17 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
     with torch.set_grad_enabled(backward):
         res_c = backbone_forward(sdo, cfg, x, train=train, noise=noise, record=rec_c, pre_gamma=pre_c, forced_idx=forced)
     oc, lc = res_c if has_loss else (res_c, None)
-    errs = dict(flips=flips, fwd=[rel(a, b) for a, b in zip(og, oc)])
+    # (2) per layer: the CUDA choice vs the oracle's own top-k on the same (forced-upstream) inputs -- ties only
+    flips = 0
+    if rec_g:
+        own = [dict(top_idx=c['logits'].topk(g['top_idx'].shape[1], dim=-1).indices, logits=c['logits']) for g, c in zip(rec_g, rec_c)]
+        flips = assert_flips_are_near_ties(rec_g, own, what=str(gold['name'] if gold else kw.get('arch')))
+    # routing vs the reference's un-forced decisions (fixture): equal unless a tie flipped somewhere upstream
+    gold_flips = 0
+    if gold is not None and rec_g:
+        gold_flips = sum(int(flipped_tokens(g['top_idx'], c['top_idx']).sum()) for g, c in zip(rec_g, gold['moe']))
+        assert flips > 0 or gold_flips == 0, 'routing differs from the fixture although every layer agrees with the oracle'
+    errs = dict(flips=flips, gold_flips=gold_flips, fwd=[rel(a, b) for a, b in zip(og, oc)])
     assert max(errs['fwd']) < TOL, errs
     if has_loss:
         errs['loss'] = (lg.item(), lc.item())
@@ -129,8 +131,8 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
             if check_pre_gamma and g.get('y') is not None:
                 assert rel(g['y'], c['y']) < TOL            # pre-gamma MoE output (what layer scale would otherwise hide)
 
-    # (3) the reference-generated fixture itself, when routing agrees everywhere
-    if gold is not None and flips == 0:
+    # (4) the reference-generated fixture itself, when routing agrees everywhere
+    if gold is not None and gold_flips == 0:
         st = gold['stride']
         errs['gold_fwd'] = [rel(o[:, :, ::st, ::st], g) for o, g in zip(og, gold['outs'])]
         assert max(errs['gold_fwd']) < TOL, errs
@@ -156,7 +158,7 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
         errs['worst_grads'] = sorted(worst.items(), key=lambda kv: -kv[1])[:6]
         bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
         assert not bad, bad
-        if gold is not None and flips == 0 and 'grads' in gold:
+        if gold is not None and gold_flips == 0 and 'grads' in gold:
             for pname, dg in gold['grads'].items():
                 got = dict(net.named_parameters())[pname].grad.detach().float().cpu().reshape(-1)
                 if 'full' in dg:
