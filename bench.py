@@ -374,8 +374,10 @@ def build_model(args, world, ep):
     net = net.cuda().train()
     model = net
     if ep:
-        from sm3det_b200.expert_parallel import enable_expert_parallel
+        from sm3det_b200.expert_parallel import ddp_ignored_parameters, enable_expert_parallel
         enable_expert_parallel(net, dist.new_group(list(range(world))))
+        # expert parameters never enter a gradient bucket: each rank keeps the gradients of the experts it owns
+        torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(net, ddp_ignored_parameters(net))
     if world > 1:
         local = int(os.environ.get('LOCAL_RANK', '0'))
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=False,
@@ -488,6 +490,8 @@ def run_ours(args):
     e3.record()
     sync()
     clocks = sampler.stop() if rank == 0 else None
+    if ep:
+        net._ep_ctx.check()                      # expert-side capacity was never exceeded (reads a device flag; off the clock)
     ms_e2e = e2.elapsed_time(e3) / args.steps
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     t = torch.tensor([ms, ms_e2e], device='cuda', dtype=torch.float64)

@@ -145,6 +145,10 @@ size_t sm3_ffn_fused_workspace_bytes(const sm3_ffn_args* args);   /* 0: accumula
 enum { SM3_LN_NHWC = 0, SM3_LN_PATCH2 = 1, SM3_LN_NCHW = 2 };
 int sm3_layernorm_fwd(const float* x, const float* weight, const float* bias, float* y, float* stats,
                       int64_t tokens, int32_t C, float eps, int32_t out_mode, int32_t H, int32_t W, void* stream);
+/* Block LayerNorm (:351) fused with the operand split of the following pointwise GEMM: writes the K-major bf16 hi|lo image
+ * (sm3_gemm_packed_act_elems(T, C, 0, 128) elements) that sm3_ffn_fused / sm3_gemm bulk-copy; y (fp32 [T,C]) is optional. */
+int sm3_layernorm_fwd_img(const float* x, const float* weight, const float* bias, uint16_t* img, float* y, float* stats,
+                          int64_t T, int32_t C, float eps, void* stream);
 int sm3_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* weight, float* dx,
                       float* dweight, float* dbias, int64_t tokens, int32_t C, int32_t in_mode, int32_t H,
                       int32_t W, int32_t dx_accumulate, void* stream);
@@ -260,6 +264,17 @@ int sm3_scale_rows(const float* x, const float* row_scale, const float* col_scal
  * src_rank < 0 or row < 0 -> zero row. */
 int sm3_gather_rows_peer(const float* const* bases, const int32_t* const* token_lists, const int32_t* src_rank,
                          const int32_t* src_row, const float* scale, float* out, int64_t rows, int32_t C, void* stream);
+
+/* Expert-parallel exchange plan on the device (no host sync): from the all-gathered [W][2][E] (pair count, segment start)
+ * table, the calling rank's expert-side gather lists / grouped-GEMM schedule and its source-side combine lists.  Replaces
+ * the index bookkeeping of SparseDispatcher.__init__ (convnext_moe.py:252-262) for the expert-sharded layout. */
+typedef struct sm3_ep_plan_args {
+  const int32_t* allm; const int32_t* tile_group_s; const int32_t* num_tiles_s; const int32_t* pair_token;
+  int32_t W, me, E, R_s, cap;
+  int32_t* src_rank; int32_t* src_slot; int32_t* tile_group; int32_t* num_tiles; int32_t* seg_begin; int32_t* seg_end;
+  int32_t* comb_rank; int32_t* comb_row; int32_t* overflow;
+} sm3_ep_plan_args;
+int sm3_ep_plan(const sm3_ep_plan_args* args, void* stream);
 
 /* ---- LSKNet-MoE backbone (BASELINE config 5; mmrotate/models/backbones/lsk_moe.py) -------------------
  * sm3_dwconv_fwd / _wgrad : depthwise ks x ks conv, dilation dil, "same" padding, NHWC; weight_t = taps as

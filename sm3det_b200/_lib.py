@@ -67,6 +67,15 @@ class FfnArgs(C.Structure):
     ]
 
 
+class EpPlanArgs(C.Structure):
+    _fields_ = [
+        ('allm', c_i32p), ('tile_group_s', c_i32p), ('num_tiles_s', c_i32p), ('pair_token', c_i32p),
+        ('W', C.c_int32), ('me', C.c_int32), ('E', C.c_int32), ('R_s', C.c_int32), ('cap', C.c_int32),
+        ('src_rank', c_i32p), ('src_slot', c_i32p), ('tile_group', c_i32p), ('num_tiles', c_i32p),
+        ('seg_begin', c_i32p), ('seg_end', c_i32p), ('comb_rank', c_i32p), ('comb_row', c_i32p), ('overflow', c_i32p),
+    ]
+
+
 # name -> argtypes (restype is always int unless listed in _RESTYPES); mirrors include/sm3det_b200.h
 _I32, _I64, _F32, _P = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 SIGNATURES = {
@@ -87,6 +96,7 @@ SIGNATURES = {
     'sm3_moe_router_workspace_bytes': [C.POINTER(RouterArgs)],
     'sm3_moe_plan_workspace_bytes': [C.POINTER(PlanArgs)],
     'sm3_layernorm_fwd': [_P, _P, _P, _P, _P, _I64, _I32, _F32, _I32, _I32, _I32, _P],
+    'sm3_layernorm_fwd_img': [_P, _P, _P, _P, _P, _P, _I64, _I32, _F32, _P],
     'sm3_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P],
     'sm3_stem_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _P],
     'sm3_stem_wgrad': [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
@@ -103,6 +113,7 @@ SIGNATURES = {
     'sm3_gather_sum': [_P, _P, _P, _P, _I32, _I32, _I32, _P],
     'sm3_scale_rows': [_P, _P, _P, _P, _I64, _I32, _P],
     'sm3_moe_router_bwd': [_P, _P],
+    'sm3_ep_plan': [C.POINTER(EpPlanArgs), _P],
     'sm3_gather_rows_peer': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     'sm3_upsample_add': [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     'sm3_upsample_add_bwd': [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P],

@@ -196,6 +196,7 @@ class ConvNeXtBlock(nn.Module):
                 packs = {'w1': pc.get('w1', [w1], False), 'w2': pc.get('w2', [w2], False)}
                 if grad:
                     packs['w1_t'] = pc.get('w1', [w1], True)
+            packs['grad'] = grad
             out = Fn.DenseBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias,
                                         w1, f.pointwise_conv1.bias, w2, f.pointwise_conv2.bias, self.gamma, rs, eps, packs)
             return out, None

@@ -86,6 +86,10 @@ int sm3_layernorm_fwd(const float* x, const float* w, const float* b, float* y, 
                       float eps, int32_t out_mode, int32_t H, int32_t W, void* stream) {
   return layernorm_fwd(x, w, b, y, stats, T, C, eps, out_mode, H, W, S(stream));
 }
+int sm3_layernorm_fwd_img(const float* x, const float* w, const float* b, uint16_t* img, float* y, float* stats, int64_t T,
+                          int32_t C, float eps, void* stream) {
+  return layernorm_fwd_img(x, w, b, img, y, stats, T, C, eps, S(stream));
+}
 int sm3_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* w, float* dx, float* dw,
                       float* db, int64_t T, int32_t C, int32_t in_mode, int32_t H, int32_t W, int32_t dx_accum,
                       void* stream) {
@@ -238,6 +242,16 @@ int sm3_im2col(const float* x, float* col, int32_t N, int32_t H, int32_t W, int3
 int sm3_col2im(const float* dcol, float* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t ks, int32_t stride,
                int32_t pad, int32_t Kp, int32_t nchw, void* stream) {
   return col2im(dcol, dx, N, H, W, Cin, ks, stride, pad, Kp, nchw, S(stream));
+}
+
+int sm3_ep_plan(const sm3_ep_plan_args* a, void* stream) {
+  if (!a) { set_last_error("sm3_ep_plan: null args"); return SM3_ERR_INVALID_ARG; }
+  EpPlanArgs p{};
+  p.allm = a->allm; p.tile_group_s = a->tile_group_s; p.num_tiles_s = a->num_tiles_s; p.pair_token = a->pair_token;
+  p.W = a->W; p.me = a->me; p.E = a->E; p.R_s = a->R_s; p.cap = a->cap;
+  p.src_rank = a->src_rank; p.src_slot = a->src_slot; p.tile_group = a->tile_group; p.num_tiles = a->num_tiles;
+  p.seg_begin = a->seg_begin; p.seg_end = a->seg_end; p.comb_rank = a->comb_rank; p.comb_row = a->comb_row; p.overflow = a->overflow;
+  return ep_plan(p, S(stream));
 }
 
 int sm3_upsample_add(const float* a, const float* b, float* out, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w,

@@ -237,13 +237,15 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_chain_kernel(const __grid_cons
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float x = __uint_as_float(rh[i + u]) + bb[u];
-            if constexpr (MODE == 0) y[i + u] = gelu_fast(x);
+            if (p.debug & 1) y[i + u] = x;
+            else if constexpr (MODE == 0) y[i + u] = gelu_fast(x);
             else y[i + u] = __uint_as_float(rd[i + u]) * gelu_grad_fast(x);
           }
         }
         mbar_wait(act_empty, (n_c & 1u) ^ 1u);          // GEMM-b of the previous chunk has finished reading the block
 #pragma unroll
         for (int i = 0; i < HCW; i += 8) {
+          if (p.debug & 2) break;
           uint4 hi, lo;
           split8(&y[i], hi, lo);
           const int kk = c0 + i;

@@ -45,6 +45,7 @@ struct ChainParams {
   float* out;             // [M, C]
   float* aux_out;         // [M, C] or null: acc_o + bias2 before scaling (y2, needed for dgamma)
   int M, C, H4, HC, passes, mode;
+  int debug;              // perf experiments only: bit0 = middle stage skips the GELU math, bit1 = skip the operand split/stores
 };
 int chain(const ChainParams& p, cudaStream_t stream);
 
@@ -59,6 +60,7 @@ struct WgradParams {
   float* dw2;             // [C, H4]  accumulated
   float* db1;             // [H4]     accumulated
   int M, C, H4, HC, passes;
+  int debug;
 };
 int wgrad(const WgradParams& p, cudaStream_t stream);
 

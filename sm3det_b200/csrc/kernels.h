@@ -11,6 +11,9 @@ const char* last_error();
 // norm.cu ----------------------------------------------------------------------------------------
 int layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, long long T, int C,
                   float eps, int out_mode, int H, int W, cudaStream_t stream);
+// LayerNorm -> K-major bf16 hi|lo operand image (128-row tiles, same layout as gemm::pack_act); y (fp32) optional
+int layernorm_fwd_img(const float* x, const float* w, const float* b, unsigned short* img, float* y, float* stats, long long T,
+                      int C, float eps, cudaStream_t stream);
 int layernorm_bwd(const float* dy, const float* x, const float* stats, const float* w, float* dx, float* dw,
                   float* db, long long T, int C, int in_mode, int H, int W, int dx_accum, cudaStream_t stream);
 int stem_fwd(const float* x, const float* wt, const float* bias, const float* lnw, const float* lnb, float* y,
@@ -127,6 +130,20 @@ int scale_rows(const float* x, const float* rs, const float* cs, float* out, lon
 
 int gather_rows_peer(const float* const* bases, const int* const* token_lists, const int* src_rank, const int* src_row,
                      const float* scale, float* out, long long rows, int C, cudaStream_t stream);
+
+struct EpPlanArgs {
+  const int* allm;            // [W][2][E] all-gathered (pair counts, segment starts) of every rank
+  const int* tile_group_s;    // local plan: expert of each 128-slot tile
+  const int* num_tiles_s;     // local plan: live tile count (device scalar)
+  const int* pair_token;      // [R_s] local slot -> token (-1 = padding)
+  int W, me, E, R_s, cap;
+  int* src_rank; int* src_slot;     // [cap]   expert side: where each of my rows comes from
+  int* tile_group; int* num_tiles;  // [cap/128], [1]  grouped-GEMM schedule of my experts
+  int* seg_begin; int* seg_end;     // [E/W]
+  int* comb_rank; int* comb_row;    // [R_s]   source side: where each of my slots' outputs lives
+  int* overflow;                    // [1]     max rows needed if it ever exceeded cap (else untouched)
+};
+int ep_plan(const EpPlanArgs& a, cudaStream_t stream);
 
 // lsk.cu (LSKNet-MoE, BASELINE config 5) --------------------------------------------------------------
 // wt: depthwise taps transposed to [ks*ks][C]; "same" padding dil*(ks-1)/2.  Instantiated: (3,1) (5,1) (7,3).

@@ -91,6 +91,86 @@ __global__ void __launch_bounds__(256) ln_fwd_nchw_kernel(const float* __restric
   }
 }
 
+// LayerNorm whose output goes straight into the K-major bf16 hi|lo operand image of the following GEMM (the fused FFN's A
+// operand): fp32 `v` is never written and the separate pack_act pass (read v, write image) disappears.  G lanes per token,
+// each lane owns one 16-byte operand chunk = 8 consecutive channels (G = 16 for C <= 128, 32 for C <= 256).
+template <int G>
+__global__ void __launch_bounds__(256) ln_fwd_img_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, uint8_t* __restrict__ img,
+                                                        float* __restrict__ y, float* __restrict__ stats, long long T,
+                                                        long long T_pad, int C, float eps) {
+  constexpr int TPW = 32 / G;                       // tokens per warp
+  const int lane = threadIdx.x & 31, g = lane % G;
+  const long long t = ((long long)(blockIdx.x * blockDim.x + threadIdx.x) >> 5) * TPW + lane / G;
+  const int chunks = C / 8, kblocks = C / 32;
+  const bool act = g < chunks, row_ok = t < T;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (act && row_ok) {
+    const float4 p0 = ldg_f4(x + t * C + g * 8), p1 = ldg_f4(x + t * C + g * 8 + 4);
+    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s += v[e];
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  if (act) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = v[e] - mean; q += d * d; }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  if (!act || t >= T_pad) return;
+  if (stats && g == 0 && row_ok) { stats[2 * t] = mean; stats[2 * t + 1] = rstd; }
+  float o8[8];
+  if (row_ok) {
+    const float4 w0 = ldg_f4(w + g * 8), w1 = ldg_f4(w + g * 8 + 4), b0 = ldg_f4(b + g * 8), b1 = ldg_f4(b + g * 8 + 4);
+    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o8[e] = (v[e] - mean) * rstd * ww[e] + bb[e];
+    if (y) {
+      *reinterpret_cast<float4*>(y + t * C + g * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+      *reinterpret_cast<float4*>(y + t * C + g * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o8[e] = 0.f;        // rows of the last 128-row tile beyond T: zero operand rows
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) {
+    const uint32_t u0 = __float_as_uint(o8[e]), u1 = __float_as_uint(o8[e + 1]);
+    hi[e / 2] = __byte_perm(u0, u1, 0x7632);
+    const uint32_t r0 = __float_as_uint(o8[e] - __uint_as_float(u0 & 0xFFFF0000u)) + 0x8000u;
+    const uint32_t r1 = __float_as_uint(o8[e + 1] - __uint_as_float(u1 & 0xFFFF0000u)) + 0x8000u;
+    lo[e / 2] = __byte_perm(r0, r1, 0x7632);
+  }
+  const long long rt = t >> 7;
+  const uint32_t rr = (uint32_t)(t & 127), kb = (uint32_t)g >> 2, c = (uint32_t)g & 3u;
+  uint8_t* dst = img + (rt * kblocks + kb) * 16384LL + ((rr >> 3) * 512u + (rr & 7u) * 64u + ((c ^ ((rr >> 1) & 3u)) << 4));
+  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+int layernorm_fwd_img(const float* x, const float* w, const float* b, unsigned short* img, float* y, float* stats, long long T,
+                      int C, float eps, cudaStream_t stream) {
+  SM3_REQUIRE(x && w && b && img && T > 0, SM3_ERR_INVALID_ARG, "layernorm_fwd_img: null/empty argument");
+  SM3_REQUIRE(C % 32 == 0 && C <= 256, SM3_ERR_UNSUPPORTED_SHAPE, "layernorm_fwd_img: C=%d must be a multiple of 32 <= 256", C);
+  const long long T_pad = (T + 127) / 128 * 128;
+  if (C <= 128) {
+    const long long warps = (T_pad + 1) / 2;
+    ln_fwd_img_kernel<16><<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(x, w, b, reinterpret_cast<uint8_t*>(img), y, stats, T, T_pad, C, eps);
+  } else {
+    ln_fwd_img_kernel<32><<<(unsigned)((T_pad + 7) / 8), 256, 0, stream>>>(x, w, b, reinterpret_cast<uint8_t*>(img), y, stats, T, T_pad, C, eps);
+  }
+  return check_launch("layernorm_fwd_img");
+}
+
 int layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, long long T, int C,
                   float eps, int out_mode, int H, int W, cudaStream_t stream) {
   SM3_REQUIRE(x && w && b && y && T > 0, SM3_ERR_INVALID_ARG, "layernorm_fwd: null/empty argument");

@@ -139,4 +139,74 @@ int gather_rows_peer(const float* const* bases, const int* const* token_lists, c
   return check_launch("gather_rows_peer");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Expert-parallel exchange plan, built ON THE DEVICE from the all-gathered per-rank (count, segment start) tables -- no host
+// round trip per layer (round 1 did `.cpu()` + a Python loop here).  One block.  For the calling rank `me` of `W`:
+//   expert side: row r of my padded expert-major space <- (source rank, slot in that rank's expert-sorted pair list);
+//                experts are laid out one after another, each padded to 128 rows; inside an expert, sources in rank order;
+//   source side: my slot l (expert g) lives on rank g / E_loc at row  l - seg_s[g] + seg_owner[g] + off[g][me].
+// Rows beyond `cap` are dropped and *overflow = rows needed (the host checks it off the critical path).
+__global__ void __launch_bounds__(1024) ep_plan_kernel(const EpPlanArgs a) {
+  __shared__ int s_cnt[8][32], s_seg[8][32];   // [rank][expert]
+  __shared__ int s_start[32];                   // first row of global expert g on its owner
+  __shared__ int s_off[32][8];                  // offset of source s inside expert g's segment
+  const int W = a.W, E = a.E, El = E / W, me = a.me, tid = threadIdx.x;
+  for (int i = tid; i < W * E; i += blockDim.x) {
+    const int r = i / E, e = i % E;
+    s_cnt[r][e] = a.allm[(r * 2 + 0) * E + e];
+    s_seg[r][e] = a.allm[(r * 2 + 1) * E + e];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int my_rows = 0, my_tiles = 0;
+    for (int d = 0; d < W; ++d) {
+      int pos = 0;
+      for (int el = 0; el < El; ++el) {
+        const int g = d * El + el;
+        s_start[g] = pos;
+        int acc = 0;
+        for (int s = 0; s < W; ++s) { s_off[g][s] = acc; acc += s_cnt[s][g]; }
+        const int nt = (acc + 127) / 128;
+        if (d == me) {
+          a.seg_begin[el] = pos; a.seg_end[el] = pos + acc;
+          for (int t = 0; t < nt; ++t) if (my_tiles + t < a.cap / 128) a.tile_group[my_tiles + t] = el;
+          my_tiles += nt;
+        }
+        pos += nt * 128;
+      }
+      if (d == me) my_rows = pos;
+    }
+    *a.num_tiles = min(my_tiles, a.cap / 128);
+    if (my_rows > a.cap) atomicMax(a.overflow, my_rows);
+  }
+  for (int r = tid; r < a.cap; r += blockDim.x) { a.src_rank[r] = -1; a.src_slot[r] = 0; }
+  __syncthreads();
+  for (int el = 0; el < El; ++el) {
+    const int g = me * El + el;
+    for (int s = 0; s < W; ++s) {
+      const int L = s_cnt[s][g], D = s_start[g] + s_off[g][s], S = s_seg[s][g];
+      for (int i = tid; i < L; i += blockDim.x)
+        if (D + i < a.cap) { a.src_rank[D + i] = s; a.src_slot[D + i] = S + i; }
+    }
+  }
+  const int live_rows = __ldg(a.num_tiles_s) * 128;
+  for (int l = tid; l < a.R_s; l += blockDim.x) {
+    int g = __ldg(a.tile_group_s + (l >> 7));
+    g = g < 0 ? 0 : (g >= E ? E - 1 : g);
+    const bool live = l < live_rows && __ldg(a.pair_token + l) >= 0;
+    const int row = l - s_seg[me][g] + s_start[g] + s_off[g][me];
+    a.comb_rank[l] = live ? g / El : -1;
+    a.comb_row[l] = live ? row : 0;
+  }
+}
+
+int ep_plan(const EpPlanArgs& a, cudaStream_t stream) {
+  SM3_REQUIRE(a.allm && a.tile_group_s && a.num_tiles_s && a.pair_token && a.src_rank && a.src_slot && a.tile_group &&
+              a.num_tiles && a.seg_begin && a.seg_end && a.comb_rank && a.comb_row && a.overflow, SM3_ERR_INVALID_ARG, "ep_plan: null argument");
+  SM3_REQUIRE(a.W >= 1 && a.W <= 8 && a.E >= a.W && a.E <= 32 && a.E % a.W == 0 && a.me >= 0 && a.me < a.W && a.cap % 128 == 0 && a.cap > 0,
+              SM3_ERR_UNSUPPORTED_SHAPE, "ep_plan: W=%d E=%d cap=%d", a.W, a.E, a.cap);
+  ep_plan_kernel<<<1, 1024, 0, stream>>>(a);
+  return check_launch("ep_plan_kernel");
+}
+
 }  // namespace sm3

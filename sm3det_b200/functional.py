@@ -166,12 +166,14 @@ class DenseBlockFn(Function):
     def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps, packs):
         N, H, W, C = x.shape
         T = N * H * W
-        train = any(ctx.needs_input_grad)
-        u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
+        # autograd.Function.forward runs with grad mode off and needs_input_grad reflects requires_grad only: the caller
+        # says whether a backward can follow (it also chose which weight images to provide on that basis)
+        train = any(ctx.needs_input_grad) and packs.get('grad', True)
         fused = packs.get('fused')
         if fused is not None and (not train or fused['train']):
-            v_img = ops.pack_act(v, rows=T, cols=C, mn_major=False)
-            del v
+            # LayerNorm writes the FFN's A-operand image directly: fp32 v and the separate split pass never exist
+            u = ops.dwconv7(x, _taps(dww), dwb)
+            v_img, _, stats = ops.layernorm_fwd_img(u, lnw, lnb, eps, tokens=T, C=C, save_stats=train)
             out, y2 = ops.ffn_fused_fwd(v_img, packs['w1_c'][0], packs['w2_n'][0], b1, b2, T=T, C=C, chunk=fused['fwd'],
                                         gamma=gamma, row_scale=row_scale, resid=x.view(T, C), want_aux=train)
             if train:
@@ -180,6 +182,7 @@ class DenseBlockFn(Function):
                 ctx.packs = packs
             return out.view(N, H, W, C)
         ctx.fused = None
+        u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
         # GEMM1 stores the pre-activation only; GELU runs in the HBM-bound act_pack kernel, which emits the result
         # directly as GEMM2's pre-split A operand (fp32 `a` never exists)
         h = ops.linear_fwd(v, w1, b1, packed=packs.get('w1'))

@@ -5,6 +5,7 @@ all arithmetic happens in ``libsm3det_b200.so``.  Every wrapper validates that i
 fp32/int32, contiguous and on the current CUDA device, then passes raw pointers.
 """
 import ctypes as C
+import ctypes as _ct      # the fused-FFN wrappers take a keyword argument named C (channels)
 from typing import Optional
 
 import torch
@@ -195,7 +196,7 @@ def ffn_fused_fwd(v_img, w1_img, w2_img, b1, b2, *, T, C, chunk, gamma=None, row
     a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_FWD, a1=v_img, wa1=w1_img, b1=b1, wb=w2_img)
     a.bias2 = _p(b2); a.col_scale = _p(gamma); a.row_scale = _p(row_scale); a.resid = _p(resid)
     a.out = _p(out); a.aux_out = _p(aux)
-    _lib.check(lib.sm3_ffn_fused(C.byref(a), _stream()), 'sm3_ffn_fused(fwd)')
+    _lib.check(lib.sm3_ffn_fused(_ct.byref(a), _stream()), 'sm3_ffn_fused(fwd)')
     return out, aux
 
 
@@ -205,7 +206,7 @@ def ffn_fused_bwd(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, *, T, C, chunk):
     out = torch.empty((T, C), device=b1.device, dtype=torch.float32)
     a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_BWD_DX, a1=v_img, a2=dz_img, wa1=w1_img, wa2=w2gt_img, b1=b1, wb=w1t_img)
     a.out = _p(out)
-    _lib.check(lib.sm3_ffn_fused(C.byref(a), _stream()), 'sm3_ffn_fused(bwd)')
+    _lib.check(lib.sm3_ffn_fused(_ct.byref(a), _stream()), 'sm3_ffn_fused(bwd)')
     return out
 
 
@@ -214,7 +215,7 @@ def ffn_fused_wgrad(v_img, dz_img, w1_img, w2gt_img, b1, gamma, dw1, dw2, db1, *
     lib = _lib.load()
     a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_WGRAD, a1=v_img, a2=dz_img, wa1=w1_img, wa2=w2gt_img, b1=b1)
     a.col_scale = _p(gamma); a.dw1 = _p(dw1); a.dw2 = _p(dw2); a.db1 = _p(db1)
-    _lib.check(lib.sm3_ffn_fused(C.byref(a), _stream()), 'sm3_ffn_fused(wgrad)')
+    _lib.check(lib.sm3_ffn_fused(_ct.byref(a), _stream()), 'sm3_ffn_fused(wgrad)')
 
 
 def ffn_fused_bwd_all(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, gamma, dw1, dw2, db1, *, T, C, chunk):
@@ -366,6 +367,17 @@ def layernorm_fwd(x, w, b, eps, *, tokens, C, out=None, out_mode=LN_NHWC, H=0, W
     _lib.check(lib.sm3_layernorm_fwd(_p(x), _p(w), _p(b), _p(out), _p(stats), tokens, C, float(eps), out_mode, H, W,
                                      _stream()), 'sm3_layernorm_fwd')
     return out, stats
+
+
+def layernorm_fwd_img(x, w, b, eps, *, tokens, C, save_stats=False, want_f32=False):
+    """LayerNorm whose output is the K-major bf16 hi|lo operand image of the next GEMM -> (img, v_f32 | None, stats | None)."""
+    lib = _lib.load()
+    img = torch.empty((lib.sm3_gemm_packed_act_elems(tokens, C, 0, 128),), device=x.device, dtype=torch.int16)
+    y = torch.empty((tokens, C), device=x.device, dtype=torch.float32) if want_f32 else None
+    stats = torch.empty((tokens, 2), device=x.device, dtype=torch.float32) if save_stats else None
+    _lib.check(lib.sm3_layernorm_fwd_img(_p(x), _p(w), _p(b), img.data_ptr(), _p(y), _p(stats), tokens, C, float(eps), _stream()),
+               'sm3_layernorm_fwd_img')
+    return img, y, stats
 
 
 def layernorm_bwd(dy, x, stats, w, dw, db, *, tokens, C, in_mode=LN_NHWC, H=0, W=0, dx=None, accumulate=False):

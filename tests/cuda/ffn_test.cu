@@ -173,6 +173,7 @@ static void check(int M, int C, bool with_rs) {
   }
 }
 
+static int g_passes = 3, g_debug = 0;
 static void timeit(int M, int C) {
   const int H4 = 4 * C;
   std::vector<float> w1((size_t)H4 * C, 0.01f), w2((size_t)C * H4, 0.01f), b1(H4, 0.1f), b2(C, 0.1f), gm(C, 0.5f);
@@ -193,10 +194,10 @@ static void timeit(int M, int C) {
       p.a1 = v_img; p.a2 = dz_img; p.wa1 = wa1; p.wa2 = wa2;
       p.wb = mode == 0 ? pack_w(dw2, H4, 1, C, H4, C) : pack_w(dw1, 1, C, C, H4, C);
       p.bias1 = db1; p.bias2 = mode == 0 ? db2 : nullptr; p.col_scale = mode == 0 ? dgm : nullptr; p.resid = mode == 0 ? dx : nullptr;
-      p.out = dout; p.aux_out = mode == 0 ? daux : nullptr; p.M = M; p.C = C; p.H4 = H4; p.HC = HC; p.passes = 3; p.mode = mode;
+      p.out = dout; p.aux_out = mode == 0 ? daux : nullptr; p.M = M; p.C = C; p.H4 = H4; p.HC = HC; p.passes = g_passes; p.mode = mode; p.debug = g_debug;
     } else {
       q.a1 = v_img; q.a2 = dz_img; q.wa1 = wa1; q.wa2 = wa2; q.bias1 = db1; q.gamma = dgm; q.dw1 = gw1; q.dw2 = gw2; q.db1 = gb1;
-      q.M = M; q.C = C; q.H4 = H4; q.HC = HC; q.passes = 3;
+      q.M = M; q.C = C; q.H4 = H4; q.HC = HC; q.passes = g_passes;
     }
     auto launch = [&]() { return mode < 2 ? ffn::chain(p, 0) : ffn::wgrad(q, 0); };
     for (int i = 0; i < 2; ++i) if (launch() != 0) { printf("launch failed: %s\n", last_error()); exit(3); }
@@ -217,6 +218,9 @@ static void timeit(int M, int C) {
 
 int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "all";
+  if (argc > 2) g_passes = atoi(argv[2]);
+  if (argc > 3) g_debug = atoi(argv[3]);
+  if (what == "one") { printf("passes=%d debug=%d\n", g_passes, g_debug); timeit(524288, 96); return 0; }
   if (what == "check" || what == "all") {
     check(128, 96, false);
     check(640, 96, true);

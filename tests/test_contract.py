@@ -136,8 +136,8 @@ def test_pack_cache_invalidation(monkeypatch):
     from sm3det_b200.backbone import PackCache
     calls = []
 
-    def fake_pack(w, *, transposed, groups=1, out=None):
-        calls.append((w.data_ptr(), transposed, groups))
+    def fake_pack(w, *, transposed, groups=1, out=None, tile=0):
+        calls.append((w.data_ptr(), transposed, groups, tile))
         return (out if out is not None else torch.zeros(4, dtype=torch.int16)), 4
 
     monkeypatch.setattr(ops, 'pack_weight', fake_pack)
@@ -147,6 +147,10 @@ def test_pack_cache_invalidation(monkeypatch):
     assert pc.get('w1', [p], False) is a and len(calls) == 1            # hit
     pc.get('w1', [p], True)
     assert len(calls) == 2                                               # the transposed image is a separate entry
+    pc.get('w1', [p], False, tile=64)
+    assert len(calls) == 3 and pc.get('w1', [p], False, tile=64) is not a  # so is an image with another tile width
+    assert pc.get('w1', [p], False) is a
+    calls.pop()
     with torch.no_grad():
         p.add_(1.0)                                                      # what an optimizer step does
     pc.get('w1', [p], False)

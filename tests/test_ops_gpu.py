@@ -1,5 +1,6 @@
 """GPU parity of each C-ABI kernel against plain torch fp32 on the CPU (oracle arithmetic)."""
 import math
+import os
 
 import pytest
 import torch
@@ -268,3 +269,118 @@ def test_gather_rows_peer_single_device(ops):
     want2 = x.cpu()[(src_slot % T).long()]
     want2[src_rank < 0] = 0
     assert torch.equal(direct.cpu(), want2)
+
+
+@pytest.mark.parametrize('W,E,k', [(2, 4, 2), (4, 8, 2), (8, 16, 2), (8, 8, 3)])
+def test_ep_plan_kernel_matches_host_plan(W, E, k):
+    """sm3_ep_plan (the device-side expert-parallel exchange plan, no host sync) against the host plan the world-2 gloo test
+    validates (expert_parallel._build_plan), for every rank of a simulated W-rank group: ragged counts, an idle expert."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'dist'))
+    from ep_plan_worker import local_plan
+    from sm3det_b200.expert_parallel import EPContext, _build_plan, device_plan
+    T = 700
+    plans = []
+    for r in range(W):
+        g = torch.Generator().manual_seed(40 + r)
+        logits = torch.randn(T, E, generator=g)
+        if r == 1:
+            logits[:, E - 1] = -1e9               # an expert that receives nothing from this rank
+        plans.append(local_plan(logits.topk(k, dim=1).indices, E))
+    allm = torch.stack([torch.stack([p[0], p[1]]) for p in plans]).to(torch.int32)          # [W, 2, E]
+    for me in range(W):
+        counts, seg_begin, tile_group, num_tiles, pair_token, slot_of = plans[me]
+        R_s = pair_token.numel()
+        ctx = EPContext.__new__(EPContext)
+        ctx.world, ctx.rank = W, me
+        ctx.overflow = torch.zeros(1, device='cuda', dtype=torch.int32)
+        ref = _build_plan(ctx, allm[:, 0], allm[:, 1], tile_group, num_tiles, pair_token, E, R_s, torch.device('cpu'))
+        cap = (ref['R_d'] // 128 + 3) * 128
+        tg = tile_group.clone()
+        tg[tg == 12345] = 0                        # the device plan clamps garbage tile ids itself; keep the input in range too
+        P = device_plan(ctx, allm.cuda(), tile_group.cuda(), num_tiles.cuda(), pair_token.cuda(), E, R_s, cap)
+        torch.cuda.synchronize()
+        R_d = ref['R_d']
+        assert int(P['num_tiles']) * 128 == R_d and int(ctx.overflow) == 0
+        assert torch.equal(P['src_rank'][:R_d].cpu(), ref['src_rank'][:R_d]) and bool((P['src_rank'][R_d:] == -1).all())
+        live = ref['src_rank'][:R_d] >= 0
+        assert torch.equal(P['src_slot'][:R_d].cpu()[live], ref['src_slot'][:R_d][live])
+        assert torch.equal(P['tile_group'][:R_d // 128].cpu(), ref['tile_group'][:R_d // 128])
+        assert torch.equal(P['seg_begin'].cpu(), ref['seg_begin']) and torch.equal(P['seg_end'].cpu(), ref['seg_end'])
+        assert torch.equal(P['comb_rank'].cpu(), ref['comb_rank'])
+        lv = ref['comb_rank'] >= 0
+        assert torch.equal(P['comb_row'].cpu()[lv], ref['comb_row'][lv])
+        # capacity overflow is reported, not silently truncated
+        ctx.overflow.zero_()
+        device_plan(ctx, allm.cuda(), tile_group.cuda(), num_tiles.cuda(), pair_token.cuda(), E, R_s, 128)
+        assert int(ctx.overflow) == R_d or R_d <= 128
+
+
+def decode_k_image(img, T, C):
+    """fp32 [T,C] value (hi + lo) of a K-major bf16 hi|lo operand image (128-row tiles, 32-k blocks, SWIZZLE_64B)."""
+    img = img.cpu().view(torch.int16).numpy().view('uint16')
+    t = torch.arange(T).view(-1, 1)
+    c = torch.arange(C).view(1, -1)
+    rt, rr, kb, ch, e = t // 128, t % 128, c // 32, (c % 32) // 8, c % 8
+    off = (rt * (C // 32) + kb) * 16384 + (rr >> 3) * 512 + (rr & 7) * 64 + ((ch ^ ((rr >> 1) & 3)) << 4) + e * 2
+    idx = (off // 2).numpy()
+
+    def bf(a):
+        return torch.from_numpy((a.astype('uint32') << 16).view('float32').copy())
+    return bf(img[idx]) + bf(img[idx + 4096])
+
+
+@pytest.mark.parametrize('T,C', [(300, 96), (1024, 64), (129, 192), (5, 128), (256, 32)])
+def test_layernorm_to_operand_image(T, C):
+    """sm3_layernorm_fwd_img: LN output written directly as the fused FFN's A-operand image (hi + lo = fp32 value to 2^-17),
+    statistics as the plain kernel's, rows of the last 128-row tile beyond T zero."""
+    from sm3det_b200 import ops
+    g = torch.Generator().manual_seed(T + C)
+    x = torch.randn(T, C, generator=g) * 2 + 0.5
+    w, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    ref = F.layer_norm(x, (C,), w, b, 1e-6)
+    img, v, stats = ops.layernorm_fwd_img(x.cuda(), w.cuda(), b.cuda(), 1e-6, tokens=T, C=C, save_stats=True, want_f32=True)
+    T_pad = (T + 127) // 128 * 128
+    dec = decode_k_image(img, T_pad, C)
+    assert (dec[:T] - ref).abs().max() < 2e-5 * ref.abs().max()
+    assert (v.cpu() - ref).abs().max() < 1e-5 * ref.abs().max()
+    assert (dec[:T] - v.cpu()).abs().max() <= 2.0 ** -16 * ref.abs().max()
+    assert float(dec[T:].abs().max() if T_pad > T else 0.0) == 0.0
+    assert torch.allclose(stats[:, 0].cpu(), x.mean(1), atol=1e-5) and torch.allclose(stats[:, 1].cpu(), (x.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-5)
+    # and the same image as the separate pack of the fp32 output, up to LN rounding
+    dec2 = decode_k_image(ops.pack_act(v, rows=T, cols=C, mn_major=False), T_pad, C)
+    assert (dec2[:T] - dec[:T]).abs().max() <= 2.0 ** -16 * ref.abs().max()
+
+
+@pytest.mark.parametrize('T,C', [(640, 96), (200, 64), (384, 32)])
+def test_fused_ffn_matches_torch(T, C):
+    """sm3_ffn_fused (forward, backward into dv, weight gradients) vs plain torch fp32 on the CPU."""
+    from sm3det_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    v = torch.randn(T, C, generator=g, requires_grad=True)
+    x = torch.randn(T, C, generator=g)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).requires_grad_(True)
+    b1 = (torch.randn(4 * C, generator=g) * 0.2).requires_grad_(True)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).requires_grad_(True)
+    b2 = torch.randn(C, generator=g) * 0.2
+    gamma = torch.rand(C, generator=g) * 0.9 + 0.1
+    y2 = F.linear(F.gelu(F.linear(v, w1, b1)), w2, b2)
+    out = x + gamma * y2
+    dz = torch.randn(T, C, generator=g) * 0.1
+    out.backward(dz)
+    cf, cb, cw = ops.ffn_chunk(0, C), ops.ffn_chunk(1, C), ops.ffn_chunk(2, C)
+    assert cf and cb and cb == cw
+    dev = lambda t: t.detach().cuda().contiguous()
+    v_img = ops.pack_act(dev(v), rows=T, cols=C, mn_major=False)
+    w1c, _ = ops.pack_weight(dev(w1), transposed=False, tile=cf)
+    w2n, _ = ops.pack_weight(dev(w2), transposed=False, tile=C)
+    o, aux = ops.ffn_fused_fwd(v_img, w1c, w2n, dev(b1), dev(b2), T=T, C=C, chunk=cf, gamma=dev(gamma), resid=dev(x), want_aux=True)
+    assert rel(o, out) < 5e-5 and rel(aux, y2) < 5e-5
+    dz_img = ops.pack_act(dev(dz), rows=T, cols=C, mn_major=False)
+    w1cb, _ = ops.pack_weight(dev(w1), transposed=False, tile=cb)
+    w2gt, _ = ops.pack_weight(dev(w2) * dev(gamma)[:, None], transposed=True, tile=cb)
+    w1tn, _ = ops.pack_weight(dev(w1), transposed=True, tile=C)
+    dw1, dw2, db1 = torch.zeros(4 * C, C, device='cuda'), torch.zeros(C, 4 * C, device='cuda'), torch.zeros(4 * C, device='cuda')
+    dv = ops.ffn_fused_bwd_all(v_img, dz_img, w1cb, w2gt, w1tn, dev(b1), dev(gamma), dw1, dw2, db1, T=T, C=C, chunk=cb)
+    assert rel(dv, v.grad) < 1e-4
+    assert rel(dw1, w1.grad) < 1e-4 and rel(dw2, w2.grad) < 1e-4 and rel(db1, b1.grad) < 1e-4
