@@ -26,6 +26,10 @@ build/ffn_test: tests/cuda/ffn_test.cu $(SRC)/ffn_fused.cu $(SRC)/gemm_tc.cu $(S
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -I $(SRC) tests/cuda/ffn_test.cu $(SRC)/ffn_fused.cu $(SRC)/gemm_tc.cu $(SRC)/common.cu -o $@
 
+build/mma_bench: tests/cuda/mma_bench.cu $(SRC)/gemm_tc.cuh $(SRC)/common.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -I $(SRC) tests/cuda/mma_bench.cu $(SRC)/common.cu -o $@
+
 clean:
 	rm -rf build sm3det_b200/lib/*.so
 

@@ -130,6 +130,7 @@ typedef struct sm3_ffn_args {
   const float* resid;              /* [M,C] mode 0: shortcut (optional) */
   float* out;                      /* [M,C] modes 0, 1 */
   float* aux_out;                  /* [M,C] mode 0, optional */
+  float* h_out;                    /* [M,4C] mode 0, optional: hidden pre-activation, for the GEMM-based backward */
   float* dw1; float* dw2; float* db1;   /* mode 2: [4C,C], [C,4C], [4C]; accumulated, pre-zeroed by the caller */
   int32_t M, C, H4, chunk, mma_passes, mode;
 } sm3_ffn_args;

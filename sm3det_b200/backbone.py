@@ -184,14 +184,16 @@ class ConvNeXtBlock(nn.Module):
             w1, w2 = f.pointwise_conv1.weight, f.pointwise_conv2.weight
             C = w2.shape[0]
             cf, cb, cw = ops.ffn_chunk(0, C), ops.ffn_chunk(1, C), ops.ffn_chunk(2, C)
-            train_ok = cb > 0 and cb == cw
-            if cf > 0 and (train_ok or not grad):
-                # fused FFN kernels: weight images in the chunk widths they stream (csrc/ffn_fused.cu)
-                packs = {'fused': dict(fwd=cf, bwd=cb, train=train_ok),
+            trio = ops.FUSED_BWD and cb > 0 and cb == cw
+            if cf > 0:
+                # fused FFN forward: weight images in the chunk widths the kernel streams (csrc/ffn_fused.cu)
+                packs = {'fused': dict(fwd=cf, bwd=cb, trio=trio),
                          'w1_c': pc.get('w1', [w1], False, tile=cf), 'w2_n': pc.get('w2', [w2], False, tile=C)}
-                if grad:
+                if grad and trio:
                     packs['w1_cb'] = pc.get('w1', [w1], False, tile=cb)
                     packs['w1_tn'] = pc.get('w1', [w1], True, tile=C)
+                elif grad:
+                    packs['w1_t'] = pc.get('w1', [w1], True)
             else:
                 packs = {'w1': pc.get('w1', [w1], False), 'w2': pc.get('w2', [w2], False)}
                 if grad:

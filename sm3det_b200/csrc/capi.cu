@@ -77,7 +77,7 @@ int sm3_ffn_fused(const sm3_ffn_args* a, void* stream) {
   ffn::ChainParams p{};
   p.a1 = a->a1; p.a2 = a->a2; p.wa1 = a->wa1; p.wa2 = a->wa2; p.wb = a->wb;
   p.bias1 = a->bias1; p.bias2 = a->bias2; p.col_scale = a->col_scale; p.row_scale = a->row_scale; p.resid = a->resid;
-  p.out = a->out; p.aux_out = a->aux_out;
+  p.out = a->out; p.aux_out = a->aux_out; p.h_out = a->h_out;
   p.M = a->M; p.C = a->C; p.H4 = a->H4; p.HC = a->chunk; p.passes = a->mma_passes; p.mode = a->mode;
   return ffn::chain(p, S(stream));
 }

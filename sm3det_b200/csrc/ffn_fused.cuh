@@ -44,6 +44,7 @@ struct ChainParams {
   const float* resid;     // [M, C] or null (shortcut)
   float* out;             // [M, C]
   float* aux_out;         // [M, C] or null: acc_o + bias2 before scaling (y2, needed for dgamma)
+  float* h_out;           // MODE 0: [M, H4] or null: hidden pre-activation A1 Wa1^T + b1 (saved for a GEMM-based backward)
   int M, C, H4, HC, passes, mode;
   int debug;              // perf experiments only: bit0 = middle stage skips the GELU math, bit1 = skip the operand split/stores
 };

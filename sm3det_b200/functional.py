@@ -158,9 +158,11 @@ def _block_front_bwd(dv, dout, x, u, stats, dww, lnw):
 
 @ops.captures_precision
 class DenseBlockFn(Function):
-    """Dense ConvNeXt block.  Narrow stages (ops.ffn_chunk: C <= 96 for training, <= 192 for inference) run the FFN as the
-    fused tcgen05 kernels of csrc/ffn_fused.cu -- the [T,4C] hidden tensor is never written to HBM and the backward
-    recomputes it; wider stages keep the GEMM -> act_pack -> GEMM sequence."""
+    """Dense ConvNeXt block.  Narrow stages (ops.ffn_chunk: C <= 192) run the FFN forward as the fused tcgen05 kernel of
+    csrc/ffn_fused.cu (GEMM1 -> GELU -> GEMM2 on chip; the hidden tensor is written once, as fp32 h, only when a backward
+    follows).  The backward is the GEMM sequence (dgrad2 -> act_pack -> wgrads / dgrad1) or, with SM3_FUSED_BWD=1 and
+    C <= 96, the fused recompute kernels (nothing hidden-sized saved at all; slower today: the narrow MMAs are paced by
+    the 64-byte/clk operand fetch, profiles/r02_mma_microbench.txt).  Wider stages keep GEMM -> act_pack -> GEMM."""
 
     @staticmethod
     def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps, packs):
@@ -170,15 +172,22 @@ class DenseBlockFn(Function):
         # says whether a backward can follow (it also chose which weight images to provide on that basis)
         train = any(ctx.needs_input_grad) and packs.get('grad', True)
         fused = packs.get('fused')
-        if fused is not None and (not train or fused['train']):
-            # LayerNorm writes the FFN's A-operand image directly: fp32 v and the separate split pass never exist
+        if fused is not None:
+            # LayerNorm writes the FFN's A-operand image directly: the separate split pass never exists
             u = ops.dwconv7(x, _taps(dww), dwb)
-            v_img, _, stats = ops.layernorm_fwd_img(u, lnw, lnb, eps, tokens=T, C=C, save_stats=train)
-            out, y2 = ops.ffn_fused_fwd(v_img, packs['w1_c'][0], packs['w2_n'][0], b1, b2, T=T, C=C, chunk=fused['fwd'],
-                                        gamma=gamma, row_scale=row_scale, resid=x.view(T, C), want_aux=train)
-            if train:
-                ctx.fused = fused
+            trio = train and fused['trio']
+            v_img, v, stats = ops.layernorm_fwd_img(u, lnw, lnb, eps, tokens=T, C=C, save_stats=train, want_f32=train and not trio)
+            res = ops.ffn_fused_fwd(v_img, packs['w1_c'][0], packs['w2_n'][0], b1, b2, T=T, C=C, chunk=fused['fwd'],
+                                    gamma=gamma, row_scale=row_scale, resid=x.view(T, C), want_aux=train, want_h=train and not trio)
+            out, y2 = res[0], res[1]
+            ctx.fused = fused if trio else None
+            if trio:
+                # nothing hidden-sized is saved: the backward kernels recompute h from the operand image of v
                 ctx.save_for_backward(x, u, stats, v_img, y2, dww, lnw, w1, b1, w2, gamma, row_scale)
+                ctx.packs = packs
+            elif train:
+                # h (pre-activation) was stored once by the fused forward; the backward is the GEMM sequence below
+                ctx.save_for_backward(x, u, stats, v, res[2], y2, dww, lnw, w1, w2, gamma, row_scale)
                 ctx.packs = packs
             return out.view(N, H, W, C)
         ctx.fused = None

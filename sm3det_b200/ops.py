@@ -168,6 +168,8 @@ ACT_GELU, ACT_DGELU, ACT_COPY, ACT_BWD = 0, 1, 2, 3
 
 # ---- fused dense FFN (narrow stages): the [T,4C] hidden tensor never leaves the SM --------------------------------------
 FFN_FWD, FFN_BWD_DX, FFN_WGRAD = 0, 1, 2
+import os as _os2
+FUSED_BWD = _os2.environ.get('SM3_FUSED_BWD', '0') == '1'   # fused recompute backward (C <= 96); default: GEMM backward
 
 
 def ffn_chunk(mode: int, C: int) -> int:
@@ -188,16 +190,19 @@ def _ffn_args(*, T, C, chunk, mode, a1, wa1, b1, a2=None, wa2=None, wb=None):
     return a
 
 
-def ffn_fused_fwd(v_img, w1_img, w2_img, b1, b2, *, T, C, chunk, gamma=None, row_scale=None, resid=None, want_aux=False):
-    """out[T,C] = resid + row_scale * gamma * (gelu(v W1^T + b1) W2^T + b2); aux = the value before gamma (y2)."""
+def ffn_fused_fwd(v_img, w1_img, w2_img, b1, b2, *, T, C, chunk, gamma=None, row_scale=None, resid=None, want_aux=False,
+                  want_h=False):
+    """out[T,C] = resid + row_scale * gamma * (gelu(v W1^T + b1) W2^T + b2); aux = the value before gamma (y2);
+    want_h: also return the hidden pre-activation h [T,4C] (-> (out, aux, h))."""
     lib = _lib.load()
     out = torch.empty((T, C), device=b1.device, dtype=torch.float32)
     aux = torch.empty((T, C), device=b1.device, dtype=torch.float32) if want_aux else None
+    h = torch.empty((T, 4 * C), device=b1.device, dtype=torch.float32) if want_h else None
     a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_FWD, a1=v_img, wa1=w1_img, b1=b1, wb=w2_img)
     a.bias2 = _p(b2); a.col_scale = _p(gamma); a.row_scale = _p(row_scale); a.resid = _p(resid)
-    a.out = _p(out); a.aux_out = _p(aux)
+    a.out = _p(out); a.aux_out = _p(aux); a.h_out = _p(h)
     _lib.check(lib.sm3_ffn_fused(_ct.byref(a), _stream()), 'sm3_ffn_fused(fwd)')
-    return out, aux
+    return (out, aux, h) if want_h else (out, aux)
 
 
 def ffn_fused_bwd(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, *, T, C, chunk):

@@ -47,9 +47,32 @@ __global__ void scale_rows_k(const float* w, const float* g, float* o, int C, in
   if (i < (long long)C * H4) o[i] = w[i] * g[i / H4];
 }
 
+static int g_cols = 0;     // row length of the tensor being compared (for the non-finite pattern dump)
 static double maxrel(const std::vector<float>& got, const std::vector<double>& ref) {
   double mx = 0, sc = 0;
-  for (size_t i = 0; i < ref.size(); ++i) { mx = std::max(mx, fabs((double)got[i] - ref[i])); sc = std::max(sc, fabs(ref[i])); }
+  size_t bad = 0;
+  std::vector<int> by_col_mod8(8, 0);
+  long long rmin = 1LL << 60, rmax = -1;
+  std::vector<char> colhit(g_cols > 0 ? g_cols : 1, 0);
+  for (size_t i = 0; i < ref.size(); ++i) {
+    if (!std::isfinite(got[i])) {
+      if (bad++ < 3) printf("    non-finite value %g at flat index %zu (of %zu)\n", got[i], i, ref.size());
+      if (g_cols > 0) { const long long r = i / g_cols; const int c = (int)(i % g_cols); by_col_mod8[c % 8]++; colhit[c] = 1; rmin = std::min(rmin, r); rmax = std::max(rmax, r); }
+      continue;
+    }
+    mx = std::max(mx, fabs((double)got[i] - ref[i])); sc = std::max(sc, fabs(ref[i]));
+  }
+  if (bad) {
+    printf("    %zu non-finite values", bad);
+    if (g_cols > 0) {
+      printf("; rows %lld..%lld; by (col %% 8):", rmin, rmax);
+      for (int m = 0; m < 8; ++m) printf(" %d", by_col_mod8[m]);
+      printf("; columns hit:");
+      for (int c = 0; c < g_cols; ++c) if (colhit[c]) printf(" %d", c);
+    }
+    printf("\n");
+    return 1e30;
+  }
   return mx / (sc + 1e-30);
 }
 
@@ -158,6 +181,7 @@ static void check(int M, int C, bool with_rs) {
       p.bias1 = db1; p.gamma = dgm;
       float* gw1 = dalloc<float>((size_t)H4 * C); float* gw2 = dalloc<float>((size_t)C * H4); float* gb1 = dalloc<float>(H4);
       p.dw1 = gw1; p.dw2 = gw2; p.db1 = gb1; p.M = M; p.C = C; p.H4 = H4; p.HC = HC; p.passes = 3;
+      p.debug = getenv("SM3_WDEBUG") ? atoi(getenv("SM3_WDEBUG")) : 0;
       const int rc = ffn::wgrad(p, 0);
       cudaError_t e = cudaDeviceSynchronize();
       if (rc != 0 || e != cudaSuccess) { printf("wgrd M=%-6d C=%-4d LAUNCH FAILED rc=%d %s %s\n", M, C, rc, last_error(), cudaGetErrorString(e)); g_fail++; exit(3); }
@@ -165,7 +189,7 @@ static void check(int M, int C, bool with_rs) {
       CK(cudaMemcpy(h1.data(), gw1, h1.size() * 4, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(h2.data(), gw2, h2.size() * 4, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(hb.data(), gb1, hb.size() * 4, cudaMemcpyDeviceToHost));
-      const double e1 = maxrel(h1, rdw1), e2 = maxrel(h2, rdw2), e3 = maxrel(hb, rdb1);
+      g_cols = C; const double e1 = maxrel(h1, rdw1); g_cols = H4; const double e2 = maxrel(h2, rdw2); g_cols = 32; const double e3 = maxrel(hb, rdb1); g_cols = 0;
       const bool ok = e1 < 2e-4 && e2 < 2e-4 && e3 < 2e-4;
       printf("wgrd M=%-6d C=%-4d chunk=%d        dw1 err %.2e  dw2 err %.2e  db1 err %.2e  %s\n", M, C, HC, e1, e2, e3, ok ? "ok" : "FAIL");
       if (!ok) g_fail++;
@@ -220,6 +244,7 @@ int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "all";
   if (argc > 2) g_passes = atoi(argv[2]);
   if (argc > 3) g_debug = atoi(argv[3]);
+  if (what == "check640") { check(640, 96, true); printf(g_fail ? "FAILED\n" : "PASSED\n"); return g_fail; }
   if (what == "one") { printf("passes=%d debug=%d\n", g_passes, g_debug); timeit(524288, 96); return 0; }
   if (what == "check" || what == "all") {
     check(128, 96, false);
