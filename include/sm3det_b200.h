@@ -108,30 +108,28 @@ int sm3_gemm_pack_b_tile(const float* B, int64_t stride_mn, int64_t stride_k, in
  * it exists so that callers can size allocations uniformly through the C ABI. */
 size_t sm3_gemm_workspace_bytes(const sm3_gemm_args* args);
 
-/* ---- fused dense FFN for the narrow stages (C <= 192 forward, C <= 128 backward into dv, C <= 96 weight gradients) ------
- * The [M, 4C] hidden tensor never leaves the SM (GEMM1 -> +b1 -> GELU -> bf16 hi/lo split -> shared memory -> GEMM2 with
- * the accumulators in TMEM); the backward RECOMPUTES the hidden pre-activation instead of loading a saved copy.
- * Replaces FFN.forward (convnext_moe.py:397-405) + layer scale / drop-path / shortcut (:367-370) and autograd's backward
- * of them for dense ConvNeXt blocks.
- *   mode 0 (forward)     out = resid + row_scale * col_scale * (gelu(A1 Wa1^T + b1) Wb^T + bias2);  aux_out = pre-scale value
+/* ---- fused dense FFN for the narrow stages (C <= 192 forward, C <= 128 backward into dv) ------------------------------
+ * The [M, 4C] hidden tensor is produced and consumed on chip (GEMM1 -> +b1 -> GELU -> bf16 hi/lo split -> shared memory ->
+ * GEMM2 with the accumulators in TMEM).  Replaces FFN.forward (convnext_moe.py:397-405) + layer scale / drop-path /
+ * shortcut (:367-370) of dense ConvNeXt blocks.
+ *   mode 0 (forward)     out = resid + row_scale * col_scale * (gelu(A1 Wa1^T + b1) Wb^T + bias2);  aux_out = pre-scale value;
+ *                        h_out (optional) = A1 Wa1^T + b1, stored once for the GEMM-based backward
  *                        A1 = v, Wa1 = W1 [4C,C], Wb = W2 [C,4C]
- *   mode 1 (backward dv) out = ((A2 Wa2^T) * gelu'(A1 Wa1^T + b1)) Wb^T
+ *   mode 1 (backward dv) out = ((A2 Wa2^T) * gelu'(A1 Wa1^T + b1)) Wb^T      (the hidden pre-activation is recomputed)
  *                        A1 = v, A2 = dz, Wa1 = W1, Wa2 = (gamma W2)^T stored [4C,C], Wb = W1^T stored [C,4C]
- *   mode 2 (weight grads) dw1 += dh^T v, dw2 += gamma * dz^T gelu(h), db1 += sum dh   (h, dh recomputed as in mode 1)
- * a1 / a2: K-major images from sm3_gemm_pack_act(tile 128); wa1 / wa2: sm3_gemm_pack_b_tile(tile = chunk) of the [4C,C]
- * matrices; wb: sm3_gemm_pack_b_tile(tile = C) of the [C,4C] matrix; chunk = sm3_ffn_fused_chunk(mode, C). */
+ * a1 / a2: K-major images from sm3_gemm_pack_act(tile 128) or sm3_layernorm_fwd_img; wa1 / wa2: sm3_gemm_pack_b_tile(tile =
+ * chunk) of the [4C,C] matrices; wb: sm3_gemm_pack_b_tile(tile = C) of the [C,4C] matrix; chunk = sm3_ffn_fused_chunk(mode, C). */
 typedef struct sm3_ffn_args {
   const uint16_t* a1; const uint16_t* a2;
   const uint16_t* wa1; const uint16_t* wa2; const uint16_t* wb;
   const float* bias1;              /* [4C] */
   const float* bias2;              /* [C]  mode 0 */
-  const float* col_scale;          /* [C]  mode 0: gamma (optional); mode 2: gamma (required) */
+  const float* col_scale;          /* [C]  mode 0: gamma (optional) */
   const float* row_scale;          /* [M]  mode 0: drop-path scale (optional) */
   const float* resid;              /* [M,C] mode 0: shortcut (optional) */
   float* out;                      /* [M,C] modes 0, 1 */
   float* aux_out;                  /* [M,C] mode 0, optional */
   float* h_out;                    /* [M,4C] mode 0, optional: hidden pre-activation, for the GEMM-based backward */
-  float* dw1; float* dw2; float* db1;   /* mode 2: [4C,C], [C,4C], [4C]; accumulated, pre-zeroed by the caller */
   int32_t M, C, H4, chunk, mma_passes, mode;
 } sm3_ffn_args;
 int32_t sm3_ffn_fused_chunk(int32_t mode, int32_t C);   /* hidden chunk width for (mode, C); 0 = shape not supported */

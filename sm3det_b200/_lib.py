@@ -61,7 +61,7 @@ class FfnArgs(C.Structure):
     _fields_ = [
         ('a1', C.c_void_p), ('a2', C.c_void_p), ('wa1', C.c_void_p), ('wa2', C.c_void_p), ('wb', C.c_void_p),
         ('bias1', c_f32p), ('bias2', c_f32p), ('col_scale', c_f32p), ('row_scale', c_f32p), ('resid', c_f32p),
-        ('out', c_f32p), ('aux_out', c_f32p), ('h_out', c_f32p), ('dw1', c_f32p), ('dw2', c_f32p), ('db1', c_f32p),
+        ('out', c_f32p), ('aux_out', c_f32p), ('h_out', c_f32p),
         ('M', C.c_int32), ('C', C.c_int32), ('H4', C.c_int32), ('chunk', C.c_int32), ('mma_passes', C.c_int32),
         ('mode', C.c_int32),
     ]

@@ -183,21 +183,14 @@ class ConvNeXtBlock(nn.Module):
             f = self.ffn
             w1, w2 = f.pointwise_conv1.weight, f.pointwise_conv2.weight
             C = w2.shape[0]
-            cf, cb, cw = ops.ffn_chunk(0, C), ops.ffn_chunk(1, C), ops.ffn_chunk(2, C)
-            trio = ops.FUSED_BWD and cb > 0 and cb == cw
+            cf = ops.ffn_chunk(0, C)
             if cf > 0:
                 # fused FFN forward: weight images in the chunk widths the kernel streams (csrc/ffn_fused.cu)
-                packs = {'fused': dict(fwd=cf, bwd=cb, trio=trio),
-                         'w1_c': pc.get('w1', [w1], False, tile=cf), 'w2_n': pc.get('w2', [w2], False, tile=C)}
-                if grad and trio:
-                    packs['w1_cb'] = pc.get('w1', [w1], False, tile=cb)
-                    packs['w1_tn'] = pc.get('w1', [w1], True, tile=C)
-                elif grad:
-                    packs['w1_t'] = pc.get('w1', [w1], True)
+                packs = {'fused': dict(fwd=cf), 'w1_c': pc.get('w1', [w1], False, tile=cf), 'w2_n': pc.get('w2', [w2], False, tile=C)}
             else:
                 packs = {'w1': pc.get('w1', [w1], False), 'w2': pc.get('w2', [w2], False)}
-                if grad:
-                    packs['w1_t'] = pc.get('w1', [w1], True)
+            if grad:
+                packs['w1_t'] = pc.get('w1', [w1], True)
             packs['grad'] = grad
             out = Fn.DenseBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias,
                                         w1, f.pointwise_conv1.bias, w2, f.pointwise_conv2.bias, self.gamma, rs, eps, packs)

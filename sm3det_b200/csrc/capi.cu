@@ -63,17 +63,10 @@ int sm3_gemm_pack_b_tile(const float* B, int64_t s_mn, int64_t s_k, int64_t grou
 }
 size_t sm3_gemm_workspace_bytes(const sm3_gemm_args*) { return 0; }
 
-int32_t sm3_ffn_fused_chunk(int32_t mode, int32_t C) { return mode == 2 ? ffn::wgrad_chunk(C) : ffn::chain_chunk(mode, C); }
+int32_t sm3_ffn_fused_chunk(int32_t mode, int32_t C) { return (mode == 0 || mode == 1) ? ffn::chain_chunk(mode, C) : 0; }
 size_t sm3_ffn_fused_workspace_bytes(const sm3_ffn_args*) { return 0; }
 int sm3_ffn_fused(const sm3_ffn_args* a, void* stream) {
   if (!a) { set_last_error("sm3_ffn_fused: null args"); return SM3_ERR_INVALID_ARG; }
-  if (a->mode == 2) {
-    ffn::WgradParams p{};
-    p.a1 = a->a1; p.a2 = a->a2; p.wa1 = a->wa1; p.wa2 = a->wa2; p.bias1 = a->bias1; p.gamma = a->col_scale;
-    p.dw1 = a->dw1; p.dw2 = a->dw2; p.db1 = a->db1;
-    p.M = a->M; p.C = a->C; p.H4 = a->H4; p.HC = a->chunk; p.passes = a->mma_passes;
-    return ffn::wgrad(p, S(stream));
-  }
   ffn::ChainParams p{};
   p.a1 = a->a1; p.a2 = a->a2; p.wa1 = a->wa1; p.wa2 = a->wa2; p.wb = a->wb;
   p.bias1 = a->bias1; p.bias2 = a->bias2; p.col_scale = a->col_scale; p.row_scale = a->row_scale; p.resid = a->resid;

@@ -17,12 +17,10 @@
 //      RECOMPUTED, A2 = dz, Wa1 = W1, Wa2 = (gamma W2)^T, Wb = W1^T) -- the tensor pipe has >2x slack on these shapes,
 //      HBM does not, so nothing hidden-sized is saved by the forward at all.
 //
-//   ffn_wgrad_kernel<HC>            weight gradients, hidden slice [hb, hb+HW) per CTA, token tiles streamed:
-//        recompute acc_h / acc_d as above;  middle: dh = acc_d * gelu'(.), a = gelu(.) -> two smem operand blocks;
-//        accW1[c, hid] += v^T dh,  accW2[c, hid] += dz^T a   (the SAME smem images serve as K-major and MN-major operands:
-//        a [128 x 32] SWIZZLE_64B block is both), accumulated in TMEM over all the CTA's token tiles, flushed once with
-//        fp32 reductions:  dW1[hid, c] += accW1[c, hid],  dW2[c, hid] += gamma_c accW2[c, hid],  db1[hid] += accW1[C, hid]
-//        (the bias gradient rides on the tensor cores: a constant "ones" channel appended to v, when C < 128).
+// Not fused (measured, profiles/r02_mma_microbench.txt + r02_ffn_fused_timing.txt): the weight gradients.  A kernel that
+// recomputed h / dh per hidden slice and accumulated dW1, dW2, db1 in TMEM was written and measured at 1.9 ms per stage-0
+// block (vs ~0.4 ms for the two split-K GEMMs it would replace): with M = 128, K = 16 every tcgen05.mma costs >= 64-88 cycles
+// for its 4 KB A-operand fetch regardless of N, so N = 32..96 MMAs run the tensor pipe at 18-55 %.  It was removed.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -50,24 +48,8 @@ struct ChainParams {
 };
 int chain(const ChainParams& p, cudaStream_t stream);
 
-struct WgradParams {
-  const uint16_t* a1;     // K-major image of v  [M, C]
-  const uint16_t* a2;     // K-major image of dz [M, C]
-  const uint16_t* wa1;    // image of W1 [H4, C], tile width HC
-  const uint16_t* wa2;    // image of (gamma W2)^T [H4, C], tile width HC
-  const float* bias1;     // [H4]
-  const float* gamma;     // [C]: dW2 rows are scaled by it (dz already carries drop-path)
-  float* dw1;             // [H4, C]  accumulated (pre-zeroed)
-  float* dw2;             // [C, H4]  accumulated
-  float* db1;             // [H4]     accumulated
-  int M, C, H4, HC, passes;
-  int debug;
-};
-int wgrad(const WgradParams& p, cudaStream_t stream);
-
 // largest hidden chunk the shared-memory budget allows for (mode, C); 0 if the shape is unsupported
 int chain_chunk(int mode, int C);
-int wgrad_chunk(int C);
 
 }  // namespace ffn
 }  // namespace sm3

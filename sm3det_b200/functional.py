@@ -160,9 +160,9 @@ def _block_front_bwd(dv, dout, x, u, stats, dww, lnw):
 class DenseBlockFn(Function):
     """Dense ConvNeXt block.  Narrow stages (ops.ffn_chunk: C <= 192) run the FFN forward as the fused tcgen05 kernel of
     csrc/ffn_fused.cu (GEMM1 -> GELU -> GEMM2 on chip; the hidden tensor is written once, as fp32 h, only when a backward
-    follows).  The backward is the GEMM sequence (dgrad2 -> act_pack -> wgrads / dgrad1) or, with SM3_FUSED_BWD=1 and
-    C <= 96, the fused recompute kernels (nothing hidden-sized saved at all; slower today: the narrow MMAs are paced by
-    the 64-byte/clk operand fetch, profiles/r02_mma_microbench.txt).  Wider stages keep GEMM -> act_pack -> GEMM."""
+    follows).  The backward is the GEMM sequence (dgrad2 -> act_pack -> wgrads / dgrad1): fused recompute kernels for it
+    were built and measured slower (narrow tcgen05 MMAs are paced by the 64-byte/clk operand fetch, not by N --
+    profiles/r02_mma_microbench.txt).  Wider stages keep GEMM -> act_pack -> GEMM."""
 
     @staticmethod
     def forward(ctx, x, dww, dwb, lnw, lnb, w1, b1, w2, b2, gamma, row_scale, eps, packs):
@@ -173,24 +173,16 @@ class DenseBlockFn(Function):
         train = any(ctx.needs_input_grad) and packs.get('grad', True)
         fused = packs.get('fused')
         if fused is not None:
-            # LayerNorm writes the FFN's A-operand image directly: the separate split pass never exists
+            # LayerNorm writes the FFN's A-operand image directly (the separate split pass never exists); the fused kernel
+            # keeps the hidden tensor on chip and, when a backward follows, stores the pre-activation h once for it
             u = ops.dwconv7(x, _taps(dww), dwb)
-            trio = train and fused['trio']
-            v_img, v, stats = ops.layernorm_fwd_img(u, lnw, lnb, eps, tokens=T, C=C, save_stats=train, want_f32=train and not trio)
+            v_img, v, stats = ops.layernorm_fwd_img(u, lnw, lnb, eps, tokens=T, C=C, save_stats=train, want_f32=train)
             res = ops.ffn_fused_fwd(v_img, packs['w1_c'][0], packs['w2_n'][0], b1, b2, T=T, C=C, chunk=fused['fwd'],
-                                    gamma=gamma, row_scale=row_scale, resid=x.view(T, C), want_aux=train, want_h=train and not trio)
-            out, y2 = res[0], res[1]
-            ctx.fused = fused if trio else None
-            if trio:
-                # nothing hidden-sized is saved: the backward kernels recompute h from the operand image of v
-                ctx.save_for_backward(x, u, stats, v_img, y2, dww, lnw, w1, b1, w2, gamma, row_scale)
+                                    gamma=gamma, row_scale=row_scale, resid=x.view(T, C), want_aux=train, want_h=train)
+            if train:
+                ctx.save_for_backward(x, u, stats, v, res[2], res[1], dww, lnw, w1, w2, gamma, row_scale)
                 ctx.packs = packs
-            elif train:
-                # h (pre-activation) was stored once by the fused forward; the backward is the GEMM sequence below
-                ctx.save_for_backward(x, u, stats, v, res[2], y2, dww, lnw, w1, w2, gamma, row_scale)
-                ctx.packs = packs
-            return out.view(N, H, W, C)
-        ctx.fused = None
+            return res[0].view(N, H, W, C)
         u, v, stats = _block_front(x, dww, dwb, lnw, lnb, eps, train)
         # GEMM1 stores the pre-activation only; GELU runs in the HBM-bound act_pack kernel, which emits the result
         # directly as GEMM2's pre-split A operand (fp32 `a` never exists)
@@ -207,8 +199,6 @@ class DenseBlockFn(Function):
 
     @staticmethod
     def backward(ctx, dout):
-        if ctx.fused is not None:
-            return DenseBlockFn._backward_fused(ctx, dout)
         x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, rs = ctx.saved_tensors
         N, H, W, C = x.shape
         T = N * H * W
@@ -239,37 +229,6 @@ class DenseBlockFn(Function):
         dw1 = torch.zeros_like(w1)
         ops.linear_wgrad(None, v, dw1, rows=T, dy_packed=dh_mn)
         dv = ops.linear_dgrad(None, w1, rows=T, a_packed=dh_k, packed=ctx.packs.get('w1_t'))
-        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
-        return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
-
-    @staticmethod
-    def _backward_fused(ctx, dout):
-        """Appendix F steps 1-3 with nothing hidden-sized in HBM: dz' = drop-path-scaled dout is split once into its
-        operand image; one fused kernel gives dv (dgrad2 -> gelu' -> dgrad1), a second one dW1, dW2, db1."""
-        x, u, stats, v_img, y2, dww, lnw, w1, b1, w2, gamma, rs = ctx.saved_tensors
-        N, H, W, C = x.shape
-        T = N * H * W
-        dout = dout.contiguous()
-        dz = dout.view(T, C)
-        dev = x.device
-        f = ctx.fused
-        if rs is None:
-            csum, dgamma = ops.colstat(dz, rows=T, Cc=C, y=y2)            # one pass: sum dz and sum dz * y2
-            dzs = dz
-        else:
-            dgamma = torch.zeros((C,), device=dev, dtype=torch.float32)
-            ops.colsum(dz, dgamma, rows=T, Cc=C, b=y2, row_scale=rs)
-            csum = torch.zeros((C,), device=dev, dtype=torch.float32)
-            ops.colsum(dz, csum, rows=T, Cc=C, row_scale=rs)
-            dzs = ops.scale_rows(dz, row_scale=rs)
-        db2 = csum * gamma
-        dz_img = ops.pack_act(dzs, rows=T, cols=C, mn_major=False)
-        w2g = ops.scale_rows(w2, row_scale=gamma)                   # gamma[c] * W2[c, :]
-        w2gt_img, _ = ops.pack_weight(w2g, transposed=True, tile=f['bwd'])
-        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
-        db1 = torch.zeros((4 * C,), device=dev, dtype=torch.float32)
-        dv = ops.ffn_fused_bwd_all(v_img, dz_img, ctx.packs['w1_cb'][0], w2gt_img, ctx.packs['w1_tn'][0], b1, gamma, dw1, dw2, db1,
-                                   T=T, C=C, chunk=f['bwd'])
         dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
         return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
 

@@ -167,9 +167,7 @@ ACT_GELU, ACT_DGELU, ACT_COPY, ACT_BWD = 0, 1, 2, 3
 
 
 # ---- fused dense FFN (narrow stages): the [T,4C] hidden tensor never leaves the SM --------------------------------------
-FFN_FWD, FFN_BWD_DX, FFN_WGRAD = 0, 1, 2
-import os as _os2
-FUSED_BWD = _os2.environ.get('SM3_FUSED_BWD', '0') == '1'   # fused recompute backward (C <= 96); default: GEMM backward
+FFN_FWD, FFN_BWD_DX = 0, 1
 
 
 def ffn_chunk(mode: int, C: int) -> int:
@@ -215,20 +213,6 @@ def ffn_fused_bwd(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, *, T, C, chunk):
     return out
 
 
-def ffn_fused_wgrad(v_img, dz_img, w1_img, w2gt_img, b1, gamma, dw1, dw2, db1, *, T, C, chunk):
-    """dw1 += dh^T v, dw2 += gamma * dz^T gelu(h), db1 += colsum(dh)  (accumulating; h, dh recomputed on chip)."""
-    lib = _lib.load()
-    a = _ffn_args(T=T, C=C, chunk=chunk, mode=FFN_WGRAD, a1=v_img, a2=dz_img, wa1=w1_img, wa2=w2gt_img, b1=b1)
-    a.col_scale = _p(gamma); a.dw1 = _p(dw1); a.dw2 = _p(dw2); a.db1 = _p(db1)
-    _lib.check(lib.sm3_ffn_fused(_ct.byref(a), _stream()), 'sm3_ffn_fused(wgrad)')
-
-
-def ffn_fused_bwd_all(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, gamma, dw1, dw2, db1, *, T, C, chunk):
-    dv = ffn_fused_bwd(v_img, dz_img, w1_img, w2gt_img, w1t_img, b1, T=T, C=C, chunk=chunk)
-    ffn_fused_wgrad(v_img, dz_img, w1_img, w2gt_img, b1, gamma, dw1, dw2, db1, T=T, C=C, chunk=chunk)
-    return dv
-
-
 def fused_cost(name, *a, **kw):
     """(algorithmic FLOPs, algorithmic HBM bytes, shape) of a fused-FFN call, for bench.py's roofline (recomputation of the
     hidden pre-activation is NOT counted: FLOPs are those of the GEMMs the algorithm needs)."""
@@ -236,8 +220,8 @@ def fused_cost(name, *a, **kw):
     unit = 2.0 * T * Cc * 4 * Cc
     wbytes = 2 * 4.0 * 4 * Cc * Cc
     if name == 'ffn_fused_fwd':
-        return 2 * unit, (3 + (1 if kw.get('want_aux') else 0)) * 4.0 * T * Cc + wbytes, (T, Cc, 'fwd')
-    return 4 * unit, 3 * 4.0 * T * Cc + 2 * wbytes, (T, Cc, 'bwd')
+        return 2 * unit, (3 + (1 if kw.get('want_aux') else 0) + (4 if kw.get('want_h') else 0)) * 4.0 * T * Cc + wbytes, (T, Cc, 'fwd')
+    return 2 * unit, 3 * 4.0 * T * Cc + 2 * wbytes, (T, Cc, 'bwd-dv')
 
 
 def act_pack(h, *, rows, width, mode, da=None, want_k=False, mn_tile=0, want_f32=False, colsum=None, live_tiles=None,

@@ -171,30 +171,6 @@ static void check(int M, int C, bool with_rs) {
       if (!ok) g_fail++;
     }
   }
-  // ---------------- weight gradients ----------------
-  {
-    const int HC = ffn::wgrad_chunk(C);
-    if (HC == 0) { printf("wgrd M=%-6d C=%-4d unsupported\n", M, C); }
-    else {
-      ffn::WgradParams p{};
-      p.a1 = v_img; p.a2 = dz_img; p.wa1 = pack_w(dw1, C, 1, H4, C, HC); p.wa2 = pack_w(dw2g, 1, H4, H4, C, HC);
-      p.bias1 = db1; p.gamma = dgm;
-      float* gw1 = dalloc<float>((size_t)H4 * C); float* gw2 = dalloc<float>((size_t)C * H4); float* gb1 = dalloc<float>(H4);
-      p.dw1 = gw1; p.dw2 = gw2; p.db1 = gb1; p.M = M; p.C = C; p.H4 = H4; p.HC = HC; p.passes = 3;
-      p.debug = getenv("SM3_WDEBUG") ? atoi(getenv("SM3_WDEBUG")) : 0;
-      const int rc = ffn::wgrad(p, 0);
-      cudaError_t e = cudaDeviceSynchronize();
-      if (rc != 0 || e != cudaSuccess) { printf("wgrd M=%-6d C=%-4d LAUNCH FAILED rc=%d %s %s\n", M, C, rc, last_error(), cudaGetErrorString(e)); g_fail++; exit(3); }
-      std::vector<float> h1((size_t)H4 * C), h2((size_t)C * H4), hb(H4);
-      CK(cudaMemcpy(h1.data(), gw1, h1.size() * 4, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(h2.data(), gw2, h2.size() * 4, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(hb.data(), gb1, hb.size() * 4, cudaMemcpyDeviceToHost));
-      g_cols = C; const double e1 = maxrel(h1, rdw1); g_cols = H4; const double e2 = maxrel(h2, rdw2); g_cols = 32; const double e3 = maxrel(hb, rdb1); g_cols = 0;
-      const bool ok = e1 < 2e-4 && e2 < 2e-4 && e3 < 2e-4;
-      printf("wgrd M=%-6d C=%-4d chunk=%d        dw1 err %.2e  dw2 err %.2e  db1 err %.2e  %s\n", M, C, HC, e1, e2, e3, ok ? "ok" : "FAIL");
-      if (!ok) g_fail++;
-    }
-  }
 }
 
 static int g_passes = 3, g_debug = 0;
@@ -208,22 +184,18 @@ static void timeit(int M, int C) {
   float* dout = dalloc<float>((size_t)M * C); float* daux = dalloc<float>((size_t)M * C);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const double unit = 2.0 * M * C * (double)H4;     // FLOPs of one [M,C]x[C,4C] GEMM
-  for (int mode = 0; mode < 3; ++mode) {
-    const int HC = mode == 2 ? ffn::wgrad_chunk(C) : ffn::chain_chunk(mode, C);
+  for (int mode = 0; mode < 2; ++mode) {
+    const int HC = ffn::chain_chunk(mode, C);
     if (HC == 0) { printf("time mode %d M=%d C=%d: unsupported\n", mode, M, C); continue; }
-    ffn::ChainParams p{}; ffn::WgradParams q{};
+    ffn::ChainParams p{};
     uint16_t* wa1 = pack_w(dw1, C, 1, H4, C, HC); uint16_t* wa2 = pack_w(dw2, 1, H4, H4, C, HC);
-    float* gw1 = dalloc<float>((size_t)H4 * C); float* gw2 = dalloc<float>((size_t)C * H4); float* gb1 = dalloc<float>(H4);
-    if (mode < 2) {
+    {
       p.a1 = v_img; p.a2 = dz_img; p.wa1 = wa1; p.wa2 = wa2;
       p.wb = mode == 0 ? pack_w(dw2, H4, 1, C, H4, C) : pack_w(dw1, 1, C, C, H4, C);
       p.bias1 = db1; p.bias2 = mode == 0 ? db2 : nullptr; p.col_scale = mode == 0 ? dgm : nullptr; p.resid = mode == 0 ? dx : nullptr;
       p.out = dout; p.aux_out = mode == 0 ? daux : nullptr; p.M = M; p.C = C; p.H4 = H4; p.HC = HC; p.passes = g_passes; p.mode = mode; p.debug = g_debug;
-    } else {
-      q.a1 = v_img; q.a2 = dz_img; q.wa1 = wa1; q.wa2 = wa2; q.bias1 = db1; q.gamma = dgm; q.dw1 = gw1; q.dw2 = gw2; q.db1 = gb1;
-      q.M = M; q.C = C; q.H4 = H4; q.HC = HC; q.passes = g_passes;
     }
-    auto launch = [&]() { return mode < 2 ? ffn::chain(p, 0) : ffn::wgrad(q, 0); };
+    auto launch = [&]() { return ffn::chain(p, 0); };
     for (int i = 0; i < 2; ++i) if (launch() != 0) { printf("launch failed: %s\n", last_error()); exit(3); }
     CK(cudaDeviceSynchronize());
     const int it = 10;
@@ -232,11 +204,11 @@ static void timeit(int M, int C) {
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= it;
-    const double alg = (mode == 0 ? 2 : mode == 1 ? 2 : 2) * unit;         // GEMMs the algorithm needs (recomputation not counted)
-    const double issued = (mode == 0 ? 2 : mode == 1 ? 3 : 4) * unit;
-    const double bytes = mode == 0 ? 4.0 * M * C * 4 : mode == 1 ? 3.0 * M * C * 4 : 2.0 * M * C * 4 * (H4 / 192);
+    const double alg = 2 * unit;                                           // GEMMs the algorithm needs (recomputation not counted)
+    const double issued = (mode == 0 ? 2 : 3) * unit;
+    const double bytes = mode == 0 ? 4.0 * M * C * 4 : 3.0 * M * C * 4;
     printf("time mode %d (%s) M=%d C=%d chunk=%d: %.3f ms  algorithmic %.1f TFLOP/s  issued %.1f TFLOP/s  min-HBM %.0f GB/s\n", mode,
-           mode == 0 ? "fwd" : mode == 1 ? "bwd-dv" : "wgrad", M, C, HC, ms, alg / ms * 1e-9, issued / ms * 1e-9, bytes / ms * 1e-6);
+           mode == 0 ? "fwd" : "bwd-dv", M, C, HC, ms, alg / ms * 1e-9, issued / ms * 1e-9, bytes / ms * 1e-6);
   }
 }
 

@@ -300,3 +300,34 @@ def test_fused_dropout(ops):
     y2 = ops.dropout(x.detach(), 0.1, 1235)
     assert (y2 != 0).ne(keep).float().mean().item() > 0.1            # a different seed gives a different mask
     assert torch.equal(ops.dropout(x.detach(), 0.0, 7), x.detach())
+
+
+@pytest.mark.parametrize('C,Co,H', [(64, 128, 8), (128, 128, 4), (64, 64, 16), (128, 128, 16)])
+@pytest.mark.parametrize('N', [2, 1])
+def test_stage_boundary_norm_output_feeds_next_patch_embed(ops, N, C, Co, H):
+    """lsk_moe.py:551-559: the per-stage LayerNorm output (NCHW) is BOTH a returned feature (its own loss term) and the
+    input of the next OverlapPatchEmbed (3x3/s2 conv + BatchNorm): two gradient contributions meet at one tensor.
+    Found at the real config-5 shapes (batch 1 per image): checked here for N = 1 and N = 2."""
+    from sm3det_b200 import functional as Fn
+    from sm3det_b200.lsk_functional import BatchNormFn, PatchEmbedFn
+    g = torch.Generator().manual_seed(5 + N)
+    W = H
+    x = torch.randn(N, H, W, C, generator=g, requires_grad=True)
+    lw = (torch.rand(C, generator=g) + 0.5).requires_grad_(True); lb = (torch.randn(C, generator=g) * 0.1).requires_grad_(True)
+    cw = (torch.randn(Co, C, 3, 3, generator=g) / (9 * C) ** 0.5).requires_grad_(True); cb = (torch.randn(Co, generator=g) * 0.1).requires_grad_(True)
+    bw = (torch.rand(Co, generator=g) + 0.5).requires_grad_(True); bb = (torch.randn(Co, generator=g) * 0.1).requires_grad_(True)
+    rm, rv = torch.randn(Co, generator=g) * 0.1, torch.rand(Co, generator=g) + 0.5
+    g1 = torch.randn(N, C, H, W, generator=g); g2 = torch.randn(N, Co, H // 2, W // 2, generator=g)
+    # torch reference
+    y = F.layer_norm(x, (C,), lw, lb, 1e-6).permute(0, 3, 1, 2).contiguous()
+    z = F.batch_norm(F.conv2d(y, cw, cb, stride=2, padding=1), rm.clone(), rv.clone(), bw, bb, True, 0.1, 1e-5)
+    ((y * g1).sum() + (z * g2).sum()).backward()
+    # CUDA path
+    d = lambda t: t.detach().cuda().requires_grad_(True)
+    xg, lwg, lbg, cwg, cbg, bwg, bbg = d(x), d(lw), d(lb), d(cw), d(cb), d(bw), d(bb)
+    yg = Fn.OutNormFn.apply(xg, lwg, lbg, 1e-6)
+    zg = BatchNormFn.apply(PatchEmbedFn.apply(yg, cwg, cbg, 2, True), bwg, bbg, rm.cuda(), rv.cuda(), True, 0.1, 1e-5, False)
+    ((yg * g1.cuda()).sum() + (zg * g2.permute(0, 2, 3, 1).contiguous().cuda()).sum()).backward()
+    assert rel(yg, y) < 2e-5 and rel(zg.permute(0, 3, 1, 2), z) < 5e-5
+    for a, r, name in ((xg, x, 'x'), (lwg, lw, 'ln.w'), (lbg, lb, 'ln.b'), (cwg, cw, 'conv.w'), (bwg, bw, 'bn.w'), (bbg, bb, 'bn.b')):
+        assert rel(a.grad, r.grad) < 3e-4, (name, rel(a.grad, r.grad))
