@@ -67,6 +67,8 @@ def parse():
                     help='N > 1: shard the experts over the ranks (NVLink peer-memory dispatch); default for --config b_e16')
     ap.add_argument('--no-expert-parallel', action='store_true')
     ap.add_argument('--cpu-images', type=int, default=1, help='images in the bounded CPU sample')
+    ap.add_argument('--no-grad-sync', action='store_true',
+                    help='DIAGNOSTIC, N > 1: never all-reduce gradients (isolates the exposed cost of the DDP collective)')
     a = ap.parse_args()
     return a
 
@@ -239,7 +241,7 @@ def time_gpu_eager(args, micro):
 
 
 # ------------------------------------------------------------------------------------------------
-TENSOR_OPS = ('gemm', 'ffn_fused_fwd', 'ffn_fused_bwd_all')     # ops.* entry points that launch tcgen05 kernels
+TENSOR_OPS = ('gemm', 'ffn_fused_fwd', 'ffn_fused_bwd')     # ops.* entry points that launch tcgen05 kernels
 
 
 def gemm_roofline(step_fn, peaks):
@@ -417,7 +419,7 @@ def run_ours(args):
         all-reduced (DDP) once, during the last micro-batch's backward"""
         tot = None
         for i in range(n_micro):
-            sync_ctx = model.no_sync() if (world > 1 and i + 1 < n_micro) else contextlib.nullcontext()
+            sync_ctx = model.no_sync() if (world > 1 and (i + 1 < n_micro or args.no_grad_sync)) else contextlib.nullcontext()
             with sync_ctx:
                 t = micro_step(x[i * MB:(i + 1) * MB])
             tot = t if tot is None else tot + t
@@ -530,6 +532,10 @@ def run_ours(args):
                 'e2e': {'value': B * world / (ms_e2e * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
                 'gpu_launches': launches, 'peak_mem_gb': peak_mem, 'roofline': roof, 'roofline_moe': roof_moe}
+        if args.no_grad_sync:
+            line['diagnostic'] = 'gradients NOT all-reduced (--no-grad-sync): not a valid training step, comm-cost isolation only'
+        if os.environ.get('SM3_RESERVE_SMS'):
+            line['config']['reserved_sms_for_nccl'] = int(os.environ['SM3_RESERVE_SMS'])
         if world == 1 and not args.no_gpu_eager:
             del model, net
             torch.cuda.empty_cache()

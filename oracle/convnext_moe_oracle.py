@@ -251,7 +251,7 @@ def moe_layer(x, sd, p, cfg: OracleConfig, train: bool, noise=None, loss_coef=1e
             for e in range(cfg.num_experts)]
     # combine :269-284
     stitched = torch.cat(outs, 0).mul(nonzero_gates)
-    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True, device=stitched.device)   # :277
+    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True, device=stitched.device, dtype=stitched.dtype)   # :277
     y = zeros.index_add(0, batch_index, stitched.float())
     if record is not None:
         record.append(dict(prefix=p, x=x.detach(), top_idx=info['top_idx'].detach(),

@@ -211,7 +211,7 @@ def moe_conv_layer(x, sd, p, cfg: LskConfig, train: bool, noise=None, loss_coef=
                          sd[p + f'experts.{e}.bias'])
             outs.append(o.reshape(expert_inputs[e].shape[0], -1))
     stitched = torch.cat(outs, 0).mul(nonzero_gates)
-    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True, device=stitched.device)
+    zeros = torch.zeros(gates.size(0), outs[-1].size(1), requires_grad=True, device=stitched.device, dtype=stitched.dtype)
     y = zeros.index_add(0, batch_index, stitched)                              # :263 (no .float())
     if record is not None:
         record.append(dict(prefix=p, x=x.detach(), top_idx=info['top_idx'].detach(),

@@ -1,4 +1,5 @@
 #include "common.cuh"
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -37,6 +38,15 @@ int num_sms() {
     cached[dev] = n > 0 ? n : 148;
   });
   return cached[dev];
+}
+
+// Persistent tcgen05 kernels occupy a whole SM each (all of its registers / shared memory), so a collective launched on
+// another stream (NCCL's gradient all-reduce under DDP) cannot co-reside and is serialised behind them.  SM3_RESERVE_SMS=n
+// keeps n SMs out of the persistent grids so that NCCL's CTAs run concurrently with the backward GEMMs.
+int persistent_grid_sms() {
+  static const int reserve = []() { const char* e = getenv("SM3_RESERVE_SMS"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : v; }();
+  const int n = num_sms() - reserve;
+  return n < 1 ? 1 : n;
 }
 
 }  // namespace sm3

@@ -26,6 +26,7 @@ int check_launch(const char* what);   // cudaGetLastError() -> SM3_ERR_CUDA (+ m
   } while (0)
 
 int num_sms();  // cached per device
+int persistent_grid_sms();  // num_sms() minus SM3_RESERVE_SMS (SMs left to concurrent NCCL kernels)
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

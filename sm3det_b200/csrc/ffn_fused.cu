@@ -368,7 +368,7 @@ int chain(const ChainParams& p, cudaStream_t stream) {
   k.p.passes = (p.passes == 1) ? 1 : 3;
   k.m_tiles = (p.M + 127) / 128;
   k.nch = p.H4 / HC;
-  int grid = num_sms();
+  int grid = persistent_grid_sms();
   if (grid > k.m_tiles) grid = k.m_tiles;
 #define SM3_CHAIN_LAUNCH(MODE_, HC_)                                                                                        \
   do {                                                                                                                      \

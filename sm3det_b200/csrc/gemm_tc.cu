@@ -239,7 +239,7 @@ int launch(Params p, cudaStream_t stream) {
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     if (ns >= STAGES) { p.nstages = ns; p.stage_bytes = sb; }
   }
-  int grid = num_sms();
+  int grid = persistent_grid_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   if (grid < 1) grid = 1;
 #define SM3_GEMM_LAUNCH_E(AMN, BMN, BPK, APK, EPIT)                                                                             \

@@ -30,10 +30,10 @@ def ops():
 
 
 @pytest.mark.parametrize('ks,dil', [(3, 1), (5, 1), (7, 3)])
-@pytest.mark.parametrize('C,H,W', [(32, 8, 8), (64, 19, 33), (128, 16, 16), (64, 64, 64), (32, 50, 70)])
+@pytest.mark.parametrize('C,H,W', [(32, 8, 8), (64, 19, 33), (128, 16, 16), (64, 64, 64), (32, 50, 70), (64, 96, 96)])
 def test_dwconv_generic(ops, ks, dil, C, H, W):
     g = torch.Generator().manual_seed(C + H + ks)
-    N = 2 if H < 50 else 1           # the 256^2 .. 1024^2 levels of config 5 are multi-tile in both directions
+    N = 1 if H in (50, 64) else 2    # the 256^2 .. 1024^2 levels of config 5 are multi-tile in both directions
     x = torch.randn(N, C, H, W, generator=g, requires_grad=True)
     w = (torch.randn(C, 1, ks, ks, generator=g) * 0.2).requires_grad_(True)
     b = (torch.randn(C, generator=g) * 0.1).requires_grad_(True)
@@ -79,11 +79,11 @@ def test_colstat_affine_batchnorm(ops, C, rows):
     assert rel(out, x * w + dy * b + rm + x) < 1e-6
 
 
-@pytest.mark.parametrize('Ch,H,W', [(32, 8, 8), (64, 13, 21), (160, 16, 16), (32, 64, 64), (64, 40, 56)])
+@pytest.mark.parametrize('Ch,H,W', [(32, 8, 8), (64, 13, 21), (160, 16, 16), (32, 64, 64), (64, 40, 56), (64, 96, 96), (32, 192, 192)])
 def test_lsk_select(ops, Ch, H, W):
     from sm3det_b200.lsk_functional import LSKSelectFn
     g = torch.Generator().manual_seed(Ch + H)
-    N = 2 if H < 40 else 1
+    N = 1 if H in (40, 64) else 2
     a1 = torch.randn(N, Ch, H, W, generator=g, requires_grad=True)
     a2 = torch.randn(N, Ch, H, W, generator=g, requires_grad=True)
     wsq = (torch.randn(2, 2, 7, 7, generator=g) * 0.2).requires_grad_(True)
@@ -228,7 +228,7 @@ def test_lsk_backbone_matches_reference_golden(path):
                 e = ((got - want).abs().max() / max(want.abs().max().item(), scale, 1e-5)).item()
                 bad.append((e / grad_tol(name), e, name))
             bad.sort(reverse=True)
-            print('worst grads vs fixture', bad[:5])
+            print('worst grads vs fixture', bad[:14])
             assert bad[0][0] < 1.0, bad[:8]
             for k, v in gold['bn'].items():
                 assert rel(new_sd[k], v) < 1e-4, k
@@ -328,6 +328,6 @@ def test_stage_boundary_norm_output_feeds_next_patch_embed(ops, N, C, Co, H):
     yg = Fn.OutNormFn.apply(xg, lwg, lbg, 1e-6)
     zg = BatchNormFn.apply(PatchEmbedFn.apply(yg, cwg, cbg, 2, True), bwg, bbg, rm.cuda(), rv.cuda(), True, 0.1, 1e-5, False)
     ((yg * g1.cuda()).sum() + (zg * g2.permute(0, 2, 3, 1).contiguous().cuda()).sum()).backward()
-    assert rel(yg, y) < 2e-5 and rel(zg.permute(0, 3, 1, 2), z) < 5e-5
+    assert rel(yg, y) < 2e-5 and rel(zg.permute(0, 3, 1, 2), z) < (5e-5 if N * H * W >= 64 else 3e-4)   # BN over 4 tokens amplifies rounding
     for a, r, name in ((xg, x, 'x'), (lwg, lw, 'ln.w'), (lbg, lb, 'ln.b'), (cwg, cw, 'conv.w'), (bwg, bw, 'bn.w'), (bbg, bb, 'bn.b')):
         assert rel(a.grad, r.grad) < 3e-4, (name, rel(a.grad, r.grad))

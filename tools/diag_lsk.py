@@ -252,7 +252,155 @@ def run_both(size, n):
     print('   d(conv4) first values GPU', gc.flatten()[:4].tolist(), 'oracle', oc_.flatten()[:4].tolist())
 
 
+def run_params(size, n, mode='train_noisy', dev='cuda'):
+    """Config 5 (real LSKNet-S widths): product vs the oracle run ON THE GPU in float64 and float32 (teacher-forced routing).
+    Prints every parameter whose gradient differs by more than 1e-3, in forward order, and oracle-fp32 vs oracle-fp64 beside
+    it (the conditioning of that gradient)."""
+    from oracle.cases import LSK_S_KW
+    kw = dict(LSK_S_KW, drop_rate=0.1)
+    cfg = LskConfig(**kw)
+    sd = make_state_dict(lsk_param_shapes(cfg), 0, True)
+    net = LSKNet_moe_MultiInput(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    x = make_images(n, size, size, seed=1234)
+    gold = dict(img=(n, size, size), mode=mode)
+    noise, drops = lsk_injections(cfg, gold)
+    inject(net, cfg, noise, drops)
+    rec = []
+    res = net(x.cuda(), record=rec)
+    outs, loss = res
+    forced = [r['top_idx'].long() for r in rec]
+    ups = upstream_grads([o.detach().cpu() for o in outs])
+    (sum((o * g.cuda()).sum() for o, g in zip(outs, ups)) + loss).backward()
+    skip = ('running_', 'num_batches', '.mean', '.std')
+
+    def oracle(dt):
+        sdo = {}
+        for k, v in sd.items():
+            v = v.to(dev)
+            if v.is_floating_point():
+                v = v.to(dt)
+                if not any(t in k for t in skip):
+                    v = v.clone().requires_grad_(True)
+            sdo[k] = v
+        r = lsk_backbone_forward(sdo, cfg, x.to(dev).to(dt), train=True, noise=[t.to(dev).to(dt) for t in noise] if noise else None,
+                                 drop_masks=[t.to(dev).to(dt) for t in drops] if drops else None, bn_state={}, forced_idx=[f.to(dev) for f in forced])
+        oc, lc = r
+        (sum((o * g.to(dev).to(dt)).sum() for o, g in zip(oc, ups)) + lc).backward()
+        return sdo, oc
+    s64, o64 = oracle(torch.float64)
+    s32, o32 = oracle(torch.float32)
+    print(f'== params n={n} size {size} {mode}: fwd product-vs-f64 {[f"{rel(a, b):.1e}" for a, b in zip(outs, o64)]}  oracle32-vs-f64 {[f"{rel(a, b):.1e}" for a, b in zip(o32, o64)]}')
+    for name, p in net.named_parameters():
+        w = s64[name].grad
+        if w is None or float(w.abs().max()) < 1e-9:
+            continue
+        e, e32 = rel(p.grad, w), rel(s32[name].grad, w)
+        if e > 1e-3 or e32 > 1e-3:
+            print(f'   {name:58s} product {e:.1e}   oracle-fp32 {e32:.1e}   |g|max {float(w.abs().max()):.2e}')
+
+
+def run_sgu(size, n, mode='train_noisy'):
+    """Config 5: gradients of every tensor inside each LSK spatial gating unit, product vs oracle (fp64 on the GPU)."""
+    import torch.nn.functional as F
+    import oracle.lsk_moe_oracle as O
+    from oracle.cases import LSK_S_KW
+    from sm3det_b200 import lsk_backbone as LB
+    from sm3det_b200 import lsk_functional as LF
+    kw = dict(LSK_S_KW, drop_rate=0.1)
+    cfg = LskConfig(**kw)
+    sd = make_state_dict(lsk_param_shapes(cfg), 0, True)
+    net = LSKNet_moe_MultiInput(norm_cfg=dict(type='SyncBN', requires_grad=True), **kw)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    got = []
+
+    def p_forward(self, x):
+        t = {}
+        t['x'] = x
+        t['attn1'] = LF.DWConvFn.apply(x, self.conv0.weight, self.conv0.bias, 5, 1)
+        t['attn2'] = LF.DWConvFn.apply(t['attn1'], self.conv_spatial.weight, self.conv_spatial.bias, 7, 3)
+        t['a1'] = LB._conv1x1(self.conv1, t['attn1'])
+        t['a2'] = LB._conv1x1(self.conv2, t['attn2'])
+        t['sel'] = LF.LSKSelectFn.apply(t['a1'], t['a2'], self.conv_squeeze.weight, self.conv_squeeze.bias)
+        t['attn'] = LB._conv1x1(self.conv, t['sel'])
+        t['out'] = LF.MulFn.apply(x, t['attn'])
+        for v in t.values():
+            if v.requires_grad:
+                v.retain_grad()
+        got.append(t)
+        return t['out']
+    o_fwd = LB.LSKblock.forward
+    LB.LSKblock.forward = p_forward
+    x = make_images(n, size, size, seed=1234)
+    gold = dict(img=(n, size, size), mode=mode)
+    noise, drops = lsk_injections(cfg, gold)
+    inject(net, cfg, noise, drops)
+    rec = []
+    try:
+        outs, loss = net(x.cuda(), record=rec)
+    finally:
+        LB.LSKblock.forward = o_fwd
+    forced = [r['top_idx'].long() for r in rec]
+    ups = upstream_grads([o.detach().cpu() for o in outs])
+    (sum((o * g.cuda()).sum() for o, g in zip(outs, ups)) + loss).backward()
+    ref = []
+
+    def o_lsk_block(x, sd, p):
+        c = x.shape[1]
+        t = {'p': p, 'x': x}
+        t['attn1'] = F.conv2d(x, sd[p + 'conv0.weight'], sd[p + 'conv0.bias'], padding=2, groups=c)
+        t['attn2'] = F.conv2d(t['attn1'], sd[p + 'conv_spatial.weight'], sd[p + 'conv_spatial.bias'], padding=9, groups=c, dilation=3)
+        t['a1'] = F.conv2d(t['attn1'], sd[p + 'conv1.weight'], sd[p + 'conv1.bias'])
+        t['a2'] = F.conv2d(t['attn2'], sd[p + 'conv2.weight'], sd[p + 'conv2.bias'])
+        attn = torch.cat([t['a1'], t['a2']], dim=1)
+        agg = torch.cat([attn.mean(1, keepdim=True), attn.max(1, keepdim=True)[0]], 1)
+        top2 = attn.detach().topk(2, dim=1).values
+        t['gap'] = ((top2[:, 0] - top2[:, 1]) / attn.detach().abs().amax(1).clamp_min(1e-20)).flatten()
+        sig = F.conv2d(agg, sd[p + 'conv_squeeze.weight'], sd[p + 'conv_squeeze.bias'], padding=3).sigmoid()
+        t['sel'] = t['a1'] * sig[:, 0:1] + t['a2'] * sig[:, 1:2]
+        t['attn'] = F.conv2d(t['sel'], sd[p + 'conv.weight'], sd[p + 'conv.bias'])
+        t['out'] = x * t['attn']
+        for k, v in t.items():
+            if torch.is_tensor(v) and v.requires_grad:
+                v.retain_grad()
+        ref.append(t)
+        return t['out']
+    skip = ('running_', 'num_batches', '.mean', '.std')
+    dt, dev = torch.float64, 'cuda'
+    sdo = {}
+    for k, v in sd.items():
+        v = v.to(dev)
+        if v.is_floating_point():
+            v = v.to(dt)
+            if not any(t in k for t in skip):
+                v = v.clone().requires_grad_(True)
+        sdo[k] = v
+    o_orig = O.lsk_block
+    O.lsk_block = o_lsk_block
+    try:
+        oc, lc = lsk_backbone_forward(sdo, cfg, x.to(dev).to(dt), train=True, noise=[t.to(dev).to(dt) for t in noise] if noise else None,
+                                      drop_masks=[t.to(dev).to(dt) for t in drops] if drops else None, bn_state={}, forced_idx=[f.to(dev) for f in forced])
+    finally:
+        O.lsk_block = o_orig
+    (sum((o * g.to(dev).to(dt)).sum() for o, g in zip(oc, ups)) + lc).backward()
+    print(f'== sgu n={n} size {size}')
+    P = lambda t: t.permute(0, 3, 1, 2)
+    for g, r in zip(got, ref):
+        gap = r['gap']
+        line = f"   {r['p']:42s} shape {tuple(r['a1'].shape)}  near-ties(<1e-4) {int((gap < 1e-4).sum())}/{gap.numel()}"
+        for k in ('out', 'attn', 'sel', 'a1', 'a2', 'attn2', 'attn1', 'x'):
+            if g[k].grad is None or r[k].grad is None:
+                line += f'  d{k} -'
+                continue
+            line += f'  d{k} {rel(P(g[k].grad), r[k].grad):.1e}'
+        line += '  | fwd a1 %.1e sel %.1e' % (rel(P(g['a1']), r['a1']), rel(P(g['sel']), r['sel']))
+        print(line)
+
+
 if __name__ == '__main__':
-    run_both(64, 2)
-    run_both(64, 1)
-    run_both(256, 1)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for a in sys.argv[1:] or ['768']:
+        run_sgu(int(a), 2)
