@@ -67,6 +67,12 @@ def parse():
                     help='N > 1: shard the experts over the ranks (NVLink peer-memory dispatch); default for --config b_e16')
     ap.add_argument('--no-expert-parallel', action='store_true')
     ap.add_argument('--cpu-images', type=int, default=1, help='images in the bounded CPU sample')
+    ap.add_argument('--cuda-graph', choices=['auto', 'on', 'off'], default='auto',
+                    help='capture the whole step (fwd+bwd over all micro-batches, gradient all-reduce included) in a CUDA graph; '
+                         'auto = on except for AMP and expert parallelism')
+    ap.add_argument('--grad-sync', choices=['auto', 'ddp', 'flat'], default='auto',
+                    help='N > 1: DistributedDataParallel bucket hooks, or one flat all-reduce at the end of the step (capturable); '
+                         'auto = flat when the step is graph-captured')
     ap.add_argument('--no-grad-sync', action='store_true',
                     help='DIAGNOSTIC, N > 1: never all-reduce gradients (isolates the exposed cost of the DDP collective)')
     a = ap.parse_args()
@@ -359,7 +365,7 @@ def moe_roofline(net, x, peaks):
     return out
 
 
-def build_model(args, world, ep):
+def build_model(args, world, ep, ddp=True):
     import torch.distributed as dist
     from sm3det_b200.synth import make_state_dict
     c = CONFIGS[args.config]
@@ -380,7 +386,7 @@ def build_model(args, world, ep):
         enable_expert_parallel(net, dist.new_group(list(range(world))))
         # expert parameters never enter a gradient bucket: each rank keeps the gradients of the experts it owns
         torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(net, ddp_ignored_parameters(net))
-    if world > 1:
+    if world > 1 and ddp:
         local = int(os.environ.get('LOCAL_RANK', '0'))
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=False,
                                                           gradient_as_bucket_view=True)
@@ -390,6 +396,7 @@ def build_model(args, world, ep):
 def run_ours(args):
     import torch.distributed as dist
     from sm3det_b200 import _lib
+    from sm3det_b200.graphed import GraphedStep, allreduce_gradients
     from sm3det_b200.synth import make_images
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -401,7 +408,16 @@ def run_ours(args):
     lib = _lib.load()
     assert lib.sm3_device_supported() == 1, 'bench.py needs an sm_100 (B200) device'
     c, B, MB, scaling, ep = resolve(args, world)
-    net, model = build_model(args, world, ep)
+    # gradient sync: DDP's bucketed all-reduce hooks (eager launches), or ONE flat all-reduce at the end of the step, which
+    # is capturable in the CUDA graph together with the whole forward+backward (sm3det_b200/graphed.py)
+    want_graph = args.cuda_graph == 'on' or (args.cuda_graph == 'auto' and not args.amp and not ep)
+    flat_sync = world > 1 and (args.grad_sync == 'flat' or (args.grad_sync == 'auto' and want_graph))
+    net, model = build_model(args, world, ep, ddp=not flat_sync)
+    named_params = list(net.named_parameters())
+    ignored = set()
+    if ep:
+        from sm3det_b200.expert_parallel import ddp_ignored_parameters
+        ignored = set(ddp_ignored_parameters(net))
     S = args.size
     n_micro = B // MB
     host_x = make_images(B, S, S, seed=1234 + rank).pin_memory()
@@ -419,10 +435,12 @@ def run_ours(args):
         all-reduced (DDP) once, during the last micro-batch's backward"""
         tot = None
         for i in range(n_micro):
-            sync_ctx = model.no_sync() if (world > 1 and (i + 1 < n_micro or args.no_grad_sync)) else contextlib.nullcontext()
+            sync_ctx = model.no_sync() if (world > 1 and not flat_sync and (i + 1 < n_micro or args.no_grad_sync)) else contextlib.nullcontext()
             with sync_ctx:
                 t = micro_step(x[i * MB:(i + 1) * MB])
             tot = t if tot is None else tot + t
+        if flat_sync and not args.no_grad_sync:
+            allreduce_gradients(None, named=named_params, skip=ignored)
         return tot
 
     def sync():
@@ -433,6 +451,32 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(dev_x)
         model.zero_grad(set_to_none=True)
+    # ---- CUDA graph of the whole step (all micro-batches, forward + backward): one replay per step instead of thousands of
+    # launches.  On several GPUs the gradient all-reduce is the flat one above and is part of the graph.
+    graphed, graph_note = None, 'off'
+    if want_graph:
+        try:
+            graphed = GraphedStep(step, [dev_x], net.parameters(), warmup=2,
+                                  invalidate=[m._packs for m in net.modules() if hasattr(m, '_packs')],
+                                  capture_error_mode='global' if world == 1 else 'thread_local')
+            graph_note = f'whole step captured: {graphed.launches_per_replay} C-ABI launches per replay'
+        except Exception as e:       # noqa: BLE001 -- report and fall back to eager launches
+            if args.cuda_graph == 'on':
+                raise
+            graphed, graph_note = None, f'capture failed, eager launches: {type(e).__name__}: {e}'[:300]
+            torch.cuda.synchronize()
+            model.zero_grad(set_to_none=True)
+
+    def run(x):
+        if graphed is not None:
+            return graphed(x)            # gradients are replaced by the replay (no zero_grad between steps)
+        t = step(x)
+        return t
+
+    def after_step():
+        if graphed is None:
+            model.zero_grad(set_to_none=True)
+
     sampler = ClockSampler(local)
     # ---- device-resident timing -------------------------------------------------------------------
     _lib.LAUNCHES = 0
@@ -442,11 +486,11 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step(dev_x)
-        model.zero_grad(set_to_none=True)
+        run(dev_x)
+        after_step()
     e1.record()
     sync()
-    launches = _lib.LAUNCHES
+    launches = _lib.LAUNCHES + (graphed.launches_per_replay * args.steps if graphed is not None else 0)
     ms = e0.elapsed_time(e1) / args.steps
     # ---- end to end: pinned host input -> device, result scalar back to the host, every step --------
     # Every step's batch is copied from pinned host memory inside the timed region; the copy of step i+1 is issued on
@@ -479,14 +523,14 @@ def run_ours(args):
         if i + 1 < args.steps:
             prefetch(cur ^ 1, i == 0)
         main.wait_event(ready[cur])
-        tot = step(bufs[cur])
+        tot = run(bufs[cur])
         freed[cur].record(main)
         host_res[cur].copy_(tot, non_blocking=True)      # D2H read of the step result (4 bytes)
         res_ready[cur].record(main)
         if i > 0:
             res_ready[cur ^ 1].synchronize()
             acc += float(host_res[cur ^ 1])
-        model.zero_grad(set_to_none=True)
+        after_step()
     res_ready[(args.steps - 1) & 1].synchronize()
     acc += float(host_res[(args.steps - 1) & 1])
     e3.record()
@@ -508,7 +552,8 @@ def run_ours(args):
         except Exception:
             pass
         roof = roof_moe = None
-        if not ep and not args.amp:        # the instrumented extra passes are rank-0 only; expert parallelism needs every rank in each layer
+        # the instrumented extra passes are rank-0 only: expert parallelism and SyncBN (LSKNet) need every rank in each layer
+        if not ep and not args.amp and (world == 1 or c['family'] == 'convnext'):
             xm = dev_x[:MB]
 
             def one():
@@ -532,6 +577,9 @@ def run_ours(args):
                 'e2e': {'value': B * world / (ms_e2e * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
                 'gpu_launches': launches, 'peak_mem_gb': peak_mem, 'roofline': roof, 'roofline_moe': roof_moe}
+        line['cuda_graph'] = graph_note
+        if world > 1:
+            line['config']['grad_sync'] = 'one flat all-reduce at the end of the step' if flat_sync else 'DDP bucket hooks'
         if args.no_grad_sync:
             line['diagnostic'] = 'gradients NOT all-reduced (--no-grad-sync): not a valid training step, comm-cost isolation only'
         if os.environ.get('SM3_RESERVE_SMS'):

@@ -305,6 +305,9 @@ int sm3_mul(const float* a, const float* b, const float* add, float* out, int64_
 /* nn.Dropout (lsk_moe.py:300,311,316) with a counter-based mask: out = x * keep(seed, index) / (1-p); the same call on dy is
  * the backward (mask recomputed from the seed, nothing saved). */
 int sm3_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
+/* Same mask function with the seed read from device memory (one uint64): a captured CUDA graph replays the launch while the
+ * seed tensor is refreshed between replays, so every step still draws a new mask. */
+int sm3_dropout_dev(const float* x, float* out, int64_t n, float p, const uint64_t* seed_dev, void* stream);
 int sm3_lsk_agg(const float* a1, const float* a2, float* agg, int32_t* amax, int64_t T, int32_t Ch, void* stream);
 int sm3_conv7_c2(const float* x, const float* w, const float* b, float* y, int32_t N, int32_t H, int32_t W, int32_t act,
                  void* stream);

@@ -151,6 +151,8 @@ def batch_norm(x, sd, p, cfg: LskConfig, train: bool, bn_state: Optional[dict]):
 
 
 _FORCE = None   # iterator of forced top-k index tensors (set by *_forward(forced_idx=...)); test-only
+_FORCE_AMAX = None   # iterator of forced LSK channel-argmax tensors [N*H*W] (NHWC token order) per LSKblock; test-only
+_AMAX_RECORD = None  # list receiving {own, forced, gap, scale} per LSKblock when forcing
 
 
 def noisy_top_k_gating(x, sd, p, cfg: LskConfig, train: bool, noise=None, noise_epsilon=1e-2):
@@ -262,7 +264,19 @@ def lsk_block(x, sd, p):
     attn2 = F.conv2d(attn2, sd[p + 'conv2.weight'], sd[p + 'conv2.bias'])
     attn = torch.cat([attn1, attn2], dim=1)
     avg_attn = torch.mean(attn, dim=1, keepdim=True)
-    max_attn, _ = torch.max(attn, dim=1, keepdim=True)
+    max_attn, own_idx = torch.max(attn, dim=1, keepdim=True)
+    forced = None
+    if _FORCE_AMAX is not None:
+        # test-only teacher forcing of the channel argmax (same idea as _FORCE for the router): the max feature and its
+        # gradient follow the channel the CUDA path selected, so near-tie flips do not hide behind a loose tolerance
+        forced = next(_FORCE_AMAX).to(attn.device).long().reshape(own_idx.shape)
+    if _AMAX_RECORD is not None:
+        d = attn.detach()
+        f = own_idx if forced is None else forced
+        _AMAX_RECORD.append(dict(prefix=p, own=own_idx.detach().flatten(), forced=f.detach().flatten(),
+                                 gap=(max_attn.detach() - d.gather(1, f)).flatten(), scale=d.abs().amax(1).flatten()))
+    if forced is not None:
+        max_attn = attn.gather(1, forced)
     agg = torch.cat([avg_attn, max_attn], dim=1)
     sig = F.conv2d(agg, sd[p + 'conv_squeeze.weight'], sd[p + 'conv_squeeze.bias'], padding=3).sigmoid()
     attn = attn1 * sig[:, 0, :, :].unsqueeze(1) + attn2 * sig[:, 1, :, :].unsqueeze(1)
@@ -316,15 +330,18 @@ def block(x, sd, p, cfg: LskConfig, moe1, moe2, dpr, train, bn_state, noise_it, 
 def lsk_backbone_forward(sd: Dict[str, torch.Tensor], cfg: LskConfig, x, train: bool = False,
                          noise: Optional[List[torch.Tensor]] = None, drop_masks: Optional[List[torch.Tensor]] = None,
                          dp_masks: Optional[List[torch.Tensor]] = None, record: Optional[list] = None,
-                         bn_state: Optional[dict] = None, forced_idx: Optional[List[torch.Tensor]] = None):
+                         bn_state: Optional[dict] = None, forced_idx: Optional[List[torch.Tensor]] = None,
+                         forced_amax: Optional[List[torch.Tensor]] = None, amax_record: Optional[list] = None):
     """LSKNet_moe_MultiInput.forward :740-765 (datasets=None path) + forward_features :716-739,
     or LSKNet_moe.forward_features :541-559 when ``cfg.multi_input`` is False."""
-    global _FORCE
+    global _FORCE, _FORCE_AMAX, _AMAX_RECORD
     _FORCE = None if forced_idx is None else iter(forced_idx)
+    _FORCE_AMAX = None if forced_amax is None else iter(forced_amax)
+    _AMAX_RECORD = amax_record
     try:
         return _lsk_backbone_forward(sd, cfg, x, train, noise, drop_masks, dp_masks, record, bn_state)
     finally:
-        _FORCE = None
+        _FORCE = _FORCE_AMAX = _AMAX_RECORD = None
 
 
 def _lsk_backbone_forward(sd, cfg, x, train, noise, drop_masks, dp_masks, record, bn_state):

@@ -125,6 +125,7 @@ SIGNATURES = {
     'sm3_affine': [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     'sm3_mul': [_P, _P, _P, _P, _I64, _P],
     'sm3_dropout': [_P, _P, _I64, _F32, C.c_uint64, _P],
+    'sm3_dropout_dev': [_P, _P, _I64, _F32, _P, _P],
     'sm3_lsk_agg': [_P, _P, _P, _P, _I64, _I32, _P],
     'sm3_conv7_c2': [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     'sm3_conv7_c2_wgrad': [_P, _P, _P, _P, _I32, _I32, _I32, _P],

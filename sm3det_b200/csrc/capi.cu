@@ -207,6 +207,9 @@ int sm3_mul(const float* a, const float* b, const float* add, float* out, int64_
 int sm3_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream) {
   return dropout(x, out, n, p, seed, S(stream));
 }
+int sm3_dropout_dev(const float* x, float* out, int64_t n, float p, const uint64_t* seed_dev, void* stream) {
+  return dropout_dev(x, out, n, p, reinterpret_cast<const unsigned long long*>(seed_dev), S(stream));
+}
 int sm3_lsk_agg(const float* a1, const float* a2, float* agg, int32_t* amax, int64_t T, int32_t Ch, void* stream) {
   return lsk_agg(a1, a2, agg, amax, T, Ch, S(stream));
 }

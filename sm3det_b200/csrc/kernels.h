@@ -157,6 +157,7 @@ int affine(const float* x1, const float* a1, const float* x2, const float* a2, c
            long long rows, int C, cudaStream_t stream);
 int mul(const float* a, const float* b, const float* add, float* out, long long n, cudaStream_t stream);
 int dropout(const float* x, float* out, long long n, float p, unsigned long long seed, cudaStream_t stream);
+int dropout_dev(const float* x, float* out, long long n, float p, const unsigned long long* seed_dev, cudaStream_t stream);
 int lsk_agg(const float* a1, const float* a2, float* agg, int* amax, long long T, int Ch, cudaStream_t stream);
 int conv7_c2(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int act, cudaStream_t stream);
 int conv7_c2_wgrad(const float* x, const float* dpre, float* dw, float* db, int N, int H, int W, cudaStream_t stream);

@@ -328,9 +328,11 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {      // splitmix64 final
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4,
-                                                     uint32_t thresh, float scale, uint64_t seed) {
+                                                     uint32_t thresh, float scale, uint64_t seed,
+                                                     const unsigned long long* __restrict__ seed_dev) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
+  if (seed_dev) seed = __ldg(seed_dev);      // CUDA-graph replay: the seed lives in device memory and changes between replays
   const float4 v = ldg_f4(x + i * 4);
   const uint64_t base = seed ^ ((uint64_t)i * 4ull * 0xD1342543DE82EF95ull);
   float4 o;
@@ -344,7 +346,14 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
 int dropout(const float* x, float* out, long long n, float p, unsigned long long seed, cudaStream_t stream) {
   SM3_REQUIRE(x && out && n % 4 == 0 && p >= 0.f && p < 1.f, SM3_ERR_INVALID_ARG, "dropout: bad argument");
   const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
-  dropout_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(x, out, n / 4, thresh, 1.0f / (1.0f - p), seed);
+  dropout_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(x, out, n / 4, thresh, 1.0f / (1.0f - p), seed, nullptr);
+  return check_launch("dropout_kernel");
+}
+
+int dropout_dev(const float* x, float* out, long long n, float p, const unsigned long long* seed_dev, cudaStream_t stream) {
+  SM3_REQUIRE(x && out && seed_dev && n % 4 == 0 && p >= 0.f && p < 1.f, SM3_ERR_INVALID_ARG, "dropout_dev: bad argument");
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  dropout_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(x, out, n / 4, thresh, 1.0f / (1.0f - p), 0ull, seed_dev);
   return check_launch("dropout_kernel");
 }
 

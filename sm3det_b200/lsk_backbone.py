@@ -132,7 +132,10 @@ class Mlp(nn.Module):
         if masks:                                   # tests inject the reference's masks
             m = masks.pop(0).to(x.device, torch.float32).reshape(x.shape).contiguous()
             return LF.MulFn.apply(x, m)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # host RNG (torch.manual_seed reproducible), no device sync
+        if torch.cuda.is_current_stream_capturing():
+            seed = torch.randint(0, 2 ** 62, (1,), device=x.device)     # graph-safe: drawn on the device at every replay
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # host RNG (torch.manual_seed reproducible), no device sync
         return LF.DropoutFn.apply(x, p, seed)
 
     def forward(self, x, ls, resid, row_scale, record=None):

@@ -21,6 +21,9 @@ from . import ops
 from .ops import EPI_GELU
 
 
+AMAX_RECORD = None   # parity tests set this to a list: LSKSelectFn appends the channel argmax [T] of every LSKblock (forward order)
+
+
 def _taps(w):              # [C,1,ks,ks] -> [ks*ks][C]
     return w.reshape(w.shape[0], -1).t().contiguous()
 
@@ -36,14 +39,17 @@ def _sync_active(sync):
 def bn_batch_stats(s1, s2, n, running_mean, sync, group=None):
     """(mean, biased var, n) of a (Sync)BatchNorm from the per-rank shifted sums s1 = sum(x - running_mean),
     s2 = sum((x - running_mean)^2) over n local rows.  With ``sync`` the three are all-reduced first: the shift is the
-    running mean, identical on every rank, so the sums simply add.  Pure [C]-sized host-side glue (CPU-testable, gloo)."""
+    running mean, identical on every rank, so the sums simply add.  Pure [C]-sized glue (CPU-testable, gloo).  With ``sync``
+    the returned n is a 0-dim tensor that stays on the device: no host read-back per normalisation layer."""
     C = s1.numel()
     if _sync_active(sync):
-        st = torch.cat([s1, s2, s1.new_tensor([float(n)])])
+        st = torch.cat([s1, s2, torch.full((1,), float(n), device=s1.device, dtype=s1.dtype)])
         dist.all_reduce(st, group=group)
-        s1, s2, n = st[:C], st[C:2 * C], float(st[2 * C].item())
+        s1, s2, n = st[:C], st[C:2 * C], st[2 * C]
+    else:
+        n = float(n)
     d = s1 / n
-    return running_mean + d, (s2 / n - d * d).clamp_min_(0.0), float(n)
+    return running_mean + d, (s2 / n - d * d).clamp_min_(0.0), n
 
 
 @ops.captures_precision
@@ -62,7 +68,8 @@ class BatchNormFn(Function):
             rstd = torch.rsqrt(var + eps)
             with torch.no_grad():
                 running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-                running_var.mul_(1 - momentum).add_(var * (n / max(n - 1.0, 1.0)), alpha=momentum)
+                unbias = n / torch.clamp(n - 1.0, min=1.0) if torch.is_tensor(n) else n / max(n - 1.0, 1.0)
+                running_var.mul_(1 - momentum).add_(var * unbias, alpha=momentum)
         else:
             mean, rstd, n = running_mean, torch.rsqrt(running_var + eps), float(rows)
         scale = (weight * rstd).contiguous()
@@ -184,7 +191,9 @@ class LSKSelectFn(Function):
         T = N * H * W
         a1, a2 = a1.contiguous(), a2.contiguous()
         train = any(ctx.needs_input_grad)
-        agg, amax = ops.lsk_agg(a1, a2, T=T, Ch=Ch, want_idx=train)
+        agg, amax = ops.lsk_agg(a1, a2, T=T, Ch=Ch, want_idx=train or AMAX_RECORD is not None)
+        if AMAX_RECORD is not None:
+            AMAX_RECORD.append(amax)
         sig = ops.conv7_c2(agg, wsq.contiguous(), bsq, N=N, H=H, W=W, act=1)
         out = ops.lsk_mix(a1, a2, sig, T=T, Ch=Ch)
         if train:

@@ -581,9 +581,14 @@ def mul(a, b, add=None, out=None):
 
 
 def dropout(x, p, seed):
+    """seed: python int, or an int64 device tensor [1] (read by the kernel: CUDA-graph safe)."""
     lib = _lib.load()
     out = torch.empty_like(x)
-    _lib.check(lib.sm3_dropout(_p(x), _p(out), x.numel(), float(p), int(seed), _stream()), 'sm3_dropout')
+    if torch.is_tensor(seed):
+        assert seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 1
+        _lib.check(lib.sm3_dropout_dev(_p(x), _p(out), x.numel(), float(p), seed.data_ptr(), _stream()), 'sm3_dropout_dev')
+    else:
+        _lib.check(lib.sm3_dropout(_p(x), _p(out), x.numel(), float(p), int(seed), _stream()), 'sm3_dropout')
     return out
 
 

@@ -25,3 +25,13 @@ def test_syncbn_stat_combination_world2_gloo():
                        capture_output=True, text=True, timeout=300, env=dict(os.environ, MASTER_ADDR='127.0.0.1'))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count('syncbn stats ok') == 2, r.stdout[-2000:]
+
+
+def test_flat_gradient_allreduce_world2_gloo():
+    """graphed.allreduce_gradients (the capturable replacement of DDP's bucket hooks): mean over ranks, skip list, None grads."""
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29546',
+                        os.path.join(ROOT, 'tests', 'dist', 'gradsync_worker.py')],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, MASTER_ADDR='127.0.0.1'))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count('grad sync ok') == 2, r.stdout[-2000:]

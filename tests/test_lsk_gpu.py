@@ -11,7 +11,8 @@ import torch.nn.functional as F
 from oracle.cases import LSK_CASES, lsk_injections, upstream_grads
 from oracle.lsk_moe_oracle import LskConfig, lsk_backbone_forward, lsk_param_shapes
 from sm3det_b200.synth import make_images, make_state_dict
-from parity_util import assert_flips_are_near_ties, flipped_tokens
+from parity_util import GAP_TOL, MAX_FLIP_FRACTION, assert_flips_are_near_ties, flipped_tokens
+from sm3det_b200 import lsk_functional as LF
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
@@ -181,9 +182,13 @@ def test_lsk_backbone_matches_reference_golden(path):
     net.train(train)
     noise, drops = lsk_injections(cfg, gold)
     inject(net, cfg, noise, drops)
-    rec = []
-    with torch.set_grad_enabled(train):
-        res = net(x, record=rec)
+    rec, amax = [], []
+    LF.AMAX_RECORD = amax
+    try:
+        with torch.set_grad_enabled(train):
+            res = net(x, record=rec)
+    finally:
+        LF.AMAX_RECORD = None
     has_loss = 'gate_loss' in gold
     outs, loss = res if has_loss else (res, None)
     st = gold.get('stride', 1)
@@ -203,35 +208,13 @@ def test_lsk_backbone_matches_reference_golden(path):
         # a conv bias in front of a training-mode BatchNorm: the true gradient is exactly 0, both sides hold fp32 noise
         return name.endswith('proj.bias') or name == 'dataset_stems.single.bias'
 
-    if flips == 0:
-        # ---- the reference-generated fixture itself ----
-        errs = [rel(o[:, :, ::st, ::st], g) for o, g in zip(outs, gold['outs'])]
-        print(os.path.basename(path), 'rel errs vs fixture', errs)
-        assert max(errs) < TOL
-        if has_loss:
-            assert abs(loss.item() - gold['gate_loss'].item()) <= 1e-4 * abs(gold['gate_loss'].item()) + 1e-8
-        if train:
-            bad = []
-            for name, p in net.named_parameters():
-                gg = gold['grads'].get(name)
-                if gg is None:
-                    continue
-                got = p.grad.detach().float().cpu().reshape(-1)
-                if 'full' in gg:
-                    want = gg['full']
-                else:
-                    want, got = gg['sample'], got[gg['idx']]
-                scale = (gg['l2'] / (p.numel() ** 0.5)) if 'l2' in gg else want.abs().max().item()
-                if zero_grad_bias(name):
-                    assert (got - want).abs().max().item() < 1e-5, name
-                    continue
-                e = ((got - want).abs().max() / max(want.abs().max().item(), scale, 1e-5)).item()
-                bad.append((e / grad_tol(name), e, name))
-            bad.sort(reverse=True)
-            print('worst grads vs fixture', bad[:14])
-            assert bad[0][0] < 1.0, bad[:8]
-            for k, v in gold['bn'].items():
-                assert rel(new_sd[k], v) < 1e-4, k
+    # LSKblock's channel max (lsk_moe.py:337) is the second discrete selection on this path: at 10^4..10^5 tokens per level a few
+    # tokens have their two largest channels closer than the 3e-5 forward error, and ONE flipped token moves the whole d(max) of
+    # that token (a 7x7x2-tap sum over all channels) to another channel -- percent-level changes in the conv1/conv2 gradients
+    # (profiles/r02_lsk_argmax_flips.txt).  The forced-oracle pass below follows the CUDA path's channel choice, counts the
+    # tokens where that differs from the oracle's own argmax and requires each of them to be a numerical tie.
+    amax_flips, arec = 0, []
+    is_lsk = gold.get('unit', 'lsk') == 'lsk'
     if full or flips > 0:
         # ---- the oracle teacher-forced to the CUDA path's routing: every element, every gradient (tests/parity_util.py) ----
         forced = [r['top_idx'].cpu().long() for r in rec]
@@ -241,8 +224,15 @@ def test_lsk_backbone_matches_reference_golden(path):
         rec_c = []
         with torch.set_grad_enabled(train):
             res_c = lsk_backbone_forward(sdo, cfg, x.cpu(), train=train, noise=noise, drop_masks=drops, bn_state=bn_state, forced_idx=forced,
-                                         record=rec_c)
+                                         record=rec_c, forced_amax=[a.cpu() for a in amax] if is_lsk else None, amax_record=arec)
         oc, lc = res_c if has_loss else (res_c, None)
+        for a in arec:
+            flip = a['own'] != a['forced']
+            amax_flips += int(flip.sum())
+            if flip.any():
+                assert float((a['gap'][flip] / a['scale'][flip]).max()) < GAP_TOL, (a['prefix'], 'channel-argmax flip is not a near-tie')
+            assert int(flip.sum()) <= max(2, MAX_FLIP_FRACTION * flip.numel()), (a['prefix'], int(flip.sum()), flip.numel())
+        print(os.path.basename(path), 'channel-argmax flips', amax_flips, 'of', sum(a['own'].numel() for a in arec))
         # per layer: the CUDA routing vs the oracle's own top-k on the same (forced-upstream) inputs -- numerical ties only
         own = [dict(top_idx=c['logits'].topk(g['top_idx'].shape[1], dim=-1).indices, logits=c['logits']) for g, c in zip(rec, rec_c)]
         own_flips = assert_flips_are_near_ties(rec, own, what=gold['name'])
@@ -269,6 +259,35 @@ def test_lsk_backbone_matches_reference_golden(path):
             print('worst grads vs forced oracle', bad[:5])
             assert bad[0][0] < 1.0, bad[:8]
             for k, v in bn_state.items():
+                assert rel(new_sd[k], v) < 1e-4, k
+    if flips == 0:
+        # ---- the reference-generated fixture itself ----
+        errs = [rel(o[:, :, ::st, ::st], g) for o, g in zip(outs, gold['outs'])]
+        print(os.path.basename(path), 'rel errs vs fixture', errs)
+        assert max(errs) < TOL
+        if has_loss:
+            assert abs(loss.item() - gold['gate_loss'].item()) <= 1e-4 * abs(gold['gate_loss'].item()) + 1e-8
+        if train and amax_flips == 0:
+            bad = []
+            for name, p in net.named_parameters():
+                gg = gold['grads'].get(name)
+                if gg is None:
+                    continue
+                got = p.grad.detach().float().cpu().reshape(-1)
+                if 'full' in gg:
+                    want = gg['full']
+                else:
+                    want, got = gg['sample'], got[gg['idx']]
+                scale = (gg['l2'] / (p.numel() ** 0.5)) if 'l2' in gg else want.abs().max().item()
+                if zero_grad_bias(name):
+                    assert (got - want).abs().max().item() < 1e-5, name
+                    continue
+                e = ((got - want).abs().max() / max(want.abs().max().item(), scale, 1e-5)).item()
+                bad.append((e / grad_tol(name), e, name))
+            bad.sort(reverse=True)
+            print('worst grads vs fixture', bad[:14])
+            assert bad[0][0] < 1.0, bad[:8]
+            for k, v in gold['bn'].items():
                 assert rel(new_sd[k], v) < 1e-4, k
 
 

@@ -150,3 +150,31 @@ def test_van_contract():
     if ref_shim.reference_available():
         ref = ref_shim.load_reference_module('van_moe').VAN_moe_MultiInput(**kw)
         assert set(ref.state_dict()) == set(sd)
+
+
+def test_forced_channel_argmax_is_identity_on_own_choice():
+    """forced_amax with the oracle's own argmax reproduces outputs and gradients; forcing another channel moves the gradient
+    of the max feature to that channel (the mechanism the GPU parity test relies on for near-tie flips)."""
+    spec = LSK_CASES['lsk_mini_dense_eval']
+    cfg = LskConfig(**spec['kw'])
+    sd = make_state_dict(lsk_param_shapes(cfg), 0, True)
+    n, h, w = spec['img']
+    x = make_images(n, h, w, seed=1234)
+
+    def run(forced):
+        sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running_' not in k and 'num_batches' not in k else v) for k, v in sd.items()}
+        rec = []
+        outs = lsk_backbone_forward(sdg, cfg, x, train=True, bn_state={}, forced_amax=forced, amax_record=rec)
+        outs = outs[0] if isinstance(outs[0], (tuple, list)) else outs
+        sum(o.square().sum() for o in outs).backward()
+        return outs, sdg, rec
+    o_p, sd_p, rec = run(None)
+    assert len(rec) == sum(cfg.depths) and all(float(r['gap'].abs().max()) == 0.0 for r in rec)
+    o_f, sd_f, rec_f = run([r['own'] for r in rec])
+    assert all(int((r['own'] != r['forced']).sum()) == 0 for r in rec_f)
+    assert all(torch.equal(a, b) for a, b in zip(o_f, o_p))
+    name = 'block1.0.attn.spatial_gating_unit.conv1.bias'
+    assert torch.allclose(sd_f[name].grad, sd_p[name].grad, rtol=1e-5, atol=1e-9)
+    _, sd_z, rec_z = run([torch.zeros_like(r['own']) for r in rec])
+    assert float(rec_z[0]['gap'].max()) > 0.0
+    assert not torch.allclose(sd_z[name].grad, sd_p[name].grad, rtol=1e-3)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Condense `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:gemm_bf16x3 --csv`
-(one fwd+bwd step of bench.py) into profiles/r01_gemm_traffic.json: measured DRAM bytes per GEMM launch (bench.py reports
+"""Condense `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k "regex:gemm_bf16x3|ffn_chain" --csv`
+(one fwd+bwd step of bench.py) into profiles/r02_gemm_traffic.json: measured DRAM bytes per GEMM launch (bench.py reports
 it as roofline.traffic next to the algorithmic bytes).  usage: python tools/gemm_traffic.py launches.csv out.json"""
 import collections
 import csv
@@ -27,8 +27,8 @@ def main(path, out):
     t = sum(d.get('gpu__time_duration.sum', 0) for d in per.values())
     json.dump({'launches': n, 'dram_read_bytes': rd, 'dram_write_bytes': wr, 'bytes_per_launch': (rd + wr) / max(n, 1),
                'time_s_under_ncu': t,
-               'note': f'ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the {n} gemm_bf16x3 launches captured '
-                       f'(first fwd+bwd step of bench.py, bs 8 1024^2), divided by the launch count'}, open(out, 'w'), indent=1)
+               'note': f'ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the {n} tcgen05 (gemm_bf16x3 + ffn_chain) launches captured '
+                       f'(first fwd+bwd micro-batch of bench.py, 8 x 1024^2), divided by the launch count'}, open(out, 'w'), indent=1)
     print(open(out).read())
 
 
