@@ -559,6 +559,12 @@ def run_ours(args):
             def one():
                 outs, loss = net(xm)
                 (sum(o.mean() for o in outs) + loss).backward()
+            if graphed is not None:
+                # torch.cuda.graph() empties the caching allocator before capture: re-grow the eager pool off the clock so
+                # that no cudaMalloc lands between the CUDA events of the instrumented pass
+                one()
+                net.zero_grad(set_to_none=True)
+                torch.cuda.synchronize()
             roof = gemm_roofline(one, peaks)
             net.zero_grad(set_to_none=True)
             try:   # measured DRAM traffic of the tensor-core launches of one micro-batch (ncu dram__bytes_read+write, profiles/)
