@@ -394,6 +394,8 @@ def build_model(args, world, ep, ddp=True):
 
 
 def run_ours(args):
+    global T0
+    T0 = time.time()
     import torch.distributed as dist
     from sm3det_b200 import _lib
     from sm3det_b200.graphed import GraphedStep, allreduce_gradients
@@ -602,10 +604,24 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             ips, dt, threads, fwd_ips = time_cpu_reference(args, args.cpu_images, 1, 0)
             line['cpu_baseline'] = cpu_baseline_entry(args, ips, dt, threads, fwd_ips)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down order matters when the step was graph-captured: NCCL keeps a communicator alive (and ncclCommDestroy
+        # blocks) while a CUDA graph that captured collectives on it exists -- measured as a hang at exit after the JSON line
+        # on 4 GPUs (profiles/r02_multi_gpu.txt).  Destroy the graph first, then leave without tearing the group down.
+        def stamp(msg):
+            print(f'[bench rank {rank}] {msg} t={time.time() - T0:.1f}s', file=sys.stderr, flush=True)
+        stamp('result printed' if rank == 0 else 'timed region done')
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        stamp('graph released')
         dist.barrier()
-        dist.destroy_process_group()
+        stamp('barrier passed, exiting')
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -8,5 +8,4 @@ timeout 600 python -m pytest tests/test_ep_gpu.py -m gpu -q -x > gpurun_out/m4_e
 timeout 500 $TR --nproc-per-node 4 --master-port 29611 bench.py --gpus 4 --config lsk_s --steps 6 --warmup 3 > gpurun_out/m4_lsk_s_graph.json 2> gpurun_out/m4_lsk_s_graph.err; head -c 700 gpurun_out/m4_lsk_s_graph.json; tail -2 gpurun_out/m4_lsk_s_graph.err | cut -c1-300
 timeout 500 $TR --nproc-per-node 4 --master-port 29612 bench.py --gpus 4 --config lsk_s --steps 6 --warmup 3 --cuda-graph off > gpurun_out/m4_lsk_s_eager.json 2> gpurun_out/m4_lsk_s_eager.err; head -c 400 gpurun_out/m4_lsk_s_eager.json; tail -2 gpurun_out/m4_lsk_s_eager.err | cut -c1-300
 timeout 700 $TR --nproc-per-node 4 --master-port 29615 bench.py --gpus 4 --config b_e16 --steps 3 --warmup 3 > gpurun_out/m4_b_e16.json 2> gpurun_out/m4_b_e16.err; head -c 700 gpurun_out/m4_b_e16.json; tail -3 gpurun_out/m4_b_e16.err | cut -c1-300
-timeout 700 $TR --nproc-per-node 4 --master-port 29616 bench.py --gpus 4 --config b_e16 --steps 3 --warmup 3 --cuda-graph on > gpurun_out/m4_b_e16_graph.json 2> gpurun_out/m4_b_e16_graph.err; head -c 400 gpurun_out/m4_b_e16_graph.json; tail -3 gpurun_out/m4_b_e16_graph.err | cut -c1-300
 timeout 500 $TR --nproc-per-node 4 --master-port 29617 bench.py --gpus 4 --steps 6 --warmup 3 > gpurun_out/m4_t_e8_graph.json 2> gpurun_out/m4_t_e8_graph.err; head -c 400 gpurun_out/m4_t_e8_graph.json; tail -2 gpurun_out/m4_t_e8_graph.err | cut -c1-300
