@@ -28,6 +28,19 @@ CASES = {
                                        img=(2, 128, 128), mode='train', weights='trained', stride=2),
 }
 
+# ---- ConvNeXt_DA_MultiInput (convnext_moe_DA.py, local_configs/main_DA_convnext_t_orcnn_gfl.py): a DALayer per block ----
+# `datasets`: one name = whole batch through that dataset's gate; three names = one image per modality (the detector's call)
+DA_CASES = {
+    'da_mini_dense_eval_rgb': dict(kw=dict(arch=MINI), img=(2, 64, 64), mode='eval', weights='trained', stride=1, da=True,
+                                   datasets=['rgb']),
+    'da_mini_dense_train_3mod': dict(kw=dict(arch=MINI), img=(3, 64, 64), mode='train', weights='trained', stride=1, da=True,
+                                     datasets=['sar', 'rgb', 'ifr']),
+    'da_mini_moe_e4k2_train_noisy_3mod': dict(kw=dict(arch=MINI, MoE_Block_inds=[[], [0], [0, 1], [0]], num_experts=4, top_k=2),
+                                              img=(3, 64, 96), mode='train_noisy', weights='trained', stride=1, da=True,
+                                              datasets=['sar', 'rgb', 'ifr']),
+}
+CASES.update(DA_CASES)
+
 # ---- full-size cases: the shapes bench.py times (BASELINE configs 2/3, the shipped k=3 recipe, config 4's widths) -----
 # One 1024^2 (or 512^2) image each; fixtures keep strided output samples, compact routing (int8 indices + the oracle's own
 # (k)-vs-(k+1) logit gap per token, which is what decides whether a routing flip is a numerical tie) and gradient digests.

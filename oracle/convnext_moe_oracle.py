@@ -61,6 +61,8 @@ class OracleConfig:
     layer_scale_init_value: float = 1e-6
     eps: float = 1e-6
     multi_input: bool = True   # ConvNeXt_moe_MultiInput (stem conv under dataset_stems.single)
+    da: bool = False           # ConvNeXt_DA_MultiInput (convnext_moe_DA.py): a DALayer gates every block's branch per dataset
+    da_reduction: int = 16     # DALayer(channel, reduction=16) :296
 
     @property
     def depths(self):
@@ -128,6 +130,12 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, tuple]:
                 sh[p + 'ffn.pointwise_conv1.bias'] = (4 * c,)
                 sh[p + 'ffn.pointwise_conv2.weight'] = (c, 4 * c)
                 sh[p + 'ffn.pointwise_conv2.bias'] = (c,)
+            if cfg.da:
+                # DALayer.fc = ModuleList([Sequential(...)] * 3) (convnext_moe_DA.py:299-304): ONE Sequential registered three
+                # times, so the state_dict lists the same two weights under fc.0 / fc.1 / fc.2
+                for m in range(3):
+                    sh[p + f'DA.fc.{m}.0.weight'] = (c // cfg.da_reduction, c)
+                    sh[p + f'DA.fc.{m}.2.weight'] = (c, c // cfg.da_reduction)
         if i in cfg.out_indices:
             sh[f'norm{i}.weight'] = (c,)
             sh[f'norm{i}.bias'] = (c,)
@@ -273,9 +281,38 @@ def drop_path(x, rate, train, mask=None):
     return x * mask
 
 
+DA_INDEX = {'sar': 0, 'rgb': 1, 'ifr': 2}      # DALayer.dataset_DA, convnext_moe_DA.py:305
+
+
+def tie_da_weights(sd):
+    """The three DALayer.fc entries are one module in the reference: make fc.1 / fc.2 the same tensors as fc.0 (what
+    load_state_dict leaves behind is the LAST entry's values, so fc.2 wins).  Returns sd (modified in place)."""
+    for k in list(sd):
+        if '.DA.fc.2.' in k:
+            sd[k.replace('.DA.fc.2.', '.DA.fc.0.')] = sd[k]
+            sd[k.replace('.DA.fc.2.', '.DA.fc.1.')] = sd[k]
+    return sd
+
+
+def da_layer(x, sd, p, datasets):
+    """DALayer.forward convnext_moe_DA.py:307-319: squeeze (global average pool) -> Linear/ReLU/Linear/Sigmoid chosen by the
+    sample's dataset -> channel-wise scale.  One dataset name = the whole batch; otherwise one name per sample."""
+    b, c = x.shape[:2]
+    y = F.adaptive_avg_pool2d(x, 1).view(b, c)
+
+    def fc(m, v):
+        return torch.sigmoid(F.linear(F.relu(F.linear(v, sd[p + f'fc.{m}.0.weight'])), sd[p + f'fc.{m}.2.weight']))
+    if len(datasets) == 1:
+        s = fc(DA_INDEX[datasets[0]], y).view(b, c, 1, 1)
+    else:
+        s = torch.cat([fc(DA_INDEX[d], row.view(1, c)) for row, d in zip(y, datasets)], dim=1).view(b, c, 1, 1)
+    return x * s.expand_as(x)
+
+
 def convnext_block(x, sd, p, cfg: OracleConfig, is_moe: bool, dpr: float, train: bool,
-                   noise=None, dp_mask=None, record=None, pre_gamma=None):
-    """ConvNeXtBlock._inner_forward :343-372 (linear_pw_conv=True path)."""
+                   noise=None, dp_mask=None, record=None, pre_gamma=None, datasets=None):
+    """ConvNeXtBlock._inner_forward :343-372 (linear_pw_conv=True path); with cfg.da the DA variant
+    convnext_moe_DA.py:374-403 (the branch is gated by DALayer before drop_path and the shortcut)."""
     shortcut = x
     C = x.shape[1]
     x = F.conv2d(x, sd[p + 'depthwise_conv.weight'], sd[p + 'depthwise_conv.bias'], padding=3,
@@ -292,6 +329,8 @@ def convnext_block(x, sd, p, cfg: OracleConfig, is_moe: bool, dpr: float, train:
     x = x.permute(0, 3, 1, 2)
     if cfg.layer_scale_init_value > 0:
         x = x.mul(sd[p + 'gamma'].view(1, -1, 1, 1))
+    if cfg.da:
+        x = da_layer(x, sd, p + 'DA.', datasets)                           # convnext_moe_DA.py:400
     x = shortcut + drop_path(x, dpr, train, dp_mask)
     return x, loss
 
@@ -300,7 +339,7 @@ def backbone_forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, x, train: b
                      noise: Optional[List[torch.Tensor]] = None,
                      dp_masks: Optional[List[torch.Tensor]] = None,
                      record: Optional[list] = None, pre_gamma: Optional[list] = None,
-                     forced_idx: Optional[List[torch.Tensor]] = None):
+                     forced_idx: Optional[List[torch.Tensor]] = None, datasets: Optional[Sequence[str]] = None):
     """ConvNeXt_moe.forward :582-600 / ConvNeXt_moe_MultiInput.forward :794-820.
 
     ``forced_idx`` (test-only): per MoE layer, in forward order, a [T,k] index tensor that replaces the layer's own
@@ -312,12 +351,12 @@ def backbone_forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, x, train: b
     global _FORCE
     _FORCE = None if forced_idx is None else iter(forced_idx)
     try:
-        return _backbone_forward(sd, cfg, x, train, noise, dp_masks, record, pre_gamma)
+        return _backbone_forward(sd, cfg, x, train, noise, dp_masks, record, pre_gamma, datasets)
     finally:
         _FORCE = None
 
 
-def _backbone_forward(sd, cfg, x, train, noise, dp_masks, record, pre_gamma):
+def _backbone_forward(sd, cfg, x, train, noise, dp_masks, record, pre_gamma, datasets=None):
     if isinstance(x, (list, tuple)):
         x = torch.cat(list(x), dim=0)
     C, depths = cfg.channels, cfg.depths
@@ -346,7 +385,7 @@ def _backbone_forward(sd, cfg, x, train, noise, dp_masks, record, pre_gamma):
             if is_moe and noise is not None:
                 nz = noise[moe_i]
             x, loss = convnext_block(x, sd, f'stages.{i}.{j}.', cfg, is_moe, dpr[blk], train, nz,
-                                     None if dp_masks is None else dp_masks[blk], record, pre_gamma)
+                                     None if dp_masks is None else dp_masks[blk], record, pre_gamma, datasets)
             if is_moe:
                 moe_i += 1
             if loss is not None:

@@ -13,7 +13,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ref_shim                                   # noqa: E402
 from oracle.cases import CASES, make_noise, summarize_grad, upstream_grads   # noqa: E402
-from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes  # noqa: E402
+from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes, tie_da_weights  # noqa: E402
 from sm3det_b200.synth import make_images, make_state_dict, state_dict_checksum    # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
@@ -44,27 +44,40 @@ def moe_digest(r, full):
 
 def run_case(name, spec):
     kw = dict(spec['kw'])
-    cfg = OracleConfig(**kw)
-    net = ref_shim.build_reference_backbone('ConvNeXt_moe_MultiInput', seed=0, **kw)
+    da = bool(spec.get('da', False))
+    datasets = spec.get('datasets')
+    cfg = OracleConfig(da=da, **kw)
+    if da:
+        net = ref_shim.build_reference_backbone('ConvNeXt_DA_MultiInput', seed=0, module='convnext_moe_DA', **kw)
+    else:
+        net = ref_shim.build_reference_backbone('ConvNeXt_moe_MultiInput', seed=0, **kw)
+    call = (lambda inp: net(inp, datasets)) if da else net
+    okw = dict(datasets=datasets) if da else {}
     shapes = param_shapes(cfg)
     rsd = net.state_dict()
     assert set(shapes) == set(rsd), set(shapes) ^ set(rsd)
     for k, s in shapes.items():
         assert tuple(rsd[k].shape) == tuple(s), k
     sd = make_state_dict(shapes, seed=0, trained_like=(spec['weights'] == 'trained'))
+    if da:
+        tie_da_weights(sd)                      # the reference registers ONE Sequential three times (fc.2's values survive a load)
     net.load_state_dict(sd, strict=True)
     n, h, w = spec['img']
     x = make_images(n, h, w, seed=1234)
     mode = spec['mode']
     gold = dict(name=name, kw=kw, img=spec['img'], mode=mode, weights=spec['weights'],
                 sd_checksum=state_dict_checksum(sd), x_checksum=float(x.double().abs().sum()))
+    if da:
+        gold.update(da=True, datasets=list(datasets))
+        if len(datasets) > 1:
+            x = [x[i:i + 1] for i in range(n)]      # the detector passes one tensor per modality (trisource detector :141-153)
     record = []
     st = spec['stride']
     if mode == 'eval':
         net.eval()
         with torch.no_grad():
-            ref = net(x)
-            orc = backbone_forward(sd, cfg, x, train=False, record=record)
+            ref = call(x)
+            orc = backbone_forward(sd, cfg, x, train=False, record=record, **okw)
     else:
         net.train()
         noise = None
@@ -74,13 +87,15 @@ def run_case(name, spec):
             orig = torch.randn_like
             torch.randn_like = lambda t, *a, **k: next(it).to(t.dtype)   # inject the noise stream
         try:
-            ref = net(x)
+            ref = call(x)
         finally:
             if mode == 'train_noisy':
                 torch.randn_like = orig
         sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'ffn.mean' not in k and 'ffn.std' not in k else v)
                for k, v in sd.items()}
-        orc = backbone_forward(sdg, cfg, x, train=True, noise=noise, record=record)
+        if da:
+            tie_da_weights(sdg)
+        orc = backbone_forward(sdg, cfg, x, train=True, noise=noise, record=record, **okw)
     has_loss = isinstance(ref, tuple) and len(ref) == 2 and isinstance(ref[0], tuple)
     r_outs, r_loss = (ref if has_loss else (ref, None))
     o_outs, o_loss = (orc if has_loss else (orc, None))

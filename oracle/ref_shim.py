@@ -166,9 +166,9 @@ def load_reference_module(name="convnext_moe", package="backbones"):
     return mod
 
 
-def build_reference_backbone(cls_name="ConvNeXt_moe_MultiInput", seed=0, **kwargs):
+def build_reference_backbone(cls_name="ConvNeXt_moe_MultiInput", seed=0, module="convnext_moe", **kwargs):
     """Construct the reference class under a fixed seed (it never calls init_weights())."""
-    mod = load_reference_module("convnext_moe")
+    mod = load_reference_module(module)
     torch.manual_seed(seed)
     net = getattr(mod, cls_name)(**kwargs)
     return net

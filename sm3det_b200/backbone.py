@@ -173,7 +173,10 @@ class ConvNeXtBlock(nn.Module):
 
     def forward(self, x, record=None):
         """x: NHWC fp32.  Returns (x, loss) like the reference block (:343-379); loss is None if dense."""
-        rs = self._row_scale(x)
+        return self._run(x, self._row_scale(x), record, True)
+
+    def _run(self, x, rs, record, shortcut):
+        """shortcut=False returns the branch rs * gamma * ffn(norm(dwconv(x))) without the residual add (ConvNeXt_DA)."""
         eps = self.norm.eps
         dw = self.depthwise_conv
         grad = torch.is_grad_enabled()
@@ -192,6 +195,7 @@ class ConvNeXtBlock(nn.Module):
             if grad:
                 packs['w1_t'] = pc.get('w1', [w1], True)
             packs['grad'] = grad
+            packs['shortcut'] = shortcut
             out = Fn.DenseBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias,
                                         w1, f.pointwise_conv1.bias, w2, f.pointwise_conv2.bias, self.gamma, rs, eps, packs)
             return out, None
@@ -210,6 +214,8 @@ class ConvNeXtBlock(nn.Module):
         epc = getattr(self, '_ep', None)
         if epc is not None:
             # expert parallel (sm3det_b200.expert_parallel): this rank only packs / runs the experts it owns
+            if not shortcut:
+                raise NotImplementedError('sm3det_b200: expert parallelism is not wired for the ConvNeXt_DA blocks')
             from .expert_parallel import EPMoEBlockFn
             El = E // epc.world
             o1, o2 = w1s[epc.rank * El:(epc.rank + 1) * El], w2s[epc.rank * El:(epc.rank + 1) * El]
@@ -226,15 +232,55 @@ class ConvNeXtBlock(nn.Module):
             packs['w1_t'] = pc.get('w1', w1s, True)
             packs['w2_t'] = pc.get('w2', w2s, True)
             packs['wp_t'] = pc.get('wp', [g.cosine_projector.weight], True)
+        packs['shortcut'] = shortcut
         out, loss = Fn.MoEBlockFn.apply(x, dw.weight, dw.bias, self.norm.weight, self.norm.bias, self.gamma,
                                         g.cosine_projector.weight, g.cosine_projector.bias, g.sim_matrix, g.temperature,
                                         m.w_noise, rs, noise, eps, E, m.k, record, packs, *ep)
         return out, loss
 
 
+class DALayer(nn.Module):
+    """Per-dataset squeeze-and-excitation gate (convnext_moe_DA.py:295-319).  The module tree repeats the reference's:
+    ``fc`` is a ModuleList holding the SAME Sequential three times (`[...] * 3`, :299-304), so the state_dict lists one pair
+    of weights under fc.0 / fc.1 / fc.2 and the three datasets share them."""
+    dataset_DA = {'sar': 0, 'rgb': 1, 'ifr': 2}
+
+    def __init__(self, channel, reduction=16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.ModuleList([nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(inplace=True),
+                                               nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())] * 3)
+
+    def gate(self, m, datasets):
+        """m: [N, C] per-sample means of the branch -> [N, C] gates.  [N,C]-sized glue in torch (fp32 also under autocast)."""
+        with torch.autocast('cuda', enabled=False):
+            if len(datasets) == 1:
+                return self.fc[self.dataset_DA[datasets[0]]](m)
+            if len(datasets) != m.shape[0]:
+                raise ValueError(f'ConvNeXt_DA: {len(datasets)} dataset names for a batch of {m.shape[0]} (the reference zips them '
+                                 f'sample by sample, convnext_moe_DA.py:315-318)')
+            return torch.cat([self.fc[self.dataset_DA[d]](row.view(1, -1)) for row, d in zip(m, datasets)], dim=0)
+
+
+class ConvNeXtDABlock(ConvNeXtBlock):
+    """ConvNeXtBlock whose branch is gated by a DALayer before drop-path and the shortcut (convnext_moe_DA.py:372-403)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)            # unused by the reference's forward too (:368); no parameters
+        self.DA = DALayer(self.gamma.shape[0])
+
+    def forward(self, x, record=None, datasets=('rgb',)):
+        rs = self._row_scale(x)
+        y, loss = self._run(x, None, record, False)        # gamma * ffn(norm(dwconv(x))), NHWC
+        s = self.DA.gate(Fn.SampleMeanFn.apply(y), list(datasets))
+        return Fn.DAGateFn.apply(y, x, s, rs), loss
+
+
 @ROTATED_BACKBONES.register_module()
 class ConvNeXt_moe(BaseModule):
     arch_settings = ARCH_SETTINGS
+    block_cls = ConvNeXtBlock
 
     def __init__(self, arch='tiny', in_channels=3, stem_patch_size=4, norm_cfg=dict(type='LN2d', eps=1e-6),
                  act_cfg=dict(type='GELU'), linear_pw_conv=True, use_grn=False, drop_path_rate=0.,
@@ -300,7 +346,7 @@ class ConvNeXt_moe(BaseModule):
                     nn.Conv2d(self.channels[i - 1], channels, kernel_size=2, stride=2)))
             moe_ind = [list(range(depth))[q] for q in self.MoE_Block_inds[i] if q < depth]
             stage = nn.Sequential(*[
-                ConvNeXtBlock(in_channels=channels, drop_path_rate=dpr[block_idx + j], norm_cfg=norm_cfg,
+                self.block_cls(in_channels=channels, drop_path_rate=dpr[block_idx + j], norm_cfg=norm_cfg,
                               MoE_cfg={'noisy_gating': noisy_gating, 'num_experts': num_experts, 'top_k': top_k,
                                        'gating': gate} if j in moe_ind else None,
                               layer_scale_init_value=layer_scale_init_value) for j in range(depth)])
@@ -320,14 +366,14 @@ class ConvNeXt_moe(BaseModule):
         conv, ln = self.downsample_layers[0][0], self.downsample_layers[0][1]
         return Fn.StemFn.apply(x, conv.weight, conv.bias, ln.weight, ln.bias, ln.eps, self.stem_patch_size)
 
-    def _trunk(self, x, record=None):
+    def _trunk(self, x, record=None, datasets=None):
         outs, gate_losses = [], []
         for i, stage in enumerate(self.stages):
             if i >= 1:
                 ln, conv = self.downsample_layers[i][0], self.downsample_layers[i][1]
                 x = Fn.DownsampleFn.apply(x, ln.weight, ln.bias, conv.weight, conv.bias, ln.eps)
             for blk in stage:
-                x, gate_loss = blk(x, record)
+                x, gate_loss = blk(x, record) if datasets is None else blk(x, record, datasets)
                 if gate_loss is not None:
                     gate_losses.append(gate_loss)
             if i in self.out_indices:
@@ -468,3 +514,35 @@ class ConvNeXt_moe_MultiInput(ConvNeXt_moe):
         self._check_input(x)
         with self._precision():
             return self._trunk(self._stem(x), record)
+
+
+@ROTATED_BACKBONES.register_module()
+class ConvNeXt_DA_MultiInput(ConvNeXt_moe_MultiInput):
+    """convnext_moe_DA.py:762-860 (local_configs/main_DA_convnext_t_orcnn_gfl.py): ConvNeXt_moe_MultiInput whose every block
+    carries a DALayer; `forward(x, datasets)` hands the dataset names to the blocks -- one name for the whole batch, or one
+    name per sample (the detector passes one image per modality)."""
+    block_cls = ConvNeXtDABlock
+
+    def __init__(self, *args, datasets=None, **kwargs):
+        super().__init__(*args, datasets=datasets, **kwargs)
+        if datasets is not None and list(datasets) != ['single']:
+            raise NotImplementedError('sm3det_b200: per-dataset stems (datasets=[...]) are not implemented; the reference forward '
+                                      "only ever uses dataset_stems['single'] (convnext_moe_DA.py:836)")
+        self.init_datasets = datasets
+
+    def forward(self, x, datasets=['single'], record=None):
+        if len(datasets) == 1:
+            x = [x]
+        x = torch.cat(list(x), dim=0)
+        self._check_input(x)
+        with self._precision():
+            return self._trunk(self._stem(x), record, list(datasets))
+
+    def init_weights(self):
+        super().init_weights()
+        cfg = self.init_cfg
+        if isinstance(cfg, dict) and cfg.get('type') == 'Pretrained':
+            for stage in self.stages:                      # :935-941: the gates start at sigmoid(0) = 0.5
+                for blk in stage:
+                    for m in range(3):
+                        nn.init.constant_(blk.DA.fc[m][2].weight, 0.0)

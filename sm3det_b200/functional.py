@@ -172,13 +172,16 @@ class DenseBlockFn(Function):
         # says whether a backward can follow (it also chose which weight images to provide on that basis)
         train = any(ctx.needs_input_grad) and packs.get('grad', True)
         fused = packs.get('fused')
+        # packs['shortcut'] = False: return the branch gamma * ffn(...) alone (ConvNeXt_DA gates it before the shortcut add)
+        ctx.shortcut = packs.get('shortcut', True)
+        resid = x.view(T, C) if ctx.shortcut else None
         if fused is not None:
             # LayerNorm writes the FFN's A-operand image directly (the separate split pass never exists); the fused kernel
             # keeps the hidden tensor on chip and, when a backward follows, stores the pre-activation h once for it
             u = ops.dwconv7(x, _taps(dww), dwb)
             v_img, v, stats = ops.layernorm_fwd_img(u, lnw, lnb, eps, tokens=T, C=C, save_stats=train, want_f32=train)
             res = ops.ffn_fused_fwd(v_img, packs['w1_c'][0], packs['w2_n'][0], b1, b2, T=T, C=C, chunk=fused['fwd'],
-                                    gamma=gamma, row_scale=row_scale, resid=x.view(T, C), want_aux=train, want_h=train)
+                                    gamma=gamma, row_scale=row_scale, resid=resid, want_aux=train, want_h=train)
             if train:
                 ctx.save_for_backward(x, u, stats, v, res[2], res[1], dww, lnw, w1, w2, gamma, row_scale)
                 ctx.packs = packs
@@ -189,9 +192,10 @@ class DenseBlockFn(Function):
         h = ops.linear_fwd(v, w1, b1, packed=packs.get('w1'))
         a_k, _, _ = ops.act_pack(h, rows=T, width=4 * C, mode=ops.ACT_GELU, want_k=True)
         y2 = torch.empty((T, C), device=x.device, dtype=torch.float32) if train else None
-        epi = EPI_COLSCALE | EPI_RESID | (EPI_ROWSCALE if row_scale is not None else 0) | (EPI_AUXSTORE if train else 0)
+        epi = (EPI_COLSCALE | (EPI_RESID if resid is not None else 0) | (EPI_ROWSCALE if row_scale is not None else 0)
+               | (EPI_AUXSTORE if train else 0))
         out = ops.linear_fwd(None, w2, b2, rows=T, a_packed=a_k, epilogue=epi, aux_out=y2, col_scale=gamma,
-                             row_scale=row_scale, resid=x.view(T, C), packed=packs.get('w2'))
+                             row_scale=row_scale, resid=resid, packed=packs.get('w2'))
         if train:
             ctx.save_for_backward(x, u, stats, v, h, y2, dww, lnw, w1, w2, gamma, row_scale)
             ctx.packs = packs
@@ -229,7 +233,7 @@ class DenseBlockFn(Function):
         dw1 = torch.zeros_like(w1)
         ops.linear_wgrad(None, v, dw1, rows=T, dy_packed=dh_mn)
         dv = ops.linear_dgrad(None, w1, rows=T, a_packed=dh_k, packed=ctx.packs.get('w1_t'))
-        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
+        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout if ctx.shortcut else None, x, u, stats, dww, lnw)
         return dx, ddww, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma, None, None, None
 
 
@@ -271,8 +275,9 @@ class MoEBlockFn(Function):
         a_k, _, _ = ops.act_pack(h, rows=R, width=4 * C, mode=ops.ACT_GELU, want_k=True, live_tiles=plan['num_m_tiles'])
         o = ops.linear_fwd(None, w2s[0], b2s[0], rows=R, a_packed=a_k, grouped=grouped, w_group_stride=4 * C * C,
                            bias_group_stride=C, packed=packs.get('w2'))
-        out, y = ops.moe_combine(o, slot_of, r['top_idx'], r['top_gate'], gamma, x.view(T, C), row_scale, T=T, Cc=C,
-                                 k=k, want_y=record is not None)
+        ctx.shortcut = packs.get('shortcut', True)
+        out, y = ops.moe_combine(o, slot_of, r['top_idx'], r['top_gate'], gamma, x.view(T, C) if ctx.shortcut else None,
+                                 row_scale, T=T, Cc=C, k=k, want_y=record is not None)
         if record is not None:
             record.append(dict(v=v, top_idx=r['top_idx'], top_gate=r['top_gate'], importance=plan['importance'],
                                load=plan['load'], loss=plan['loss'], y=y, counts=plan['counts']))
@@ -345,10 +350,65 @@ class MoEBlockFn(Function):
             dwn = dwn_t[:E].t().contiguous()
             dv_r = ops.linear_dgrad(dr, wn_t, epilogue=EPI_RESID, resid=dv_r)
         dv = ops.gather_sum(dxp, slot_of, dv_r, T=T, Cc=C, k=k)
-        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout, x, u, stats, dww, lnw)
+        dx, ddww, ddwb, dlnw, dlnb = _block_front_bwd(dv, dout if ctx.shortcut else None, x, u, stats, dww, lnw)
         if dwn is None and ctx.has_noise_param:
             dwn = torch.zeros((C, E), device=dev, dtype=torch.float32)
         grads_e = [dw1s[e] for e in range(E)] + [db1s[e] for e in range(E)] + [dw2s[e] for e in range(E)] + \
                   [db2s[e] for e in range(E)]
         return (dx, ddww, ddwb, dlnw, dlnb, dgamma, dwp, dbp, dsim, dtau, dwn, None, None, None, None, None, None, None,
                 *grads_e)
+
+
+@ops.captures_precision
+class DAGateFn(Function):
+    """ConvNeXt_DA block tail (convnext_moe_DA.py:400-401): out = shortcut + row_scale * s[n, c] * y  with y the gamma-scaled
+    FFN branch [N,H,W,C] and s = DALayer's per-sample channel gate [N,C]; also returns nothing else -- the squeeze
+    (per-sample mean of y) is SampleMeanFn.  Per sample one `affine` launch (N is the per-GPU batch)."""
+
+    @staticmethod
+    def forward(ctx, y, x, s, row_scale):
+        N, H, W, C = y.shape
+        y, x = y.contiguous(), x.contiguous()
+        hw = H * W
+        out = torch.empty_like(x)
+        # per-sample scale vector: s[n] (* the sample's drop-path factor: row_scale is constant over a sample's tokens)
+        sc = s if row_scale is None else s * row_scale.view(N, hw)[:, :1]
+        sc = sc.contiguous()
+        for n in range(N):
+            ops.affine(y[n].view(hw, C), a1=sc[n], add=x[n].view(hw, C), out=out[n].view(hw, C))
+        ctx.save_for_backward(y, sc, s, row_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        y, sc, s, rs = ctx.saved_tensors
+        N, H, W, C = y.shape
+        hw = H * W
+        d = d.contiguous()
+        dy = torch.empty_like(y)
+        dsc = torch.zeros((N, C), device=y.device, dtype=torch.float32)
+        for n in range(N):
+            ops.affine(d[n].view(hw, C), a1=sc[n], out=dy[n].view(hw, C))
+            ops.colsum(d[n].view(hw, C), dsc[n], rows=hw, Cc=C, b=y[n].view(hw, C))       # sum_hw d * y
+        ds = dsc if rs is None else dsc * rs.view(N, hw)[:, :1]
+        return dy, d, ds, None
+
+
+@ops.captures_precision
+class SampleMeanFn(Function):
+    """DALayer's squeeze: AdaptiveAvgPool2d(1) over an NHWC tensor -> [N, C]."""
+
+    @staticmethod
+    def forward(ctx, y):
+        N, H, W, C = y.shape
+        y = y.contiguous()
+        m = torch.zeros((N, C), device=y.device, dtype=torch.float32)
+        for n in range(N):
+            ops.colsum(y[n].view(H * W, C), m[n], rows=H * W, Cc=C)
+        ctx.shape = (N, H, W, C)
+        return m / float(H * W)
+
+    @staticmethod
+    def backward(ctx, dm):
+        N, H, W, C = ctx.shape
+        return (dm / float(H * W)).view(N, 1, 1, C).expand(N, H, W, C).contiguous()

@@ -22,7 +22,7 @@ The oracle itself is pinned bit-for-bit to the unmodified reference by oracle/ge
 import torch
 
 from oracle.cases import make_noise, upstream_grads
-from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes
+from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes, tie_da_weights
 from oracle.gen_golden import moe_token_counts
 from sm3det_b200.synth import make_images, make_state_dict
 
@@ -38,10 +38,13 @@ def rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
-def build(kw, weights='trained', seed=0, cls=None):
-    from sm3det_b200 import ConvNeXt_moe_MultiInput
-    cfg = OracleConfig(**kw)
+def build(kw, weights='trained', seed=0, cls=None, da=False):
+    from sm3det_b200 import ConvNeXt_DA_MultiInput, ConvNeXt_moe_MultiInput
+    cfg = OracleConfig(da=da, **kw)
     sd = make_state_dict(param_shapes(cfg), seed, weights == 'trained')
+    if da:
+        tie_da_weights(sd)                     # the reference shares one Sequential between the three dataset gates
+        cls = cls or ConvNeXt_DA_MultiInput
     net = (cls or ConvNeXt_moe_MultiInput)(**kw)
     net.load_state_dict(sd, strict=True)
     return cfg, sd, net.cuda()
@@ -77,13 +80,21 @@ def assert_flips_are_near_ties(rec_gpu, ref_layers, what=''):
     return total
 
 
-def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backward=None, check_pre_gamma=True):
+def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backward=None, check_pre_gamma=True, datasets=None):
     """Full comparison of the CUDA backbone with the (teacher-forced) oracle, and with ``gold`` when given.
     Returns a dict of the measured errors (printed by the callers)."""
     kw = dict(kw)
-    cfg, sd, net = build(kw, weights)
+    da = datasets is not None              # ConvNeXt_DA_MultiInput: `datasets` names the DALayer gate per batch / per sample
+    cfg, sd, net = build(kw, weights, da=da)
     n, h, w = img
     x = make_images(n, h, w, seed=img_seed)
+    okw, gkw = {}, {}
+    xg = x.cuda()
+    if da:
+        okw, gkw = dict(datasets=list(datasets)), dict(datasets=list(datasets))
+        if len(datasets) > 1:
+            x = [x[i:i + 1] for i in range(n)]
+            xg = [t.cuda() for t in x]
     train = mode != 'eval'
     noisy = mode == 'train_noisy'
     if backward is None:
@@ -96,7 +107,7 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
             m._injected_noise = nz
     rec_g = []
     with torch.set_grad_enabled(backward):
-        res_g = net(x.cuda(), record=rec_g)
+        res_g = net(xg, record=rec_g, **gkw)
     has_loss = isinstance(res_g, tuple) and len(res_g) == 2 and isinstance(res_g[0], tuple)
     og, lg = res_g if has_loss else (res_g, None)
 
@@ -105,10 +116,12 @@ def run_case(kw, img, mode, weights='trained', gold=None, img_seed=1234, backwar
     rec_c, pre_c = [], []
     if backward:
         sdo = {k: (v.clone().requires_grad_(True) if 'ffn.mean' not in k and 'ffn.std' not in k else v) for k, v in sd.items()}
+        if da:
+            tie_da_weights(sdo)
     else:
         sdo = sd
     with torch.set_grad_enabled(backward):
-        res_c = backbone_forward(sdo, cfg, x, train=train, noise=noise, record=rec_c, pre_gamma=pre_c, forced_idx=forced)
+        res_c = backbone_forward(sdo, cfg, x, train=train, noise=noise, record=rec_c, pre_gamma=pre_c, forced_idx=forced, **okw)
     oc, lc = res_c if has_loss else (res_c, None)
     # (2) per layer: the CUDA choice vs the oracle's own top-k on the same (forced-upstream) inputs -- ties only
     flips = 0

@@ -18,12 +18,12 @@ CONV_GOLDENS = sorted(p for p in glob.glob(os.path.join(GOLD, '*.pt')) if not os
 
 @pytest.mark.parametrize('path', CONV_GOLDENS, ids=lambda p: os.path.basename(p)[:-3])
 def test_matches_reference_golden(path):
-    """Every ConvNeXt fixture (small ones and the full-size cfg2 / shipped-k3 / cfg4 shapes): routing vs the reference's
+    """Every ConvNeXt fixture (small ones, the ConvNeXt_DA ones and the full-size cfg2 / shipped-k3 / cfg4 shapes): routing vs the reference's
     (flips must be numerical ties), then outputs / loss / pre-gamma MoE outputs / every gradient vs the teacher-forced
     oracle on all elements, plus the fixture values themselves when no token flipped.  No assertion is conditional on
     the number of flips (see parity_util)."""
     gold = torch.load(path, weights_only=False)
-    errs = run_case(gold['kw'], gold['img'], gold['mode'], gold['weights'], gold=gold)
+    errs = run_case(gold['kw'], gold['img'], gold['mode'], gold['weights'], gold=gold, datasets=gold.get('datasets'))
     print(os.path.basename(path), errs)
 
 

@@ -61,6 +61,28 @@ def test_state_dict_layout_matches_reference(kw, multi):
         assert sorted(n for n, _ in net.named_parameters()) == sorted(n for n, _ in ref.named_parameters())
 
 
+def test_convnext_da_state_dict_and_shared_gate_weights():
+    """ConvNeXt_DA_MultiInput (convnext_moe_DA.py): same keys, order and parameter names as the reference, including its quirk
+    of ONE gate MLP registered under fc.0 / fc.1 / fc.2; the literal config dict of local_configs/main_DA_*.py builds."""
+    from oracle import ref_shim
+    from oracle.convnext_moe_oracle import OracleConfig, param_shapes
+    from sm3det_b200 import build_backbone
+    kw = dict(arch='tiny', drop_path_rate=0.1, datasets=None)
+    net = build_backbone(dict(type='ConvNeXt_DA_MultiInput', **kw))
+    okw = {k: v for k, v in kw.items() if k != 'datasets'}
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == param_shapes(OracleConfig(da=True, **okw))
+    da = net.stages[0][0].DA
+    assert da.fc[0] is da.fc[1] is da.fc[2]
+    names = [n for n, _ in net.named_parameters()]
+    assert 'stages.0.0.DA.fc.0.0.weight' in names and 'stages.0.0.DA.fc.1.0.weight' not in names      # de-duplicated like the reference
+    if ref_shim.reference_available():
+        ref = ref_shim.build_reference_backbone('ConvNeXt_DA_MultiInput', module='convnext_moe_DA', **kw)
+        assert list(net.state_dict()) == list(ref.state_dict())
+        assert names == [n for n, _ in ref.named_parameters()]
+    with pytest.raises(NotImplementedError):
+        build_backbone(dict(type='ConvNeXt_DA_MultiInput', arch='tiny', datasets=['sar', 'rgb', 'ifr']))
+
+
 def test_registry_builds_literal_sm3det_config_dicts():
     """The backbone dicts of configs/SM3Det/SM3Det_convnext_{t,b}.py, verbatim (minus init_cfg's checkpoint)."""
     from sm3det_b200 import ROTATED_BACKBONES, build_backbone

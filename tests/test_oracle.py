@@ -8,7 +8,7 @@ import torch
 
 from oracle import ref_shim
 from oracle.cases import CASES, make_noise, summarize_grad, upstream_grads
-from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes
+from oracle.convnext_moe_oracle import OracleConfig, backbone_forward, param_shapes, tie_da_weights
 from oracle.gen_golden import moe_token_counts
 from sm3det_b200.synth import make_images, make_state_dict, state_dict_checksum
 
@@ -17,19 +17,28 @@ GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
 def _run_oracle(gold, record):
     kw = gold['kw']
-    cfg = OracleConfig(**kw)
+    da = bool(gold.get('da'))
+    cfg = OracleConfig(da=da, **kw)
     sd = make_state_dict(param_shapes(cfg), 0, gold['weights'] == 'trained')
+    okw = {}
+    if da:
+        tie_da_weights(sd)
+        okw = dict(datasets=gold['datasets'])
     assert abs(state_dict_checksum(sd) - gold['sd_checksum']) <= 1e-9 * abs(gold['sd_checksum']), 'weight RNG drift'
     n, h, w = gold['img']
     x = make_images(n, h, w, seed=1234)
     assert abs(float(x.double().abs().sum()) - gold['x_checksum']) <= 1e-9 * gold['x_checksum'], 'image RNG drift'
     mode = gold['mode']
+    if da and len(gold['datasets']) > 1:
+        x = [x[i:i + 1] for i in range(n)]
     if mode == 'eval':
         with torch.no_grad():
-            return cfg, sd, backbone_forward(sd, cfg, x, train=False, record=record)
+            return cfg, sd, backbone_forward(sd, cfg, x, train=False, record=record, **okw)
     noise = make_noise(cfg, moe_token_counts(cfg, n, h, w)) if mode == 'train_noisy' else None
     sdg = {k: (v.clone().requires_grad_(True) if 'ffn.mean' not in k and 'ffn.std' not in k else v) for k, v in sd.items()}
-    return cfg, sdg, backbone_forward(sdg, cfg, x, train=True, noise=noise, record=record)
+    if da:
+        tie_da_weights(sdg)
+    return cfg, sdg, backbone_forward(sdg, cfg, x, train=True, noise=noise, record=record, **okw)
 
 
 @pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, '*.pt')) if not os.path.basename(p).startswith(('lsk_', 'van_'))), ids=lambda p: os.path.basename(p)[:-3])
