@@ -587,7 +587,7 @@ def run_ours(args):
                 'gpu_launches': launches, 'peak_mem_gb': peak_mem, 'roofline': roof, 'roofline_moe': roof_moe}
         line['cuda_graph'] = graph_note
         if world > 1:
-            line['config']['grad_sync'] = 'one flat all-reduce at the end of the step' if flat_sync else 'DDP bucket hooks'
+            line['grad_sync'] = 'one flat all-reduce at the end of the step' if flat_sync else 'DDP bucket hooks'
         if args.no_grad_sync:
             line['diagnostic'] = 'gradients NOT all-reduced (--no-grad-sync): not a valid training step, comm-cost isolation only'
         if os.environ.get('SM3_RESERVE_SMS'):

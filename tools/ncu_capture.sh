@@ -8,7 +8,7 @@ for spec in "$@"; do
   k=${spec%%:*}; r=${spec#*:}; s=${r%%:*}; c=${r#*:}
   name=${tag}_$(echo $k | tr -c 'A-Za-z0-9_\n' '_')_$s
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip $s --launch-count $c \
-      -f -o gpurun_out/$name python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/$name.log 2>&1
+      -f -o gpurun_out/$name python bench.py --steps 1 --warmup 0 --global-batch 8 --cuda-graph off --no-cpu-baseline --no-gpu-eager > gpurun_out/$name.log 2>&1
   if [ -f gpurun_out/$name.ncu-rep ]; then
     python profiles/summarize_ncu.py gpurun_out/$name.ncu-rep > gpurun_out/$name.txt 2>&1
     rm -f gpurun_out/$name.ncu-rep
