@@ -108,7 +108,7 @@ LSK_CASES = {
 
 # BASELINE config 5 at its real widths (configs/SM3Det/SM3Det_lsk_s.py:14-25).  Batch 2, not 1: at batch size 1 torch 2.11's
 # CPU autograd returns gradients for this op sequence that disagree with finite differences of its own forward (the
-# unmodified reference and the oracle alike -- tools/fd_check_lsk_oracle.py), so batch-1 gradient fixtures would pin a
+# unmodified reference and the oracle alike -- tests/diag/fd_check_lsk_oracle.py), so batch-1 gradient fixtures would pin a
 # framework artefact.  Forward outputs are unaffected.
 LSK_S_KW = dict(embed_dims=[64, 128, 320, 512], depths=[2, 2, 4, 2], MoE_Block_inds_fc1=[[], [0], [0, 2], [0]],
                 MoE_Block_inds_fc2=[[], [0], [0, 2], [0]], num_experts=4, top_k=2)

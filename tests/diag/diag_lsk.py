@@ -1,18 +1,18 @@
 #!/usr/bin/env python
 """Diagnostic (GPU box): LSKNet-MoE CUDA backbone vs the live CPU oracle for config variants; prints the worst gradient
-error per top-level module group, in forward order.  usage: python tools/diag_lsk.py [size]"""
+error per top-level module group, in forward order.  usage: python tests/diag/diag_lsk.py [size]"""
 import os
 import sys
 from collections import OrderedDict
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.cases import lsk_injections, upstream_grads          # noqa: E402
 from oracle.lsk_moe_oracle import LskConfig, lsk_backbone_forward, lsk_param_shapes   # noqa: E402
 from sm3det_b200 import LSKNet_moe_MultiInput                               # noqa: E402
 from sm3det_b200.synth import make_images, make_state_dict                  # noqa: E402
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'tests'))
 from test_lsk_gpu import inject                                             # noqa: E402
 
 

@@ -10,11 +10,15 @@ central finite differences of the same float64 forward, while at batch size 2 th
     n=1 patch_embed2.norm.weight(9,):         FD -2.106801e-01  autograd +7.772075e-01
 
 Every individual op passes torch.autograd.gradcheck at N = 1, so this is a framework problem of the composite graph, not of
-the reference's math.  The CUDA path agrees with the finite differences (tools/diag_lsk.py on the GPU box), so the LSKNet
+the reference's math.  The CUDA path agrees with the finite differences (tests/diag/diag_lsk.py on the GPU box), so the LSKNet
 full-size fixtures are generated with batch 2 (oracle/cases.py) -- config 5 runs 4 images per GPU anyway.
 """
-import sys, torch, torch.nn.functional as F
-sys.path.insert(0, '/root/repo')
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.cases import upstream_grads
 from oracle.lsk_moe_oracle import LskConfig, lsk_backbone_forward, lsk_param_shapes
 from sm3det_b200.synth import make_images, make_state_dict

@@ -13,7 +13,7 @@ and reports, against the unmodified fp32 oracle: max-norm relative error of the 
 and the largest (k)-vs-(k+1) logit gap among the flipped tokens (a flip with a large gap is a real routing change, not a
 numerical tie), and the worst parameter-gradient error.  Test infrastructure: imports oracle/, never the product.
 
-    python tools/precision_study.py [--size 1024] [--modes tf32_trunc,tf32_rn,bf16,bf16x3] > profiles/r02_precision_study.txt
+    python tests/diag/precision_study.py [--size 1024] [--modes tf32_trunc,tf32_rn,bf16,bf16x3] > profiles/r02_precision_study.txt
 """
 import argparse
 import os
@@ -23,7 +23,7 @@ import time
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import convnext_moe_oracle as O                      # noqa: E402
 from oracle.cases import CFG2_KW, upstream_grads                 # noqa: E402
 from sm3det_b200.synth import make_images, make_state_dict       # noqa: E402
