@@ -7,9 +7,11 @@
 One "step" = forward + backward of the backbone over the GLOBAL batch of synthetic 1024^2 tiles:
   t_e8  (default) BASELINE configs[1]/[2]: ConvNeXt-T, E = 8 top-2, MoE in the last two stages every other block.
         Global batch 32 at every N (the batch the metric is quoted on) -> strong scaling: 32 / 16 / 8 / 4 images per GPU at
-        N = 1 / 2 / 4 / 8, processed as micro-batches of <= 8 images with gradient accumulation (configs[1]'s bs = 8 is the
-        micro-batch; `--global-batch 8` is configs[1] literally).  N > 1: one process per GPU (torchrun),
-        DistributedDataParallel over NCCL, one gradient all-reduce per step.
+        N = 1 / 2 / 4 / 8, each GPU's share in ONE forward/backward pass (61 GB of activations at 32 images; `--micro-batch 8`
+        splits it with gradient accumulation, measured 4 % slower; `--global-batch 8` is configs[1] literally).  N > 1: one
+        process per GPU (torchrun), one flat gradient all-reduce per step over NCCL, captured in the step's CUDA graph
+        (`--cuda-graph off` = eager launches under DistributedDataParallel).  Gating is the reference constructor's default
+        (noisy top-k while training); `--noisy-gating off` = deterministic routing.
   b_e16 BASELINE configs[3]: ConvNeXt-B, E = 16, all 36 blocks MoE; experts sharded over the ranks when N > 1.
   lsk_s BASELINE configs[4]: LSKNet-S MoE, SyncBN, global batch 16 (4 GPUs -> 4 per GPU).
 The timed region is bracketed by barrier + synchronize and the max over ranks is reported.  `--impl reference` times the
@@ -32,8 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = 'backbone images/sec @1024^2 (fwd+bwd)'
+NOISY_DEFAULT = 'config'
 CONFIGS = {
-    't_e8': dict(family='convnext', global_batch=32, micro=8,
+    't_e8': dict(family='convnext', global_batch=32, micro=32,
                  kw=dict(arch='tiny', MoE_Block_inds=[[], [], [0, 2, 4, 6, 8], [0, 2]], num_experts=8, top_k=2,
                          noisy_gating=False, drop_path_rate=0.0),
                  name='SM3Det ConvNeXt-T e8t2 last-2-blocks MoE backbone (BASELINE configs[1]/[2])'),
@@ -67,6 +70,9 @@ def parse():
                     help='N > 1: shard the experts over the ranks (NVLink peer-memory dispatch); default for --config b_e16')
     ap.add_argument('--no-expert-parallel', action='store_true')
     ap.add_argument('--cpu-images', type=int, default=1, help='images in the bounded CPU sample')
+    ap.add_argument('--noisy-gating', choices=['config', 'off'], default=NOISY_DEFAULT,
+                    help="ConvNeXt configs: 'config' = the reference constructor's default (noisy top-k gating while training, "
+                         "what configs/SM3Det/*.py run), 'off' = deterministic routing")
     ap.add_argument('--cuda-graph', choices=['auto', 'on', 'off'], default='auto',
                     help='capture the whole step (fwd+bwd over all micro-batches, gradient all-reduce included) in a CUDA graph; '
                          'auto = on except for AMP and expert parallelism')
@@ -76,6 +82,9 @@ def parse():
     ap.add_argument('--no-grad-sync', action='store_true',
                     help='DIAGNOSTIC, N > 1: never all-reduce gradients (isolates the exposed cost of the DDP collective)')
     a = ap.parse_args()
+    for c in CONFIGS.values():            # applies to both arms (ours and --impl reference) and to the oracle baselines
+        if c['family'] == 'convnext':
+            c['kw']['noisy_gating'] = a.noisy_gating == 'config'
     return a
 
 
@@ -103,6 +112,7 @@ def workload_config(args, world):
     return {'workload': f'{c["name"]}, fwd+bwd, global batch {per * world} = {per}/GPU x {world} GPU in micro-batches of '
                         f'{micro}, {args.size}x{args.size}x3 synthetic SAR/RGB/IR 2:1:1, fp32',
             'config': args.config, 'num_experts': kw['num_experts'], 'top_k': kw['top_k'],
+            'noisy_gating': bool(kw.get('noisy_gating', True)),
             'per_gpu_batch': per, 'micro_batch': micro, 'global_batch': per * world, 'image': args.size,
             'parallelism': f'dp{world}' + ('+ep' if ep else ''),
             'l2': 'inputs and activations exceed L2 (>= 100 MB per tensor); no flush needed'}
@@ -541,6 +551,9 @@ def run_ours(args):
     if ep:
         net._ep_ctx.check()                      # expert-side capacity was never exceeded (reads a device flag; off the clock)
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    grad_l1 = None
+    if graphed is not None:       # the last replay's gradients are still in .grad: a checksum to cross-check micro-batch splits
+        grad_l1 = float(sum(p.grad.double().abs().sum() for p in net.parameters() if p.grad is not None))
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     t = torch.tensor([ms, ms_e2e], device='cuda', dtype=torch.float64)
     if world > 1:
@@ -586,6 +599,8 @@ def run_ours(args):
                         'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
                 'gpu_launches': launches, 'peak_mem_gb': peak_mem, 'roofline': roof, 'roofline_moe': roof_moe}
         line['cuda_graph'] = graph_note
+        line['grad_l1'] = grad_l1
+        line['step_scalar'] = acc / max(args.steps, 1)      # mean of the per-step result read back in the e2e loop (sanity cross-check)
         if world > 1:
             line['grad_sync'] = 'one flat all-reduce at the end of the step' if flat_sync else 'DDP bucket hooks'
         if args.no_grad_sync:
@@ -593,10 +608,13 @@ def run_ours(args):
         if os.environ.get('SM3_RESERVE_SMS'):
             line['config']['reserved_sms_for_nccl'] = int(os.environ['SM3_RESERVE_SMS'])
         if world == 1 and not args.no_gpu_eager:
+            graphed = None                       # release the step graph's memory pool before the comparator allocates
             del model, net
+            import gc
+            gc.collect()
             torch.cuda.empty_cache()
             try:
-                line['gpu_eager'] = time_gpu_eager(args, MB)
+                line['gpu_eager'] = time_gpu_eager(args, min(MB, 8))
                 line['gpu_eager']['ours_over_eager_fp32'] = line['value'] / line['gpu_eager']['fp32']
                 line['gpu_eager']['ours_over_eager_tf32'] = line['value'] / line['gpu_eager']['tf32']
             except Exception as e:                      # a comparator failure must not lose the bench line
