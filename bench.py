@@ -231,6 +231,7 @@ def time_gpu_eager(args, micro):
     CUDA events like tools/analysis_tools/benchmark.py:118-146.  Not the product: the number our kernels have to beat."""
     from sm3det_b200.synth import make_images
     fwd, sd = oracle_model(args.config)
+    torch.cuda.reset_peak_memory_stats()
     sd = {k: v.cuda() for k, v in sd.items()}
     x = make_images(micro, args.size, args.size, seed=1234).cuda()
     out = {'kind': 'oracle port (the reference\'s torch ops) in eager PyTorch on cuda:0', 'micro_batch': micro, 'unit': 'img/s'}
