@@ -38,11 +38,11 @@ NOISY_DEFAULT = 'config'
 CONFIGS = {
     't_e8': dict(family='convnext', global_batch=32, micro=32,
                  kw=dict(arch='tiny', MoE_Block_inds=[[], [], [0, 2, 4, 6, 8], [0, 2]], num_experts=8, top_k=2,
-                         noisy_gating=False, drop_path_rate=0.0),
+                         noisy_gating=True, drop_path_rate=0.0),
                  name='SM3Det ConvNeXt-T e8t2 last-2-blocks MoE backbone (BASELINE configs[1]/[2])'),
     'b_e16': dict(family='convnext', global_batch=8, micro=2,
                   kw=dict(arch='base', MoE_Block_inds=[[0, 1, 2], [0, 1, 2], list(range(27)), [0, 1, 2]], num_experts=16,
-                          top_k=2, noisy_gating=False, drop_path_rate=0.0),
+                          top_k=2, noisy_gating=True, drop_path_rate=0.0),
                   name='SM3Det ConvNeXt-B e16t2 all-blocks MoE backbone (BASELINE configs[3])'),
     'lsk_s': dict(family='lsk', global_batch=16, micro=4,
                   kw=dict(MoE_Block_inds_fc1=[[], [0], [0, 2], [0]], MoE_Block_inds_fc2=[[], [0], [0, 2], [0]], num_experts=4,

@@ -196,3 +196,30 @@ def test_ep_expert_layout_host_plan():
     assert off[0] == [0, 5] and off[2] == [0, 130] and off[3] == [0, 1]
     assert rows == [128, 384 + 384]                     # e3: 301 rows -> 3 tiles
     assert tiles[0] == [0] and tiles[1] == [0, 0, 0, 1, 1, 1]
+
+
+def test_bench_resolves_the_named_configs():
+    """bench.py: the global batch of the named config is kept at every N (strong scaling), each GPU's share is one pass unless
+    --micro-batch splits it, cfg4 turns expert parallelism on at N > 1, --batch switches to weak scaling."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def ns(**kw):
+        d = dict(config='t_e8', batch=None, global_batch=None, micro_batch=None, no_expert_parallel=False, expert_parallel=False, size=1024)
+        d.update(kw)
+        return argparse.Namespace(**d)
+    for world, per in ((1, 32), (2, 16), (4, 8), (8, 4)):
+        c, p, micro, scaling, ep = bench.resolve(ns(), world)
+        assert (p, micro, scaling, ep) == (per, per, 'strong', False)
+    assert bench.resolve(ns(micro_batch=8), 1)[1:3] == (32, 8)
+    assert bench.resolve(ns(micro_batch=5), 1)[2] == 4                      # largest divisor of the share not above the request
+    assert bench.resolve(ns(batch=8), 4)[1:4] == (8, 8, 'weak')
+    assert bench.resolve(ns(config='b_e16'), 8)[4] is True and bench.resolve(ns(config='b_e16'), 1)[4] is False
+    assert bench.resolve(ns(config='lsk_s'), 4)[1:3] == (4, 4)
+    with pytest.raises(SystemExit):
+        bench.resolve(ns(global_batch=30), 8)
+    cfg = bench.workload_config(ns(), 8)
+    assert cfg['global_batch'] == 32 and cfg['per_gpu_batch'] == 4 and cfg['parallelism'] == 'dp8' and cfg['noisy_gating'] is True
