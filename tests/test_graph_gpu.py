@@ -48,7 +48,7 @@ def test_graphed_convnext_moe_step_matches_eager():
         now = grads(net)
         assert set(now) == set(gr)
         worst = max((rel(now[k], gr[k]) / (5.0 if k.endswith('temperature') else 1.0), k) for k in gr if float(gr[k].abs().max()) > 1e-8)
-        assert worst[0] < 1e-4, worst             # atomics reorder sums; nothing else differs between the two launch modes
+        assert worst[0] < 3e-4, worst             # atomics reorder sums; nothing else differs between the two launch modes
     # an optimizer-style in-place weight update between replays is honoured (operand images are re-split inside the graph)
     with torch.no_grad():
         for p in net.parameters():
@@ -93,4 +93,4 @@ def test_graphed_lsk_step_draws_fresh_noise_and_dropout_masks():
     now = grads(net)
     # (w_gate.temperature: a scalar sum over all tokens with heavy cancellation; atomics reorder it between runs)
     worst = max((rel(now[k], gr[k]) / (5.0 if k.endswith('temperature') else 1.0), k) for k in gr if float(gr[k].abs().max()) > 1e-8)
-    assert worst[0] < 2e-4, worst
+    assert worst[0] < 5e-4, worst
